@@ -1,0 +1,192 @@
+/*
+ * sldm_sage.h -- C-ABI of the B200-native SageBlock hot path (libsldm_sage.so).
+ *
+ * This is the drop-in boundary of the repo.  Every entry point takes plain
+ * pointers and sizes (no torch types) and launches hand-written sm_100a CUDA
+ * kernels on the stream it is given; nothing here synchronises the host unless
+ * the comment on the function says so.  The Python host (sldm_gnn_b200/) binds
+ * these with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * What each group replaces in the reference (paths relative to the reference
+ * checkout; PyG = torch-geometric 2.7.0, pinned in uv.lock:1406-1407):
+ *
+ *   sldm_csr_*            the implicit "index by edge_index[1]" of PyG
+ *                         utils/_scatter.py::scatter as called from
+ *                         src/models/blocks/sageblock.py:18 (conv(x, edge_index));
+ *                         edge_index contract: src/models/grusage.py:153,182 and
+ *                         src/gbuilder.py:88-112 (int64 [2,E], row 0 = source,
+ *                         row 1 = destination).
+ *   sldm_segment_mean     MessagePassing.propagate + MeanAggregation
+ *                         (x.index_select(0, edge_index[0]) then
+ *                         scatter(reduce='mean') by edge_index[1]).
+ *   sldm_sage_project_*   SAGEConv.forward's lin_l(agg) + lin_r(x) followed by
+ *                         posts[i] = LayerNorm -> LeakyReLU|ReLU
+ *                         (src/models/blocks/sageblock.py:10-14,18-19).
+ *   sldm_sage_layer_*     one whole iteration of the loop at
+ *                         src/models/blocks/sageblock.py:17-19 (dropout excluded:
+ *                         it stays torch's), forward and backward.
+ *   sldm_sage_block_*_host  the whole SageBlock.forward
+ *                         (src/models/blocks/sageblock.py:16-20) for hosts that
+ *                         own no device memory: host buffers in, host buffers out.
+ *
+ * Conventions
+ *   - all feature matrices are row-major fp32, contiguous; weights are
+ *     [Fout, Fin] row-major exactly as torch.nn.Linear / PyG Linear store them;
+ *   - all pointers are DEVICE pointers unless the name ends in _host / _h;
+ *   - return value: SLDM_OK or an SLDM_E* code; sldm_last_error() gives the
+ *     message for the calling thread;
+ *   - sldm_stream_t is a cudaStream_t passed as void* (0 = legacy default);
+ *   - indices: the CSR object is int32 (N and E must be < 2^31 - 2^20).
+ */
+#ifndef SLDM_SAGE_H_
+#define SLDM_SAGE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLDM_ABI_VERSION 1
+
+#define SLDM_OK            0
+#define SLDM_EINVAL        1  /* bad argument value (Python host: ValueError)   */
+#define SLDM_ESHAPE        2  /* inconsistent sizes (Python host: RuntimeError) */
+#define SLDM_ECUDA         3  /* CUDA runtime / launch failure                  */
+#define SLDM_EWORKSPACE    4  /* workspace too small                            */
+#define SLDM_EUNSUPPORTED  5  /* size outside what the kernels cover            */
+#define SLDM_ENODEVICE     6  /* no CUDA device: there is no CPU fallback       */
+
+typedef void* sldm_stream_t;
+
+/* ---- library ------------------------------------------------------------ */
+int         sldm_abi_version(void);
+const char* sldm_last_error(void);
+/* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
+int64_t     sldm_launch_count(void);
+/* number of SMs of the current device (host sync-free after the first call) */
+int         sldm_device_sm_count(int* out_sms);
+
+/* ---- CSR object ----------------------------------------------------------
+ * One int32 device buffer holding, at the offsets sldm_csr_layout() reports:
+ *   meta[64]         [0] hub chunks (by dst)  [1] hub chunks (by src)
+ *                    [2] 1 if any index was outside [0,N)   (then clamped)
+ *                    [3] 1 if edge_index[0] is NOT non-decreasing
+ *                    [4] 1 if edge_index[1] is NOT non-decreasing
+ *   rowptr_dst[N+1]  in-edges of node i are col_src[rowptr_dst[i]..rowptr_dst[i+1])
+ *   col_src[E]       source ids, STABLE in edge order inside every segment
+ *   rowptr_src[N+1]  out-edges (transpose CSR, used by backward)
+ *   col_dst[E]       destination ids, stable in edge order inside every segment
+ *   hub_dst[cap*4]   work list {row, chunk, nchunks, first_slot} for rows whose
+ *   hub_src[cap*4]   degree exceeds SLDM_HUB_DEGREE (split deterministically)
+ * Bit-exact contract: rowptr == cumsum(bincount(idx, N)), col == other[argsort(idx, stable)].
+ */
+#define SLDM_HUB_DEGREE 256   /* rows with more in-edges than this are split   */
+#define SLDM_HUB_CHUNK  2048  /* edges per split piece                         */
+
+enum {
+  SLDM_CSR_META = 0, SLDM_CSR_ROWPTR_DST = 1, SLDM_CSR_COL_SRC = 2,
+  SLDM_CSR_ROWPTR_SRC = 3, SLDM_CSR_COL_DST = 4, SLDM_CSR_HUB_DST = 5,
+  SLDM_CSR_HUB_SRC = 6, SLDM_CSR_TOTAL = 7
+};
+/* offsets (in int32 elements) of the 7 sections; out8[SLDM_CSR_TOTAL] = total size */
+int     sldm_csr_layout(int64_t N, int64_t E, int64_t* out8);
+int64_t sldm_csr_workspace_bytes(int64_t N, int64_t E);
+/* edge_index: device int64 [2,E] contiguous.  Never written.  E == 0 is legal. */
+int     sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
+                       int32_t* csr, void* workspace, int64_t workspace_bytes,
+                       sldm_stream_t stream);
+
+/* ---- segment mean (the aggregation alone) --------------------------------
+ * out[i,:] = (sum over k in segment i of src[col[k],:]) / max(deg_i,1)   (mean=1)
+ * out[i,:] = addend[i,:] + sum ...                                       (mean=0)
+ * transpose=0 walks (rowptr_dst,col_src); transpose=1 walks (rowptr_src,col_dst).
+ * Summation inside a segment is sequential in edge order (== the CPU scatter_add_
+ * order of the reference) for rows of degree <= SLDM_HUB_DEGREE; hub rows are
+ * split in fixed pieces and recombined in piece order (deterministic).
+ */
+int64_t sldm_segment_workspace_bytes(int64_t N, int64_t E, int32_t F);
+int     sldm_segment_reduce(const float* src, int64_t N, int32_t F,
+                            const int32_t* csr, int64_t E, int32_t transpose,
+                            int32_t mean, const float* addend, float* out,
+                            void* workspace, int64_t workspace_bytes,
+                            sldm_stream_t stream);
+
+/* ---- projection + LayerNorm + activation ---------------------------------
+ * z = agg W_l^T + b_l + x W_r^T ; xhat = (z-mean)*rstd ; y = xhat*g+b ;
+ * out = y > 0 ? y : slope*y        (slope = 0 -> ReLU)
+ * xhat_out / rstd_out may be NULL (inference).
+ */
+int64_t sldm_sage_project_workspace_bytes(int64_t N, int32_t Fin, int32_t Fout);
+int     sldm_sage_project_forward(const float* agg, const float* x, int64_t N,
+                                  int32_t Fin, int32_t Fout,
+                                  const float* W_l, const float* b_l, const float* W_r,
+                                  const float* ln_w, const float* ln_b,
+                                  float eps, float slope,
+                                  float* out, float* xhat_out, float* rstd_out,
+                                  void* workspace, int64_t workspace_bytes,
+                                  sldm_stream_t stream);
+
+/* ---- one SageBlock layer --------------------------------------------------
+ * forward : agg = segment_mean(x); out = act(LN(agg W_l^T + b_l + x W_r^T))
+ *           agg is always written ([N,Fin]; it is the saved tensor in training
+ *           and scratch in inference); xhat/rstd only when non-NULL.
+ * backward: given dout = dL/dout, produces dx (may be NULL: not needed),
+ *           dW_l, db_l, dW_r, dln_w, dln_b (overwritten, not accumulated).
+ *           dz [N,Fout], dagg [N,Fin] and dxroot [N,Fin] are caller-provided
+ *           scratch (dagg/dxroot may be NULL iff dx is NULL).
+ */
+int64_t sldm_sage_layer_fwd_workspace_bytes(int64_t N, int64_t E, int32_t Fin, int32_t Fout);
+int     sldm_sage_layer_forward(const float* x, int64_t N, int32_t Fin, int32_t Fout,
+                                const int32_t* csr, int64_t E,
+                                const float* W_l, const float* b_l, const float* W_r,
+                                const float* ln_w, const float* ln_b,
+                                float eps, float slope,
+                                float* out, float* agg, float* xhat_out, float* rstd_out,
+                                void* workspace, int64_t workspace_bytes,
+                                sldm_stream_t stream);
+
+int64_t sldm_sage_layer_bwd_workspace_bytes(int64_t N, int64_t E, int32_t Fin, int32_t Fout);
+int     sldm_sage_layer_backward(const float* dout, const float* x, const float* agg,
+                                 const float* xhat, const float* rstd,
+                                 int64_t N, int32_t Fin, int32_t Fout,
+                                 const int32_t* csr, int64_t E,
+                                 const float* W_l, const float* W_r,
+                                 const float* ln_w, const float* ln_b, float slope,
+                                 float* dx, float* dW_l, float* db_l, float* dW_r,
+                                 float* dln_w, float* dln_b,
+                                 float* dz, float* dagg, float* dxroot,
+                                 void* workspace, int64_t workspace_bytes,
+                                 sldm_stream_t stream);
+
+/* ---- whole block, host buffers in / host buffers out -----------------------
+ * For hosts that own no device memory (the reference-side stub in
+ * INTEGRATION.md).  All pointers are HOST pointers.  Parameters of layer l are
+ * params_h[5*l + {0:W_l, 1:b_l, 2:W_r, 3:ln_w, 4:ln_b}].  hdims has L+1 entries.
+ * Copies inputs to the current device, builds the CSR, runs L layers, copies
+ * the result back and synchronises the stream before returning.
+ *   forward_host : out_h [N, hdims[L]]
+ *   train_host   : additionally takes dout_h [N, hdims[L]] and returns
+ *                  dx_h [N, hdims[0]] (may be NULL) and grads_h[5*l+k] laid out
+ *                  like params_h.
+ */
+int sldm_sage_block_forward_host(const float* x_h, const int64_t* edge_index_h,
+                                 int64_t N, int64_t E,
+                                 const int32_t* hdims, int32_t L,
+                                 const float* const* params_h,
+                                 float eps, float slope,
+                                 float* out_h);
+int sldm_sage_block_train_host(const float* x_h, const int64_t* edge_index_h,
+                               int64_t N, int64_t E,
+                               const int32_t* hdims, int32_t L,
+                               const float* const* params_h,
+                               float eps, float slope,
+                               const float* dout_h,
+                               float* out_h, float* dx_h, float* const* grads_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLDM_SAGE_H_ */

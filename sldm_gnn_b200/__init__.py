@@ -1,0 +1,15 @@
+"""B200-native SageBlock hot path of aledima00/sldm-gnn.
+
+    from sldm_gnn_b200 import SageBlock      # drop-in for src/models/blocks/sageblock.py
+
+Importing this package loads libsldm_sage.so (hand-written sm_100a CUDA behind a
+C-ABI, include/sldm_sage.h) and fails if it has not been built.  There is no CPU
+fallback.
+"""
+from . import _lib  # noqa: F401  (raises ImportError if the CUDA library is missing)
+from . import ops
+from .ops import Csr, build_csr, segment_reduce
+from .sageblock import SageBlock, SageConvParams
+from .shim import install_reference_shim
+
+__all__ = ["SageBlock", "SageConvParams", "Csr", "build_csr", "segment_reduce", "ops", "install_reference_shim"]

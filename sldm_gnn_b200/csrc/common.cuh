@@ -1,0 +1,107 @@
+// common.cuh -- shared helpers for the sm_100a SageBlock kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/sldm_sage.h"
+
+namespace sldm {
+
+// ---- error plumbing (thread-local message, C return codes) -----------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+void count_launch();  // every kernel launch of this library goes through SLDM_LAUNCH_CHECK
+
+#define SLDM_CUDA(expr)                                                \
+  do {                                                                 \
+    cudaError_t _e = (expr);                                           \
+    if (_e != cudaSuccess) return ::sldm::cuda_fail(_e, #expr);        \
+  } while (0)
+
+#define SLDM_LAUNCH_CHECK(name)                                        \
+  do {                                                                 \
+    ::sldm::count_launch();                                            \
+    cudaError_t _e = cudaGetLastError();                               \
+    if (_e != cudaSuccess) return ::sldm::cuda_fail(_e, name);         \
+  } while (0)
+
+#define SLDM_REQUIRE(cond, code, ...)                                  \
+  do {                                                                 \
+    if (!(cond)) { ::sldm::set_error(__VA_ARGS__); return (code); }    \
+  } while (0)
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <typename T>
+__host__ __device__ constexpr T round_up(T a, T b) { return ceil_div(a, b) * b; }
+
+// every section of a workspace / CSR object starts on a 256-byte boundary
+constexpr int64_t kAlignI32 = 64;
+inline int64_t align_i32(int64_t n) { return round_up<int64_t>(n, kAlignI32); }
+inline int64_t align_bytes(int64_t n) { return round_up<int64_t>(n, 256); }
+
+int num_sms();  // cached per process (current device at first call)
+
+// bump allocator over a caller-provided workspace
+struct Arena {
+  char* base; int64_t size; int64_t off;
+  Arena(void* p, int64_t n) : base(static_cast<char*>(p)), size(n), off(0) {}
+  template <typename T> T* take(int64_t count) {
+    int64_t bytes = align_bytes(count * (int64_t)sizeof(T));
+    if (off + bytes > size) { off = size + 1; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off); off += bytes; return r;
+  }
+  bool ok() const { return off <= size; }
+};
+
+// ---- CSR object views -------------------------------------------------------
+struct CsrLayout { int64_t off[8]; };
+CsrLayout csr_layout(int64_t N, int64_t E);
+inline int64_t hub_capacity(int64_t E) {
+  return E / SLDM_HUB_CHUNK + E / SLDM_HUB_DEGREE + 2;
+}
+
+// ---- internal launchers shared between translation units --------------------
+// exclusive scan of n int32 (in place allowed); spine must hold scan_spine_elems(n) ints
+int64_t scan_spine_elems(int64_t n);
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* spine, cudaStream_t s);
+
+int segment_reduce_launch(const float* src, int64_t N, int32_t F,
+                          const int32_t* rowptr, const int32_t* col,
+                          const int32_t* hub_list, const int32_t* hub_count, int64_t hub_cap,
+                          bool mean, const float* addend, float* out,
+                          float* partials, cudaStream_t s);
+
+int project_forward_launch(const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
+                           const float* W_l, const float* b_l, const float* W_r,
+                           const float* ln_w, const float* ln_b, float eps, float slope,
+                           float* out, float* xhat, float* rstd,
+                           void* ws, int64_t ws_bytes, cudaStream_t s);
+int64_t project_forward_ws_bytes(int64_t N, int32_t Fin, int32_t Fout);
+
+int layer_backward_launch(const float* dout, const float* x, const float* agg,
+                          const float* xhat, const float* rstd,
+                          int64_t N, int32_t Fin, int32_t Fout,
+                          const int32_t* rowptr_dst,
+                          const float* W_l, const float* W_r,
+                          const float* ln_w, const float* ln_b, float slope,
+                          bool need_dx,
+                          float* dW_l, float* db_l, float* dW_r, float* dln_w, float* dln_b,
+                          float* dz, float* dagg, float* dxroot,
+                          void* ws, int64_t ws_bytes, cudaStream_t s);
+int64_t layer_backward_ws_bytes(int64_t N, int32_t Fin, int32_t Fout);
+
+// ---- device helpers -----------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4add(float4& a, const float4& b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+
+}  // namespace sldm

@@ -1,0 +1,263 @@
+// segment_reduce.cu -- deterministic CSR segment mean / sum gather.
+//
+// Forward:  agg[i,:] = sum_{e: dst[e]=i} x[src[e],:] / max(deg_i,1)
+//   replaces x.index_select(0, edge_index[0]) + scatter(reduce='mean') of PyG 2.7.0
+//   (MessagePassing.propagate / MeanAggregation / utils/_scatter.py::scatter) as
+//   reached from src/models/blocks/sageblock.py:18.  No [E,F] intermediate, no atomics.
+// Backward: dx[j,:] = dxroot[j,:] + sum_{e: src[e]=j} dagg_scaled[dst[e],:]
+//   (the autograd of index_select + scatter_add_), over the transpose CSR.
+//
+// One group of LPR lanes owns one row; every lane holds VPL 128-bit (or 32-bit
+// on the unaligned path) slices of the row.  UNR source rows are in flight per
+// group at a time; the adds are issued in edge order, so a row of degree
+// <= SLDM_HUB_DEGREE is summed exactly like the reference's sequential CPU
+// scatter_add_.  Rows above that are cut into SLDM_HUB_CHUNK-edge pieces, each
+// summed by one CTA (fixed sub-ranges per group, fixed combine order) into a
+// partial slot, then recombined in piece order: deterministic, no atomics.
+//
+// Bound: HBM.  Algorithmic bytes per call = E*(F*4 + 4) + 4(N+1) + N*F*4 (+N*F*4 addend).
+#include "common.cuh"
+#include <algorithm>
+
+namespace sldm {
+
+template <typename VT> struct Vec;
+template <> struct Vec<float4> {
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ float4 ld(const float4* p) { return __ldg(p); }
+  static __device__ __forceinline__ void add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  static __device__ __forceinline__ float4 div(const float4& a, float c) {
+    return make_float4(__fdiv_rn(a.x, c), __fdiv_rn(a.y, c), __fdiv_rn(a.z, c), __fdiv_rn(a.w, c));
+  }
+};
+template <> struct Vec<float> {
+  static __device__ __forceinline__ float zero() { return 0.f; }
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void add(float& a, const float& b) { a += b; }
+  static __device__ __forceinline__ float div(const float& a, float c) { return __fdiv_rn(a, c); }
+};
+
+// fp32 count of the reference: scatter_add_ of ones saturates at 2^24, then clamp(min=1)
+__device__ __forceinline__ float ref_count(int deg) {
+  int c = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
+  return (float)c;
+}
+
+// acc[q] += sum over edges k in [beg,end) of src[col[k]][fv0 + lig + q*LPR], in edge order
+template <typename VT, int LPR, int VPL, int UNR>
+__device__ __forceinline__ void accumulate_range(const VT* __restrict__ src, int64_t FV, int fv0,
+                                                 const int32_t* __restrict__ col, int beg, int end,
+                                                 int lig, unsigned gmask, VT (&acc)[VPL]) {
+  bool act[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) act[q] = (int64_t)fv0 + lig + q * LPR < FV;
+  for (int k = beg; k < end; k += LPR) {
+    const int nk = min(LPR, end - k);
+    const int mycol = (lig < nk) ? __ldg(col + k + lig) : 0;
+    for (int j = 0; j < nk; j += UNR) {
+      VT v[UNR][VPL];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int c = __shfl_sync(gmask, mycol, j + u, LPR);
+        const bool ok = (j + u) < nk;
+        const VT* p = src + (int64_t)c * FV + fv0 + lig;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) v[u][q] = (ok && act[q]) ? Vec<VT>::ld(p + q * LPR) : Vec<VT>::zero();
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) Vec<VT>::add(acc[q], v[u][q]);
+      }
+    }
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  if constexpr (LPR == 32) {
+    return 0xffffffffu;
+  } else {
+    return ((1u << LPR) - 1u) << ((lane / LPR) * LPR);
+  }
+}
+
+template <typename VT, int LPR, int VPL, int UNR>
+__global__ void __launch_bounds__(256)
+k_segment_rows(const VT* __restrict__ src, int64_t FV,
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+               int64_t N, int mean, const VT* __restrict__ addend, VT* __restrict__ out) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lig = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int64_t row = warp * RPW + lane / LPR;
+  if (row >= N) return;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const int deg = end - beg;
+  if (deg > SLDM_HUB_DEGREE) return;  // split rows: k_segment_hub_*
+  const float cnt = ref_count(deg);
+  for (int64_t fv0 = 0; fv0 < FV; fv0 += LPR * VPL) {
+    VT acc[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = Vec<VT>::zero();
+    accumulate_range<VT, LPR, VPL, UNR>(src, FV, (int)fv0, col, beg, end, lig, gmask, acc);
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int64_t idx = fv0 + lig + q * LPR;
+      if (idx < FV) {
+        VT r = acc[q];
+        if (mean) r = Vec<VT>::div(r, cnt);
+        if (addend) { VT a = Vec<VT>::ld(addend + row * FV + idx); Vec<VT>::add(a, r); r = a; }
+        out[row * FV + idx] = r;
+      }
+    }
+  }
+}
+
+template <typename VT, int LPR, int VPL, int UNR>
+__global__ void __launch_bounds__(256)
+k_segment_hub_chunks(const VT* __restrict__ src, int64_t FV,
+                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const int4* __restrict__ hub_list, const int32_t* __restrict__ hub_count,
+                     int cap, VT* __restrict__ partials) {
+  constexpr int G = 256 / LPR;
+  constexpr int PER = SLDM_HUB_CHUNK / G;
+  __shared__ VT sm[G][LPR * VPL];
+  const int n = min(*hub_count, cap);
+  const int lane = threadIdx.x & 31;
+  const int g = threadIdx.x / LPR, lig = threadIdx.x % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  for (int c = blockIdx.x; c < n; c += gridDim.x) {
+    const int4 ent = hub_list[c];  // {row, chunk, nchunks, first}
+    const int rbeg = __ldg(rowptr + ent.x), rend = __ldg(rowptr + ent.x + 1);
+    const int cb = rbeg + ent.y * SLDM_HUB_CHUNK;
+    const int ce = min(rend, cb + SLDM_HUB_CHUNK);
+    const int b = min(ce, cb + g * PER), e = min(ce, b + PER);
+    for (int64_t fv0 = 0; fv0 < FV; fv0 += LPR * VPL) {
+      VT acc[VPL];
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) acc[q] = Vec<VT>::zero();
+      accumulate_range<VT, LPR, VPL, UNR>(src, FV, (int)fv0, col, b, e, lig, gmask, acc);
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) sm[g][lig + q * LPR] = acc[q];
+      __syncthreads();
+      if (threadIdx.x < LPR * VPL) {
+        const int64_t idx = fv0 + threadIdx.x;
+        if (idx < FV) {
+          VT s = sm[0][threadIdx.x];
+#pragma unroll 4
+          for (int gg = 1; gg < G; ++gg) Vec<VT>::add(s, sm[gg][threadIdx.x]);
+          partials[(int64_t)c * FV + idx] = s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename VT, int LPR>
+__global__ void __launch_bounds__(256)
+k_segment_hub_finalize(const VT* __restrict__ partials, int64_t FV,
+                       const int32_t* __restrict__ rowptr,
+                       const int4* __restrict__ hub_list, const int32_t* __restrict__ hub_count,
+                       int cap, int mean, const VT* __restrict__ addend, VT* __restrict__ out) {
+  const int n = min(*hub_count, cap);
+  const int64_t groups = (int64_t)gridDim.x * (256 / LPR);
+  const int lig = threadIdx.x % LPR;
+  for (int64_t c = (int64_t)blockIdx.x * (256 / LPR) + threadIdx.x / LPR; c < n; c += groups) {
+    const int4 ent = hub_list[c];
+    if (ent.y != 0) continue;
+    const int64_t row = ent.x;
+    const float cnt = ref_count(__ldg(rowptr + row + 1) - __ldg(rowptr + row));
+    for (int64_t idx = lig; idx < FV; idx += LPR) {
+      VT s = partials[c * FV + idx];
+      for (int j = 1; j < ent.z; ++j) Vec<VT>::add(s, partials[(c + j) * FV + idx]);
+      if (mean) s = Vec<VT>::div(s, cnt);
+      if (addend) { VT a = Vec<VT>::ld(addend + row * FV + idx); Vec<VT>::add(a, s); s = a; }
+      out[row * FV + idx] = s;
+    }
+  }
+}
+
+template <typename VT, int LPR, int VPL, int UNR>
+static int launch_all(const float* src, int64_t N, int64_t FV,
+                      const int32_t* rowptr, const int32_t* col,
+                      const int32_t* hub_list, const int32_t* hub_count, int64_t hub_cap,
+                      bool mean, const float* addend, float* out, float* partials, cudaStream_t s) {
+  constexpr int RPW = 32 / LPR;
+  const VT* vsrc = reinterpret_cast<const VT*>(src);
+  const VT* vadd = reinterpret_cast<const VT*>(addend);
+  VT* vout = reinterpret_cast<VT*>(out);
+  VT* vpart = reinterpret_cast<VT*>(partials);
+  const int64_t rows_per_cta = 8 * RPW;
+  const int64_t grid = ceil_div<int64_t>(N, rows_per_cta);
+  k_segment_rows<VT, LPR, VPL, UNR><<<(unsigned)grid, 256, 0, s>>>(vsrc, FV, rowptr, col, N, mean ? 1 : 0, vadd, vout);
+  SLDM_LAUNCH_CHECK("k_segment_rows");
+  if (hub_cap > 0 && hub_list != nullptr) {
+    const int cap = (int)hub_cap;
+    const int g1 = (int)std::min<int64_t>(hub_cap, (int64_t)num_sms() * 8);
+    k_segment_hub_chunks<VT, LPR, VPL, UNR><<<g1, 256, 0, s>>>(
+        vsrc, FV, rowptr, col, reinterpret_cast<const int4*>(hub_list), hub_count, cap, vpart);
+    SLDM_LAUNCH_CHECK("k_segment_hub_chunks");
+    const int g2 = (int)std::min<int64_t>(ceil_div<int64_t>(hub_cap, 256 / LPR), (int64_t)num_sms() * 4);
+    k_segment_hub_finalize<VT, LPR><<<g2, 256, 0, s>>>(
+        vpart, FV, rowptr, reinterpret_cast<const int4*>(hub_list), hub_count, cap, mean ? 1 : 0, vadd, vout);
+    SLDM_LAUNCH_CHECK("k_segment_hub_finalize");
+  }
+  return SLDM_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int segment_reduce_launch(const float* src, int64_t N, int32_t F,
+                          const int32_t* rowptr, const int32_t* col,
+                          const int32_t* hub_list, const int32_t* hub_count, int64_t hub_cap,
+                          bool mean, const float* addend, float* out,
+                          float* partials, cudaStream_t s) {
+  if (N == 0 || F == 0) return SLDM_OK;
+  const bool vec = (F % 4 == 0) && aligned16(src) && aligned16(out) && aligned16(addend) && aligned16(partials);
+  if (vec) {
+    const int64_t FV = F / 4;
+    if (FV <= 4)  return launch_all<float4, 4, 1, 8>(src, N, FV, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+    if (FV <= 8)  return launch_all<float4, 8, 1, 8>(src, N, FV, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+    if (FV <= 16) return launch_all<float4, 16, 1, 8>(src, N, FV, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+    if (FV <= 32) return launch_all<float4, 32, 1, 8>(src, N, FV, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+    return launch_all<float4, 32, 2, 4>(src, N, FV, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+  }
+  // unaligned / F % 4 != 0: same algorithm on 32-bit slices
+  if (F <= 32) return launch_all<float, 32, 1, 8>(src, N, F, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+  return launch_all<float, 32, 4, 4>(src, N, F, rowptr, col, hub_list, hub_count, hub_cap, mean, addend, out, partials, s);
+}
+
+}  // namespace sldm
+
+using namespace sldm;
+
+extern "C" int64_t sldm_segment_workspace_bytes(int64_t N, int64_t E, int32_t F) {
+  if (N < 0 || E < 0 || F < 0) return -1;
+  return align_bytes(hub_capacity(E) * (int64_t)F * 4);
+}
+
+extern "C" int sldm_segment_reduce(const float* src, int64_t N, int32_t F,
+                                   const int32_t* csr, int64_t E, int32_t transpose,
+                                   int32_t mean, const float* addend, float* out,
+                                   void* workspace, int64_t workspace_bytes,
+                                   sldm_stream_t stream) {
+  SLDM_REQUIRE(N >= 0 && E >= 0 && F >= 0, SLDM_EINVAL, "sldm_segment_reduce: negative size");
+  SLDM_REQUIRE(csr != nullptr, SLDM_EINVAL, "sldm_segment_reduce: csr is NULL");
+  SLDM_REQUIRE(N == 0 || F == 0 || (src != nullptr && out != nullptr), SLDM_EINVAL, "sldm_segment_reduce: NULL src/out");
+  const int64_t need = sldm_segment_workspace_bytes(N, E, F);
+  SLDM_REQUIRE(workspace_bytes >= need && (workspace != nullptr || need == 0), SLDM_EWORKSPACE,
+               "sldm_segment_reduce: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+  CsrLayout L = csr_layout(N, E);
+  const int32_t* meta = csr + L.off[SLDM_CSR_META];
+  const int32_t* rowptr = csr + L.off[transpose ? SLDM_CSR_ROWPTR_SRC : SLDM_CSR_ROWPTR_DST];
+  const int32_t* col = csr + L.off[transpose ? SLDM_CSR_COL_DST : SLDM_CSR_COL_SRC];
+  const int32_t* hub = csr + L.off[transpose ? SLDM_CSR_HUB_SRC : SLDM_CSR_HUB_DST];
+  return segment_reduce_launch(src, N, F, rowptr, col, E > SLDM_HUB_DEGREE ? hub : nullptr,
+                               meta + (transpose ? 1 : 0), E > SLDM_HUB_DEGREE ? hub_capacity(E) : 0,
+                               mean != 0, addend, out, static_cast<float*>(workspace),
+                               static_cast<cudaStream_t>(stream));
+}

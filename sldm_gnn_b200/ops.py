@@ -1,0 +1,167 @@
+"""Host-side wrappers over the C-ABI: torch owns device memory and streams, the
+library does the work.  Every function here launches on torch's current stream of
+the tensors' device and never synchronises the host.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"sldm_gnn_b200: `{name}` is on {t.device}; the SageBlock hot path is CUDA only "
+            "(sm_100a kernels, no CPU fallback)")
+
+
+def check_edge_index(edge_index) -> None:
+    """Same checks, same exception type as PyG 2.7.0 MessagePassing._check_input."""
+    if not isinstance(edge_index, torch.Tensor):
+        raise ValueError("`edge_index` must be a torch.Tensor of dtype torch.long and shape [2, num_edges]")
+    if edge_index.dtype != torch.long:
+        raise ValueError(f"Expected 'edge_index' to be of integer type (got '{edge_index.dtype}')")
+    if edge_index.dim() != 2:
+        raise ValueError(f"Expected 'edge_index' to be two-dimensional (got {edge_index.dim()} dimensions)")
+    if edge_index.size(0) != 2:
+        raise ValueError(f"Expected 'edge_index' to have size '2' in the first dimension (got '{edge_index.size(0)}')")
+
+
+class Csr:
+    """Device CSR object built from one edge_index (layout: include/sldm_sage.h)."""
+
+    __slots__ = ("buf", "N", "E", "layout", "device")
+
+    def __init__(self, buf, N, E, layout):
+        self.buf, self.N, self.E, self.layout, self.device = buf, N, E, layout, buf.device
+
+    def _view(self, name, n):
+        o = self.layout[name]
+        return self.buf[o:o + n]
+
+    @property
+    def meta(self): return self._view("meta", 64)
+    @property
+    def rowptr_dst(self): return self._view("rowptr_dst", self.N + 1)
+    @property
+    def col_src(self): return self._view("col_src", self.E)
+    @property
+    def rowptr_src(self): return self._view("rowptr_src", self.N + 1)
+    @property
+    def col_dst(self): return self._view("col_dst", self.E)
+
+    def status(self) -> dict:
+        """Host-synchronising read of the build flags (debug / tests)."""
+        m = self.meta[:5].cpu().tolist()
+        return {"hub_chunks_dst": m[0], "hub_chunks_src": m[1], "index_out_of_range": bool(m[2]),
+                "src_sorted": not m[3], "dst_sorted": not m[4]}
+
+
+def build_csr(edge_index: torch.Tensor, num_nodes: int) -> Csr:
+    check_edge_index(edge_index)
+    _require_cuda(edge_index, "edge_index")
+    ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+    E = int(ei.size(1))
+    N = int(num_nodes)
+    dev = ei.device
+    layout = _lib.csr_layout(N, E)
+    with torch.cuda.device(dev):
+        buf = torch.empty(layout["total"], dtype=torch.int32, device=dev)
+        wsb = int(lib.sldm_csr_workspace_bytes(N, E))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if E > 0 else None
+        check(lib.sldm_csr_build(_ptr(ei) if E > 0 else None, E, N, buf.data_ptr(), _ptr(ws), wsb if E > 0 else 0,
+                                 _stream(dev)))
+    return Csr(buf, N, E, layout)
+
+
+def segment_reduce(src: torch.Tensor, csr: Csr, *, transpose: bool = False, mean: bool = True,
+                   addend: torch.Tensor | None = None) -> torch.Tensor:
+    _require_cuda(src, "src")
+    src = src.contiguous()
+    N, F = src.shape
+    if N != csr.N:
+        raise RuntimeError(f"segment_reduce: src has {N} rows but the CSR was built for {csr.N} nodes")
+    dev = src.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(src)
+        wsb = int(lib.sldm_segment_workspace_bytes(N, csr.E, F))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        check(lib.sldm_segment_reduce(src.data_ptr(), N, F, csr.buf.data_ptr(), csr.E, int(transpose), int(mean),
+                                      _ptr(addend), out.data_ptr(), ws.data_ptr(), wsb, _stream(dev)))
+    return out
+
+
+def project_forward(agg, x, W_l, b_l, W_r, ln_w, ln_b, eps, slope, save: bool):
+    N, Fin = x.shape
+    Fout = W_l.shape[0]
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((N, Fout), dtype=torch.float32, device=dev)
+        xhat = torch.empty((N, Fout), dtype=torch.float32, device=dev) if save else None
+        rstd = torch.empty((N,), dtype=torch.float32, device=dev) if save else None
+        wsb = int(lib.sldm_sage_project_workspace_bytes(N, Fin, Fout))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        check(lib.sldm_sage_project_forward(agg.data_ptr(), x.data_ptr(), N, Fin, Fout, W_l.data_ptr(), b_l.data_ptr(),
+                                            W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), float(eps), float(slope),
+                                            out.data_ptr(), _ptr(xhat), _ptr(rstd), ws.data_ptr(), wsb, _stream(dev)))
+    return out, xhat, rstd
+
+
+def layer_forward(x, csr: Csr, W_l, b_l, W_r, ln_w, ln_b, eps: float, slope: float, save: bool):
+    """One SageBlock layer.  Returns (out, agg, xhat, rstd); xhat/rstd are None unless `save`."""
+    N, Fin = x.shape
+    Fout = W_l.shape[0]
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((N, Fout), dtype=torch.float32, device=dev)
+        agg = torch.empty((N, Fin), dtype=torch.float32, device=dev)
+        xhat = torch.empty((N, Fout), dtype=torch.float32, device=dev) if save else None
+        rstd = torch.empty((N,), dtype=torch.float32, device=dev) if save else None
+        wsb = int(lib.sldm_sage_layer_fwd_workspace_bytes(N, csr.E, Fin, Fout))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        check(lib.sldm_sage_layer_forward(x.data_ptr(), N, Fin, Fout, csr.buf.data_ptr(), csr.E,
+                                          W_l.data_ptr(), b_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(),
+                                          ln_b.data_ptr(), float(eps), float(slope),
+                                          out.data_ptr(), agg.data_ptr(), _ptr(xhat), _ptr(rstd),
+                                          ws.data_ptr(), wsb, _stream(dev)))
+    return out, agg, xhat, rstd
+
+
+def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slope: float, need_dx: bool):
+    """Returns (dx | None, dW_l, db_l, dW_r, dln_w, dln_b)."""
+    N, Fin = x.shape
+    Fout = W_l.shape[0]
+    dev = x.device
+    dout = dout.contiguous()
+    with torch.cuda.device(dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        dW_l = torch.empty((Fout, Fin), **f32)
+        dW_r = torch.empty((Fout, Fin), **f32)
+        db_l = torch.empty((Fout,), **f32)
+        dln_w = torch.empty((Fout,), **f32)
+        dln_b = torch.empty((Fout,), **f32)
+        dz = torch.empty((N, Fout), **f32)
+        dx = dagg = dxroot = None
+        if need_dx:
+            dx = torch.empty((N, Fin), **f32)
+            dagg = torch.empty((N, Fin), **f32)
+            dxroot = torch.empty((N, Fin), **f32)
+        wsb = int(lib.sldm_sage_layer_bwd_workspace_bytes(N, csr.E, Fin, Fout))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        check(lib.sldm_sage_layer_backward(dout.data_ptr(), x.data_ptr(), agg.data_ptr(), xhat.data_ptr(),
+                                           rstd.data_ptr(), N, Fin, Fout, csr.buf.data_ptr(), csr.E,
+                                           W_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                           float(slope), _ptr(dx), dW_l.data_ptr(), db_l.data_ptr(),
+                                           dW_r.data_ptr(), dln_w.data_ptr(), dln_b.data_ptr(),
+                                           dz.data_ptr(), _ptr(dagg), _ptr(dxroot), ws.data_ptr(), wsb, _stream(dev)))
+    return dx, dW_l, db_l, dW_r, dln_w, dln_b

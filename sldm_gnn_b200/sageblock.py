@@ -1,0 +1,146 @@
+"""Drop-in SageBlock (reference: src/models/blocks/sageblock.py:4-20).
+
+Same constructor, same forward(x, edge_index) (a third positional `batch` is accepted
+and ignored), same module tree and therefore the same state-dict keys:
+
+    convs.{i}.lin_l.weight [Fout,Fin]   convs.{i}.lin_l.bias [Fout]
+    convs.{i}.lin_r.weight [Fout,Fin]   (no lin_r.bias)
+    posts.{i}.0.weight [Fout]           posts.{i}.0.bias [Fout]
+
+so snapshots written by the reference's src/utils.py:22-30 load strictly
+(test.py:121-122, rcv.py:62-63).  The arithmetic is libsldm_sage.so: one CSR build
+per edge_index, then per layer a deterministic segment-mean gather and a fused
+projection + LayerNorm + activation kernel, with a hand-written backward.  Dropout
+stays torch's own (posts[i][2]) so RNG consumption is identical to the reference.
+CUDA only: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class _Linear(nn.Module):
+    """Parameter holder with the names / shapes / init of torch_geometric.nn.dense.Linear."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        # PyG: kaiming_uniform(a=sqrt(5), fan=in) == U(+-1/sqrt(in)); bias U(+-1/sqrt(in))
+        bound = 1.0 / math.sqrt(self.in_channels) if self.in_channels > 0 else 0.0
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                self.bias.uniform_(-bound, bound)
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, bias={self.bias is not None}"
+
+
+class SageConvParams(nn.Module):
+    """Stands where PyG's SAGEConv(in, out) stands in the module tree (lin_l, lin_r)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = _Linear(in_channels, out_channels, bias=True)
+        self.lin_r = _Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self) -> None:
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, aggr=mean"
+
+
+class _SageLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W_l, b_l, W_r, ln_w, ln_b, csr, eps, slope):
+        save = any(ctx.needs_input_grad[:6])
+        out, agg, xhat, rstd = ops.layer_forward(x, csr, W_l, b_l, W_r, ln_w, ln_b, eps, slope, save)
+        if save:
+            ctx.save_for_backward(x, agg, xhat, rstd, W_l, W_r, ln_w, ln_b)
+            ctx.csr, ctx.slope = csr, slope
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, agg, xhat, rstd, W_l, W_r, ln_w, ln_b = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
+            dout, x, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slope, need_dx)
+        return dx, dW_l, db_l, dW_r, dln_w, dln_b, None, None, None
+
+
+class SageBlock(nn.Module):
+    def __init__(self, hdims: list[int], dropout: float | None = None, negative_slope: float | None = None):
+        super().__init__()
+        assert len(hdims) >= 1, "hdims must contain at least one element"
+        self.convs = nn.ModuleList([SageConvParams(hdims[i], hdims[i + 1]) for i in range(len(hdims) - 1)])
+        self.posts = nn.ModuleList([
+            nn.Sequential(
+                nn.LayerNorm(hdims[i + 1]),
+                nn.LeakyReLU(negative_slope=negative_slope) if negative_slope is not None else nn.ReLU(),
+                nn.Dropout(p=dropout) if dropout is not None else nn.Identity(),
+            ) for i in range(len(hdims) - 1)
+        ])
+        self._csr_key = None   # (edge_index tensor kept alive, its version, num_nodes)
+        self._csr = None
+
+    # -- CSR cache: one entry, valid while the same tensor object is passed unmodified --------
+    def _get_csr(self, edge_index: torch.Tensor, num_nodes: int) -> ops.Csr:
+        try:
+            version = edge_index._version
+        except RuntimeError:  # inference tensors do not track versions: never cached
+            version = None
+        key = self._csr_key
+        if (version is not None and key is not None and key[0] is edge_index and key[1] == version
+                and key[2] == num_nodes):
+            return self._csr
+        csr = ops.build_csr(edge_index, num_nodes)
+        if version is not None:
+            self._csr_key, self._csr = (edge_index, version, num_nodes), csr
+        return csr
+
+    def clear_cache(self) -> None:
+        self._csr_key = self._csr = None
+
+    def forward(self, x, edge_index, batch=None):
+        if len(self.convs) == 0:
+            return x
+        ops.check_edge_index(edge_index)
+        if not isinstance(x, torch.Tensor) or x.dim() != 2:
+            raise RuntimeError("SageBlock: x must be a 2-D [num_nodes, features] tensor")
+        ops._require_cuda(x, "x")
+        ops._require_cuda(edge_index, "edge_index")
+        if edge_index.device != x.device:
+            raise RuntimeError(f"SageBlock: x is on {x.device} but edge_index is on {edge_index.device}")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"SageBlock: expected float32 features, got {x.dtype}")
+        if x.size(1) != self.convs[0].in_channels:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.size(0)}x{x.size(1)} and "
+                               f"{self.convs[0].in_channels}x{self.convs[0].out_channels})")
+        x = x.contiguous()
+        csr = self._get_csr(edge_index, x.size(0))
+        for conv, post in zip(self.convs, self.posts):
+            ln, act, drop = post[0], post[1], post[2]
+            slope = float(act.negative_slope) if isinstance(act, nn.LeakyReLU) else 0.0
+            if conv.lin_l.weight.device != x.device:
+                raise RuntimeError(f"SageBlock: parameters are on {conv.lin_l.weight.device} but x is on {x.device}")
+            x = _SageLayerFn.apply(x, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight,
+                                   ln.weight, ln.bias, csr, float(ln.eps), slope)
+            x = drop(x)
+        return x

@@ -1,0 +1,402 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and -- at full benchmark
+sizes -- through size-independent properties.
+
+Bars (BASELINE.json north_star): CSR / indexing bit exact; fp32 outputs and gradients
+within rtol 1e-5 / atol 1e-6 of the fp32 oracle.  Parameter gradients are sums over
+all N rows, so their atol is scaled by the gradient's own magnitude (the same relative
+bar); the fp64 C oracle adjudicates (our error must not exceed a small multiple of the
+fp32 oracle's own error against fp64).
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sldm_gnn_b200 as sg
+from sldm_gnn_b200 import _lib, ops
+from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+from oracle.sage_oracle import SageBlockOracle, SAGEConvOracle, csr_oracle
+from test_oracle import c_forward, c_backward
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def assert_close(got, want, what, scale_atol=False):
+    got, want = got.detach().cpu(), want.detach().cpu()
+    atol = ATOL * (max(1.0, float(want.abs().max())) if scale_atol else 1.0)
+    err = (got - want).abs()
+    bound = atol + RTOL * want.abs()
+    bad = err > bound
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err {float(err.max()):.3e}"
+
+
+def edge_cases(kind, N, E, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "random":
+        return torch.randint(0, N, (2, E), generator=g)
+    if kind == "sorted_src":
+        ei = torch.randint(0, N, (2, E), generator=g)
+        order = torch.sort(ei[0] * N + ei[1], stable=True).indices
+        return ei[:, order].contiguous()
+    if kind == "hub":  # 60% of the edges land on node 3, the rest uniform; node 5 is a source hub
+        ei = torch.randint(0, N, (2, E), generator=g)
+        m = torch.rand(E, generator=g) < 0.6
+        ei[1, m] = 3 % N
+        m2 = torch.rand(E, generator=g) < 0.3
+        ei[0, m2] = 5 % N
+        return ei
+    if kind == "dup_self":
+        ei = torch.randint(0, N, (2, E), generator=g)
+        ei[1, ::3] = ei[0, ::3]          # self loops
+        ei[:, 1::4] = ei[:, 0:1]         # many duplicates of edge 0
+        return ei
+    raise ValueError(kind)
+
+
+# ------------------------------------------------------------------------- CSR --
+@pytest.mark.parametrize("kind,N,E", [
+    ("random", 1, 0), ("random", 1, 5), ("random", 7, 3), ("random", 200, 1000), ("random", 257, 4097),
+    ("sorted_src", 6400, 32000), ("random", 70000, 300000), ("hub", 5000, 200000), ("dup_self", 300, 5000),
+    ("random", 100, 0), ("hub", 66000, 50000),
+])
+def test_csr_bit_exact(dev, kind, N, E):
+    ei = edge_cases(kind, N, E, seed=N + E)
+    csr = sg.build_csr(ei.to(dev), N)
+    want = csr_oracle(ei, N)
+    for name, g, w in zip(("rowptr_dst", "col_src", "rowptr_src", "col_dst"),
+                          (csr.rowptr_dst, csr.col_src, csr.rowptr_src, csr.col_dst), want):
+        assert g.dtype == torch.int32
+        assert torch.equal(g.cpu(), w), f"{name} differs ({kind}, N={N}, E={E})"
+    st = csr.status()
+    assert not st["index_out_of_range"]
+    assert st["src_sorted"] == bool((ei[0][1:] >= ei[0][:-1]).all())
+    assert st["dst_sorted"] == bool((ei[1][1:] >= ei[1][:-1]).all())
+    deg = (want[0][1:] - want[0][:-1])
+    hubs = deg[deg > _lib.HUB_DEGREE]
+    assert st["hub_chunks_dst"] == int(((hubs + _lib.HUB_CHUNK - 1) // _lib.HUB_CHUNK).sum())
+
+
+def test_csr_full_size_properties(dev):
+    """C4 shape (1M nodes, 10M skewed edges): checksum-of-checksums + sortedness instead of an oracle sort."""
+    N, E = 1_000_000, 10_000_000
+    ei = skewed_graph(N, E, seed=0).to(dev)
+    csr = sg.build_csr(ei, N)
+    rp = csr.rowptr_dst.long()
+    assert int(rp[0]) == 0 and int(rp[-1]) == E and bool((rp[1:] >= rp[:-1]).all())
+    assert torch.equal(rp[1:] - rp[:-1], torch.bincount(ei[1], minlength=N))
+    rs = csr.rowptr_src.long()
+    assert torch.equal(rs[1:] - rs[:-1], torch.bincount(ei[0], minlength=N))
+    # every (src,dst) pair survives: order-independent checksums
+    key = ei[0] * N + ei[1]
+    dst_of_slot = torch.repeat_interleave(torch.arange(N, device=dev), rp[1:] - rp[:-1])
+    key_csr = csr.col_src.long() * N + dst_of_slot
+    assert int(key.sum()) == int(key_csr.sum()) and int((key * key % 1000003).sum()) == int((key_csr * key_csr % 1000003).sum())
+    # stability: inside a destination segment the original edge ids ascend <=> equals torch's stable sort
+    order = torch.sort(ei[1], stable=True).indices
+    assert torch.equal(csr.col_src.long(), ei[0][order])
+    order_s = torch.sort(ei[0], stable=True).indices
+    assert torch.equal(csr.col_dst.long(), ei[1][order_s])
+    assert int(csr.rowptr_dst.max()) == E and csr.status()["hub_chunks_dst"] > 0
+
+
+def test_csr_flags_out_of_range_index(dev):
+    ei = torch.tensor([[0, 1, 9], [1, 2, 0]])
+    csr = sg.build_csr(ei.to(dev), 3)
+    assert csr.status()["index_out_of_range"]
+
+
+# ------------------------------------------------------------------- aggregation --
+@pytest.mark.parametrize("F", [4, 16, 32, 64, 96, 128, 256, 13, 130, 520])
+@pytest.mark.parametrize("kind,N,E", [("random", 300, 3000), ("hub", 2000, 40000), ("dup_self", 50, 400), ("random", 10, 0)])
+def test_segment_mean_matches_cpu_scatter(dev, coracle, F, kind, N, E):
+    ei = edge_cases(kind, N, E, seed=F + N)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(F))
+    want = SAGEConvOracle(F, 1).aggregate(x, ei)
+    csr = sg.build_csr(ei.to(dev), N)
+    got = sg.segment_reduce(x.to(dev), csr, transpose=False, mean=True).cpu()
+    deg = torch.bincount(ei[1], minlength=N)
+    small = deg <= _lib.HUB_DEGREE
+    # rows that are not split: same sequential edge order as the CPU scatter_add_ -> bit equal
+    assert torch.equal(got[small], want[small]), "non-hub rows must be bit exact"
+    assert_close(got, want, "segment mean (hub rows)")
+    # transpose gather with addend == backward of index_select + scatter_add_
+    add = torch.randn(N, F, generator=torch.Generator().manual_seed(1))
+    got_t = sg.segment_reduce(x.to(dev), csr, transpose=True, mean=False, addend=add.to(dev)).cpu()
+    want_t = add.clone().index_add_(0, ei[0], x.index_select(0, ei[1]))
+    assert_close(got_t, want_t, "transpose segment sum", scale_atol=True)
+
+
+def test_segment_reduce_is_deterministic_and_linear(dev):
+    N, E, F = 200_000, 2_000_000, 128
+    ei = skewed_graph(N, E, seed=3).to(dev)
+    csr = sg.build_csr(ei, N)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    a = torch.randn(N, F, generator=g).to(dev)
+    b = torch.randn(N, F, generator=g).to(dev)
+    r1 = sg.segment_reduce(a, csr)
+    r2 = sg.segment_reduce(a, csr)
+    assert torch.equal(r1, r2), "hub splitting must be run-to-run deterministic"
+    lin = sg.segment_reduce(a + b, csr)
+    assert torch.allclose(lin, r1 + sg.segment_reduce(b, csr), rtol=1e-4, atol=1e-5)
+    ones = sg.segment_reduce(torch.ones(N, 4, device=dev), csr)
+    deg = torch.bincount(ei[1], minlength=N)
+    assert torch.equal(ones[:, 0] > 0, deg > 0) and float(ones.max()) <= 1.0 + 1e-6
+
+
+# --------------------------------------------------------------- layer and block --
+def run_pair(dev, hdims, slope, ei, N, seed=0, dropout=None, train=True, affine_rand=True):
+    torch.manual_seed(seed)
+    ref = SageBlockOracle(hdims, dropout=dropout, negative_slope=slope)
+    if affine_rand:
+        with torch.no_grad():
+            for post in ref.posts:
+                post[0].weight.uniform_(0.5, 1.5)
+                post[0].bias.uniform_(-0.5, 0.5)
+    ours = sg.SageBlock(hdims, dropout=dropout, negative_slope=slope)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.to(dev)
+    if not train:
+        ref.eval(); ours.eval()
+    x = torch.randn(N, hdims[0])
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, ei)
+    w = torch.randn_like(yr)
+    (yr * w).sum().backward()
+    xg = x.to(dev).requires_grad_(True)
+    yg = ours(xg, ei.to(dev))
+    (yg * w.to(dev)).sum().backward()
+    return ref, ours, (xr, yr), (xg, yg)
+
+
+def check_pair(ref, ours, r, g):
+    assert_close(g[1], r[1], "output")
+    assert_close(g[0].grad, r[0].grad, "dx", scale_atol=True)
+    rp = dict(ref.named_parameters())
+    for k, p in ours.named_parameters():
+        assert p.grad is not None, k
+        assert_close(p.grad, rp[k].grad, f"grad {k}", scale_atol=True)
+
+
+@pytest.mark.parametrize("hdims,slope", [
+    ([64, 64, 64], 0.1), ([128, 96, 96], 0.1), ([96, 96, 96], None), ([16, 32, 32], 0.1), ([128, 128], 0.1),
+    ([13, 7, 5], 0.2), ([8, 256], 0.1), ([200, 40], None), ([4, 4, 4, 4], 0.01), ([1, 1], 0.1), ([130, 100, 36], 0.1),
+])
+def test_block_matches_oracle(dev, hdims, slope):
+    ei, _, N = unit_map_graphs(3, seed=len(hdims) + hdims[0])
+    check_pair(*run_pair(dev, hdims, slope, ei, N))
+
+
+@pytest.mark.parametrize("kind,N,E", [("hub", 3000, 60000), ("dup_self", 100, 900), ("random", 50, 0), ("random", 1, 0), ("random", 1, 6)])
+def test_block_edge_cases(dev, kind, N, E):
+    ei = edge_cases(kind, N, E, seed=11)
+    check_pair(*run_pair(dev, [32, 48, 16], 0.1, ei, N))
+
+
+def test_block_c1_batch_of_32_map_graphs(dev):
+    """BASELINE config 1: 32 unit map graphs, hdims [64,64,64]."""
+    ei, _, N = unit_map_graphs(32, seed=0)
+    check_pair(*run_pair(dev, [64, 64, 64], 0.1, ei, N))
+
+
+def test_fp64_adjudication(dev, coracle):
+    """Our fp32 error against the fp64 oracle must be of the size of the fp32 oracle's own error."""
+    torch.manual_seed(5)
+    N, E, Fin, Fout, slope = 4000, 40000, 128, 128, 0.1
+    ei = torch.randint(0, N, (2, E))
+    ref = SageBlockOracle([Fin, Fout], negative_slope=slope)
+    ours = sg.SageBlock([Fin, Fout], negative_slope=slope)
+    ours.load_state_dict(ref.state_dict()); ours.to(dev)
+    x = torch.randn(N, Fin)
+    out64, agg64, xhat64, rstd64 = c_forward(coracle, x, ei, ref.convs[0], ref.posts[0][0], slope, "f64")
+    y_ref = ref(x, ei).detach().numpy().astype(np.float64)
+    y_gpu = ours(x.to(dev), ei.to(dev)).detach().cpu().numpy().astype(np.float64)
+    e_ref = np.abs(y_ref - out64).max()
+    e_gpu = np.abs(y_gpu - out64).max()
+    assert e_gpu <= max(4 * e_ref, 2e-6), (e_gpu, e_ref)
+
+
+def test_inference_and_nograd_modes(dev):
+    ei, _, N = unit_map_graphs(2, seed=1)
+    ref = SageBlockOracle([16, 32, 32], dropout=0.25, negative_slope=0.1).eval()
+    ours = sg.SageBlock([16, 32, 32], dropout=0.25, negative_slope=0.1)
+    ours.load_state_dict(ref.state_dict()); ours.to(dev).eval()
+    x = torch.randn(N, 16)
+    want = ref(x, ei)
+    with torch.inference_mode():      # test.py:136-139
+        got_inf = ours(x.to(dev), ei.to(dev))
+    with torch.no_grad():             # src/models/grusage.py:146-147
+        got_ng = ours(x.to(dev), ei.to(dev))
+    assert_close(got_inf, want, "inference_mode"); assert_close(got_ng, want, "no_grad")
+    assert not got_ng.requires_grad
+    with torch.inference_mode():      # edge_index created inside inference mode (rcv.py path)
+        ei_inf = ei.to(dev).clone()
+        assert_close(ours(x.to(dev), ei_inf), want, "inference tensors")
+
+
+def test_dropout_uses_torch_rng_like_the_reference(dev):
+    ei, _, N = unit_map_graphs(2, seed=2)
+    ours = sg.SageBlock([16, 32], dropout=0.5, negative_slope=0.1).to(dev).train()
+    x = torch.randn(N, 16, device=dev)
+    torch.manual_seed(123); a = ours(x, ei.to(dev))
+    torch.manual_seed(123); b = ours(x, ei.to(dev))
+    assert torch.equal(a, b)
+    ours.eval()
+    c = ours(x, ei.to(dev))
+    kept = a != 0
+    assert torch.allclose(a[kept], 2 * c[kept], rtol=1e-6, atol=1e-7)
+    assert 0.3 < float((~kept).float().mean()) < 0.7
+
+
+def test_csr_cache_and_invalidation(dev):
+    ei, _, N = unit_map_graphs(2, seed=4)
+    eid = ei.to(dev)
+    ours = sg.SageBlock([8, 8]).to(dev)
+    x = torch.randn(N, 8, device=dev)
+    y0 = ours(x, eid)
+    c0 = ours._csr
+    ours(x, eid)
+    assert ours._csr is c0, "same tensor, same version -> cached"
+    eid[1] = torch.roll(eid[1], 1)   # in-place edit bumps the version counter
+    y1 = ours(x, eid)
+    assert ours._csr is not c0
+    ref = SageBlockOracle([8, 8]); ref.load_state_dict(ours.state_dict())
+    assert_close(y1, ref(x.cpu(), eid.cpu()), "after invalidation")
+    assert not torch.equal(y0, y1)
+    assert torch.equal(eid.cpu()[0], ei[0]), "inputs are never mutated by the block"
+
+
+def test_grads_and_optimizer_step(dev):
+    """GruSage.grads() walks named_parameters() and Adam updates in place."""
+    ei, _, N = unit_map_graphs(2, seed=5)
+    ours = sg.SageBlock([8, 16, 16], dropout=0.25, negative_slope=0.1).to(dev).train()
+    opt = torch.optim.Adam(ours.parameters(), lr=1e-2)
+    x = torch.randn(N, 8, device=dev)
+    before = [p.detach().clone() for p in ours.parameters()]
+    loss = ours(x, ei.to(dev)).square().mean()
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ours.parameters())
+    opt.step()
+    assert all(not torch.equal(a, p.detach()) for a, p in zip(before, ours.parameters()))
+    ours(x, ei.to(dev)).sum().backward()  # runs again with the updated (re-packed) weights
+
+
+def test_runs_from_a_non_main_thread(dev):
+    """rcv.py:107 calls the model from a worker thread."""
+    import threading
+    ei, _, N = unit_map_graphs(1, seed=6)
+    ours = sg.SageBlock([8, 8]).to(dev).eval()
+    x = torch.randn(N, 8, device=dev)
+    want = ours(x, ei.to(dev))
+    box = {}
+    def work():
+        with torch.inference_mode():
+            box["y"] = ours(x, ei.to(dev))
+    t = threading.Thread(target=work); t.start(); t.join()
+    assert torch.equal(box["y"], want)
+
+
+def test_determinism_run_to_run(dev):
+    """No atomics anywhere: outputs and every gradient are bit-identical across runs."""
+    N = 20000
+    ei = edge_cases("hub", N, 400000, seed=9).to(dev)
+    torch.manual_seed(0)
+    ours = sg.SageBlock([64, 64, 32], negative_slope=0.1).to(dev)
+    x = torch.randn(N, 64, device=dev)
+    w = torch.randn(N, 32, device=dev)
+    runs = []
+    for _ in range(2):
+        ours.zero_grad(set_to_none=True)
+        xg = x.clone().requires_grad_(True)
+        y = ours(xg, ei)
+        (y * w).sum().backward()
+        runs.append([y.detach().clone(), xg.grad.clone()] + [p.grad.clone() for p in ours.parameters()])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------- golden fixtures --
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cuda_matches_reference_golden(dev, path):
+    g = torch.load(path)
+    ours = sg.SageBlock(g["hdims"], dropout=None, negative_slope=g["slope"])
+    ours.load_state_dict(g["state_dict"], strict=True)
+    ours.to(dev)
+    x = g["x"].to(dev).requires_grad_(True)
+    y = ours(x, g["edge_index"].to(dev))
+    (y * g["w"].to(dev)).sum().backward()
+    assert_close(y, g["y"], "golden output")
+    assert_close(x.grad, g["dx"], "golden dx", scale_atol=True)
+    for k, p in ours.named_parameters():
+        assert_close(p.grad, g["grads"][k], f"golden grad {k}", scale_atol=True)
+
+
+# ------------------------------------------------- host-buffer C entry points (numpy) --
+def test_host_buffer_entry_points(dev):
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_small_leaky.pt"))
+    hdims, L = g["hdims"], len(g["hdims"]) - 1
+    x = np.ascontiguousarray(g["x"].numpy()); ei = np.ascontiguousarray(g["edge_index"].numpy())
+    N, E = x.shape[0], ei.shape[1]
+    sd = g["state_dict"]
+    names = []
+    for l in range(L):
+        names += [f"convs.{l}.lin_l.weight", f"convs.{l}.lin_l.bias", f"convs.{l}.lin_r.weight", f"posts.{l}.0.weight", f"posts.{l}.0.bias"]
+    pbufs = [np.ascontiguousarray(sd[n].numpy()) for n in names]
+    params = (C.c_void_p * len(pbufs))(*[b.ctypes.data for b in pbufs])
+    hd = (C.c_int32 * (L + 1))(*hdims)
+    out = np.zeros((N, hdims[-1]), np.float32)
+    _lib.check(_lib.lib.sldm_sage_block_forward_host(x.ctypes.data, ei.ctypes.data, N, E, hd, L, params, 1e-5, g["slope"], out.ctypes.data))
+    assert_close(torch.from_numpy(out), g["y"], "forward_host")
+    gbufs = [np.zeros_like(b) for b in pbufs]
+    grads = (C.c_void_p * len(gbufs))(*[b.ctypes.data for b in gbufs])
+    dx = np.zeros_like(x); out2 = np.zeros_like(out)
+    w = np.ascontiguousarray(g["w"].numpy())
+    _lib.check(_lib.lib.sldm_sage_block_train_host(x.ctypes.data, ei.ctypes.data, N, E, hd, L, params, 1e-5, g["slope"],
+                                                   w.ctypes.data, out2.ctypes.data, dx.ctypes.data, grads))
+    assert np.array_equal(out, out2)
+    assert_close(torch.from_numpy(dx), g["dx"], "train_host dx", scale_atol=True)
+    for n, b in zip(names, gbufs):
+        assert_close(torch.from_numpy(b), g["grads"][n], f"train_host grad {n}", scale_atol=True)
+
+
+# --------------------------------------------------- full-size properties (C3 / C4) --
+def test_c4_full_size_forward_backward_properties(dev):
+    """1M nodes, 10M skewed edges, 128->128: finite, deterministic, row-sampled parity."""
+    N, E, F = 1_000_000, 10_000_000, 128
+    ei = skewed_graph(N, E, seed=0)
+    torch.manual_seed(0)
+    ref = SageBlockOracle([F, F], negative_slope=0.1)
+    ours = sg.SageBlock([F, F], negative_slope=0.1)
+    ours.load_state_dict(ref.state_dict()); ours.to(dev)
+    x = torch.randn(N, F)
+    xg = x.to(dev).requires_grad_(True)
+    eid = ei.to(dev)
+    y = ours(xg, eid)
+    y.sum().backward()
+    assert torch.isfinite(y).all() and torch.isfinite(xg.grad).all()
+    # LayerNorm property: every row of (y un-activated) has zero mean/unit variance -> check via xhat-free route:
+    y2 = ours(xg.detach(), eid)
+    assert torch.equal(y.detach(), y2), "forward must be bit-reproducible"
+    # sampled parity: recompute 2000 random destination rows with the oracle arithmetic on the CPU
+    rows = torch.randint(0, N, (2000,), generator=torch.Generator().manual_seed(1))
+    rows = torch.cat([rows, torch.bincount(ei[1], minlength=N).argmax().view(1)])   # include the hottest hub
+    mask = torch.isin(ei[1], rows)
+    sub = ei[:, mask]
+    conv, ln = ref.convs[0], ref.posts[0][0]
+    agg = torch.zeros(N, F).index_add_(0, sub[1], x[sub[0]])[rows]
+    cnt = torch.bincount(sub[1], minlength=N)[rows].clamp(min=1).float()
+    z = torch.nn.functional.linear(agg / cnt[:, None], conv.lin_l.weight, conv.lin_l.bias) + torch.nn.functional.linear(x[rows], conv.lin_r.weight)
+    want = torch.nn.functional.leaky_relu(torch.nn.functional.layer_norm(z, (F,), ln.weight, ln.bias, 1e-5), 0.1)
+    assert_close(y.detach().cpu()[rows], want, "sampled rows of the 1M-node graph")
+    # gradient checksum: d(sum y)/d b_l summed over rows equals column sums of dz -> finite & nonzero
+    assert all(torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0 for p in ours.parameters())
