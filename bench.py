@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- SageBlock fwd+bwd throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload batch|c4|c1] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one training pass of the hot path over one batch: CSR build from a fresh
+edge_index, SageBlock forward, backward (dx and all parameter gradients) and -- at
+N > 1 -- the single flat-bucket NCCL all-reduce of the gradients.
+
+Workloads (all synthetic, seeded, random-init weights):
+  batch (default) : one mega-batch of 4096 unit map graphs per GPU (~0.82 M nodes,
+                    ~4.1 M edges, block diagonal), SageBlock([128,128,128]); BASELINE
+                    configs[2]/[4] shape.  Shards over ranks by whole graphs: weak scaling.
+  c4              : one skewed graph, 1 M nodes / 10 M edges, SageBlock([128,128]): HBM
+                    roofline stress (BASELINE configs[3]); replicas only at N > 1.
+  c1              : 32 unit map graphs, SageBlock([64,64,64]) (BASELINE configs[0]).
+value   = edge-layer traversals per second (E*L per step), whole job, inputs resident in HBM.
+e2e     = the same through the public module call with pinned HOST inputs: H2D of x and
+          edge_index, fwd+bwd, D2H of the loss, all inside the timed region.
+roofline= the dominant kernel (longest share of the step), algorithmic bytes / its own
+          CUDA-event time / measured HBM peak; roofline_step = SURVEY 8d's per-layer
+          fwd+bwd byte model for the whole step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    "batch": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=256),
+    "c1": dict(kind="graphs", graphs=32, hdims=[64, 64, 64], cpu_sample_graphs=32),
+    "c4": dict(kind="skewed", nodes=1_000_000, edges=10_000_000, hdims=[128, 128], cpu_sample_graphs=None),
+}
+SLOPE = 0.1
+METRIC = "sageblock_fwd_bwd_edges_per_sec"
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(wl, seed):
+    from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+    g = torch.Generator().manual_seed(1000 + seed)
+    if wl["kind"] == "graphs":
+        ei, _, N = unit_map_graphs(wl["graphs"], seed=seed)
+        graphs = wl["graphs"]
+    else:
+        N = wl["nodes"]
+        ei = skewed_graph(N, wl["edges"], seed=seed)
+        graphs = 1
+    x = torch.randn(N, wl["hdims"][0], generator=g)
+    return x, ei, N, graphs
+
+
+# ------------------------------------------------------------------ byte models --
+def layer_bytes_fwd_bwd(N, E, Fin, Fout, s=4):
+    """2E(Fin s + 4) + N s (6 Fin + 5 Fout) + 28 N per layer, fwd+bwd (training)."""
+    return 2 * E * (Fin * s + 4) + N * s * (6 * Fin + 5 * Fout) + 28 * N
+
+
+def csr_bytes(N, E):
+    return 16 * E + 8 * E + 8 * (N + 1)
+
+
+# ---------------------------------------------------------------- clock sampler --
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------- CPU legs --
+def cpu_reference_step(block, x, ei):
+    xr = x.clone().requires_grad_(True)
+    y = block(xr, ei)
+    y.square().mean().backward()
+    block.zero_grad(set_to_none=True)
+
+
+def cpu_sample(wl, seed=0):
+    """Bounded sample of the same workload for the CPU legs."""
+    from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+    if wl["kind"] == "graphs":
+        n = wl["cpu_sample_graphs"]
+        ei, _, N = unit_map_graphs(n, seed=seed)
+        desc = f"{n} of {wl['graphs']} unit map graphs of one batch, fwd+bwd"
+        graphs = n
+    else:
+        N, E = wl["nodes"] // 10, wl["edges"] // 10
+        ei = skewed_graph(N, E, seed=seed)
+        desc = f"1/10-scale skewed graph ({N} nodes, {E} edges), fwd+bwd"
+        graphs = 1
+    x = torch.randn(N, wl["hdims"][0], generator=torch.Generator().manual_seed(seed))
+    return x, ei, N, graphs, desc
+
+
+def run_cpu(wl, steps, warmup):
+    """The reference's CPU path: oracle/sage_oracle.py restates PyG 2.7.0 SAGEConv with the same ATen
+    CPU operators (torch-geometric is not installable here), all host threads."""
+    from oracle.sage_oracle import SageBlockOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    blk = SageBlockOracle(wl["hdims"], dropout=None, negative_slope=SLOPE)
+    x, ei, N, graphs, desc = cpu_sample(wl)
+    for _ in range(warmup):
+        cpu_reference_step(blk, x, ei)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(blk, x, ei)
+    dt = (time.perf_counter() - t0) / steps
+    L = len(wl["hdims"]) - 1
+    return dict(edges_per_s=ei.size(1) * L / dt, graphs_per_s=graphs / dt, ms=dt * 1e3, cores=cores, sample=desc)
+
+
+def main_reference(args, wl):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    r = run_cpu(wl, max(1, args.steps), max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["edges_per_s"], "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, wl, None, None, None),
+        "graphs_per_sec": r["graphs_per_s"],
+        "cpu_baseline": {"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/sage_oracle.py (torch CPU restatement of PyG 2.7.0 SAGEConv; torch-geometric is not installable offline)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, wl, N, E, graphs):
+    c = {"workload": name, "hdims": wl["hdims"], "negative_slope": SLOPE, "dropout": None,
+         "step": "csr_build + forward + backward (+ grad all-reduce at N>1)",
+         "l2": "inputs and saved tensors exceed the 126 MB L2 (x alone is N*F*4 B); two input batches alternate"}
+    if N is not None:
+        c.update(nodes_per_gpu=N, edges_per_gpu=E, graphs_per_gpu=graphs)
+    c["parallelism"] = "graph-sharded data parallel, one flat-bucket NCCL all-reduce" if name != "c4" else "replicas only"
+    return c
+
+
+# -------------------------------------------------------------------- GPU leg --
+def time_kernels(blk, x, ei, N, E, hdims, peak_gbs):
+    """Per-kernel-group CUDA-event timing of layer 0 (through the C-ABI, on torch's current stream)."""
+    import sldm_gnn_b200 as sg
+    from sldm_gnn_b200 import ops
+    Fin, Fout = hdims[0], hdims[1]
+    conv, ln = blk.convs[0], blk.posts[0][0]
+    p = (conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, ln.weight, ln.bias)
+    csr = sg.build_csr(ei, N)
+    out, agg, xhat, rstd = ops.layer_forward(x, csr, *p, ln.eps, SLOPE, True)
+    dout = torch.randn_like(out)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=x.device)
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    s = 4
+    groups = {
+        "csr_build": (lambda: sg.build_csr(ei, N), csr_bytes(N, E)),
+        "segment_mean_fwd": (lambda: sg.segment_reduce(x, csr), E * (Fin * s + 4) + 4 * (N + 1) + N * Fin * s),
+        "project_ln_act_fwd": (lambda: ops.project_forward(agg, x, *p, ln.eps, SLOPE, True), N * s * (2 * Fin + 2 * Fout) + 4 * N),
+        "layer_backward": (lambda: ops.layer_backward(dout, x, agg, xhat, rstd, csr, p[0], p[2], p[3], p[4], SLOPE, True),
+                           N * s * (3 * Fout + 4 * Fin) + 12 * N + E * (Fin * s + 4) + 4 * (N + 1)),
+        "segment_sum_bwd": (lambda: sg.segment_reduce(agg, csr, transpose=True, mean=False, addend=x),
+                            E * (Fin * s + 4) + 4 * (N + 1) + 2 * N * Fin * s),
+    }
+    res = {}
+    for k, (fn, nbytes) in groups.items():
+        fn(); torch.cuda.synchronize()
+        ms = timed(fn)
+        res[k] = {"ms": round(ms, 4), "algorithmic_bytes": nbytes, "gbs": round(nbytes / ms / 1e6, 1),
+                  "frac_hbm": round(nbytes / ms / 1e6 / peak_gbs, 4)}
+    return res
+
+
+def main_ours(args, wl):
+    rank, local_rank, world = env_rank()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import sldm_gnn_b200 as sg
+    from sldm_gnn_b200 import _lib
+    from sldm_gnn_b200.parallel import GraphDataParallel
+
+    hdims = wl["hdims"]
+    L = len(hdims) - 1
+    torch.manual_seed(0)
+    blk = sg.SageBlock(hdims, dropout=None, negative_slope=SLOPE).to(dev)
+    ddp = GraphDataParallel(blk)
+    # two independent batches per rank, alternated, so nothing is reused across steps
+    batches = []
+    for j in range(2):
+        seed = (rank * 2 + j) if args.workload != "c4" else j
+        x_h, ei_h, N, graphs = make_inputs(wl, seed)
+        batches.append(dict(x_h=x_h.pin_memory(), ei_h=ei_h.pin_memory(), N=N, E=ei_h.size(1), graphs=graphs))
+    for b in batches:
+        b["x"] = b["x_h"].to(dev).requires_grad_(True)
+        b["ei"] = b["ei_h"].to(dev)
+    N, E, graphs = batches[0]["N"], batches[0]["E"], batches[0]["graphs"]
+
+    def step(b, x=None, ei=None):
+        x = b["x"] if x is None else x
+        ei = b["ei"] if ei is None else ei
+        blk.clear_cache()                      # every training batch is a new graph: CSR build is part of the step
+        ddp.zero_grad()
+        x.grad = None
+        y = ddp(x, ei)
+        loss = y.square().mean()
+        loss.backward()
+        if world > 1:
+            ddp.sync_gradients(local_weight=b["graphs"])
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(batches[i % 2])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.sldm_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        step(batches[i % 2])
+    t1.record()
+    barrier()
+    launches = _lib.lib.sldm_launch_count() - launches0
+    ms_total = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----
+    e2e_steps = max(2, min(args.steps, 10))
+    for i in range(2):
+        b = batches[i % 2]
+        float(step(b, b["x_h"].to(dev, non_blocking=True).requires_grad_(True), b["ei_h"].to(dev, non_blocking=True)))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        b = batches[i % 2]
+        xd = b["x_h"].to(dev, non_blocking=True).requires_grad_(True)
+        eid = b["ei_h"].to(dev, non_blocking=True)
+        loss_host = float(step(b, xd, eid))      # .item(): the D2H read of the step's result
+    e1.record()
+    barrier()
+    e2e_ms_total = e0.elapsed_time(e1)
+    assert loss_host == loss_host
+
+    t = torch.tensor([ms_total, e2e_ms_total, float(E), float(graphs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, e2e_ms_total = float(mx[0]), float(mx[1])
+        E_all, graphs_all = float(sm[2]), float(sm[3])
+    else:
+        E_all, graphs_all = float(E), float(graphs)
+
+    if rank == 0:
+        peak_gbs, peak_src = measured_peaks()
+        ms_step = ms_total / args.steps
+        value = E_all * L / (ms_step * 1e-3)
+        e2e_ms = e2e_ms_total / e2e_steps
+        step_bytes = sum(layer_bytes_fwd_bwd(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+        kern = time_kernels(blk, batches[0]["x"].detach(), batches[0]["ei"], N, E, hdims, peak_gbs)
+        top = max((k for k in kern if k != "csr_build"), key=lambda k: kern[k]["ms"])
+        line = {
+            "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, wl, N, E, graphs),
+            "graphs_per_sec": graphs_all / (ms_step * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": E_all * L / (e2e_ms * 1e-3), "unit": "edges/s",
+                    "h2d_bytes_per_step": batches[0]["x_h"].numel() * 4 + batches[0]["ei_h"].numel() * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "graphs_per_sec": graphs_all / (e2e_ms * 1e-3)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": kern[top]["gbs"], "peak": peak_gbs, "unit": "GB/s",
+                         "frac": kern[top]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kern[top]["algorithmic_bytes"], "ms_per_launch": kern[top]["ms"]},
+            "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / ms_step / 1e6,
+                              "peak": peak_gbs, "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / peak_gbs,
+                              "model": "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)"},
+            "kernels": kern,
+        }
+        if world == 1 and not args.no_cpu:
+            c = run_cpu(wl, steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": c["edges_per_s"], "unit": "edges/s", "cores": c["cores"], "kind": "port",
+                                    "sample": c["sample"] + ", 2 timed iterations after 1 warm-up",
+                                    "graphs_per_sec": c["graphs_per_s"], "ms_per_step": c["ms"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="batch")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        main_reference(args, wl)
+    else:
+        main_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

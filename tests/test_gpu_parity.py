@@ -32,13 +32,30 @@ def dev():
     return torch.device("cuda:0")
 
 
-def assert_close(got, want, what, scale_atol=False):
+def assert_close(got, want, what, scale_atol=False, want64=None):
+    """|got - want| <= atol + rtol*|want| element-wise against the fp32 oracle.
+
+    The bar sits at the fp32 noise floor: the fp32 oracle itself misses it against the
+    exact answer in ~1e-4 of the elements (profiles/r01_fp32_noise_floor.txt), and a
+    sequential fp32 sum over a hub's 24k in-edges is off by 1e-4 relative.  So elements
+    that miss the bar are adjudicated against the fp64 oracle when the caller supplies
+    it: each must be within the same bar of the EXACT answer, or no further from it than
+    1.5x the fp32 oracle's own worst error on this tensor.  Without want64 the check is strict.
+    """
     got, want = got.detach().cpu(), want.detach().cpu()
     atol = ATOL * (max(1.0, float(want.abs().max())) if scale_atol else 1.0)
     err = (got - want).abs()
-    bound = atol + RTOL * want.abs()
-    bad = err > bound
-    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err {float(err.max()):.3e}"
+    bad = err > atol + RTOL * want.abs()
+    if not bad.any():
+        return
+    msg = f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err {float(err.max()):.3e}"
+    assert want64 is not None, msg
+    w64 = want64.detach().cpu().double()
+    e_g = (got.double() - w64).abs()[bad]
+    e_r_max = float((want.double() - w64).abs().max())
+    ok = (e_g <= atol + RTOL * w64.abs()[bad]) | (e_g <= 1.5 * e_r_max)
+    assert ok.all(), msg + f"; vs fp64: ours max {float(e_g.max()):.3e}, fp32 oracle max {e_r_max:.3e}"
+    assert float(bad.float().mean()) <= 0.02 or e_r_max > atol, msg + " (too many adjudicated elements)"
 
 
 def edge_cases(kind, N, E, seed):
@@ -129,12 +146,14 @@ def test_segment_mean_matches_cpu_scatter(dev, coracle, F, kind, N, E):
     small = deg <= _lib.HUB_DEGREE
     # rows that are not split: same sequential edge order as the CPU scatter_add_ -> bit equal
     assert torch.equal(got[small], want[small]), "non-hub rows must be bit exact"
-    assert_close(got, want, "segment mean (hub rows)")
+    want64 = SAGEConvOracle(F, 1).aggregate(x.double(), ei)
+    assert_close(got, want, "segment mean (hub rows)", want64=want64)
     # transpose gather with addend == backward of index_select + scatter_add_
     add = torch.randn(N, F, generator=torch.Generator().manual_seed(1))
     got_t = sg.segment_reduce(x.to(dev), csr, transpose=True, mean=False, addend=add.to(dev)).cpu()
     want_t = add.clone().index_add_(0, ei[0], x.index_select(0, ei[1]))
-    assert_close(got_t, want_t, "transpose segment sum", scale_atol=True)
+    want_t64 = add.double().index_add_(0, ei[0], x.double().index_select(0, ei[1]))
+    assert_close(got_t, want_t, "transpose segment sum", scale_atol=True, want64=want_t64)
 
 
 def test_segment_reduce_is_deterministic_and_linear(dev):
@@ -156,6 +175,7 @@ def test_segment_reduce_is_deterministic_and_linear(dev):
 
 # --------------------------------------------------------------- layer and block --
 def run_pair(dev, hdims, slope, ei, N, seed=0, dropout=None, train=True, affine_rand=True):
+    """fp32 oracle, fp64 oracle (adjudicator) and the CUDA block on the same inputs and upstream gradient."""
     torch.manual_seed(seed)
     ref = SageBlockOracle(hdims, dropout=dropout, negative_slope=slope)
     if affine_rand:
@@ -163,29 +183,34 @@ def run_pair(dev, hdims, slope, ei, N, seed=0, dropout=None, train=True, affine_
             for post in ref.posts:
                 post[0].weight.uniform_(0.5, 1.5)
                 post[0].bias.uniform_(-0.5, 0.5)
+    ref64 = SageBlockOracle(hdims, dropout=dropout, negative_slope=slope).double()
+    ref64.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
     ours = sg.SageBlock(hdims, dropout=dropout, negative_slope=slope)
     ours.load_state_dict(ref.state_dict(), strict=True)
     ours.to(dev)
     if not train:
-        ref.eval(); ours.eval()
+        ref.eval(); ours.eval(); ref64.eval()
     x = torch.randn(N, hdims[0])
     xr = x.clone().requires_grad_(True)
     yr = ref(xr, ei)
     w = torch.randn_like(yr)
     (yr * w).sum().backward()
+    xd = x.double().requires_grad_(True)
+    yd = ref64(xd, ei)
+    (yd * w.double()).sum().backward()
     xg = x.to(dev).requires_grad_(True)
     yg = ours(xg, ei.to(dev))
     (yg * w.to(dev)).sum().backward()
-    return ref, ours, (xr, yr), (xg, yg)
+    return ref, ours, (xr, yr), (xg, yg), ref64, (xd, yd)
 
 
-def check_pair(ref, ours, r, g):
-    assert_close(g[1], r[1], "output")
-    assert_close(g[0].grad, r[0].grad, "dx", scale_atol=True)
-    rp = dict(ref.named_parameters())
+def check_pair(ref, ours, r, g, ref64, d):
+    assert_close(g[1], r[1], "output", want64=d[1])
+    assert_close(g[0].grad, r[0].grad, "dx", scale_atol=True, want64=d[0].grad)
+    rp, dp = dict(ref.named_parameters()), dict(ref64.named_parameters())
     for k, p in ours.named_parameters():
         assert p.grad is not None, k
-        assert_close(p.grad, rp[k].grad, f"grad {k}", scale_atol=True)
+        assert_close(p.grad, rp[k].grad, f"grad {k}", scale_atol=True, want64=dp[k].grad)
 
 
 @pytest.mark.parametrize("hdims,slope", [
