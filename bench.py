@@ -90,11 +90,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          str(self.index), "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -102,7 +109,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -114,7 +121,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t) + 0.05]
+        window = "timed region"
+        if len(inside) < 3:   # region shorter than a few sampling periods: use everything since warm-up started
+            inside, window = [r for (_, r) in self.rows], "warm-up + timed region (timed region < 3 samples)"
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -123,7 +134,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------- CPU legs --
@@ -278,27 +290,30 @@ def main_ours(args, wl):
         loss.backward()
         if world > 1:
             ddp.sync_gradients(local_weight=b["graphs"])
-        return loss
+        return loss.detach()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
-        step(batches[i % 2])
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)                        # let nvidia-smi come up before the load starts
+    for i in range(max(3, args.warmup)):
+        step(batches[i % 2])
+    barrier()
     launches0 = _lib.lib.sldm_launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     t0.record()
     for i in range(args.steps):
         step(batches[i % 2])
     t1.record()
     barrier()
+    sampler.mark_end()
     launches = _lib.lib.sldm_launch_count() - launches0
     ms_total = t0.elapsed_time(t1)
     clocks = sampler.stop() if rank == 0 else None
@@ -307,7 +322,7 @@ def main_ours(args, wl):
     e2e_steps = max(2, min(args.steps, 10))
     for i in range(2):
         b = batches[i % 2]
-        float(step(b, b["x_h"].to(dev, non_blocking=True).requires_grad_(True), b["ei_h"].to(dev, non_blocking=True)))
+        step(b, b["x_h"].to(dev, non_blocking=True).requires_grad_(True), b["ei_h"].to(dev, non_blocking=True)).item()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -315,7 +330,7 @@ def main_ours(args, wl):
         b = batches[i % 2]
         xd = b["x_h"].to(dev, non_blocking=True).requires_grad_(True)
         eid = b["ei_h"].to(dev, non_blocking=True)
-        loss_host = float(step(b, xd, eid))      # .item(): the D2H read of the step's result
+        loss_host = step(b, xd, eid).detach().item()      # the D2H read of the step's result
     e1.record()
     barrier()
     e2e_ms_total = e0.elapsed_time(e1)
