@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/sldm_sage.h"
 
 namespace sldm {
@@ -79,6 +80,14 @@ int project_forward_launch(const float* agg, const float* x, int64_t N, int32_t 
                            float* out, float* xhat, float* rstd,
                            void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t project_forward_ws_bytes(int64_t N, int32_t Fin, int32_t Fout);
+// tensor-core (tcgen05, 3xTF32) variant: sage_fwd_tc.cu
+bool project_forward_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* agg, const float* x,
+                                 const float* out, const float* xhat);
+int64_t project_forward_tc_ws_bytes(int32_t Fin, int32_t Fout);
+int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
+                              const float* W_l, const float* b_l, const float* W_r,
+                              const float* ln_w, const float* ln_b, float eps, float slope,
+                              float* out, float* xhat, float* rstd, void* ws, int64_t ws_bytes, cudaStream_t s);
 
 int layer_backward_launch(const float* dout, const float* x, const float* agg,
                           const float* xhat, const float* rstd,

@@ -239,7 +239,9 @@ static int proj_bn(int Fout) {
 
 int64_t project_forward_ws_bytes(int64_t /*N*/, int32_t Fin, int32_t Fout) {
   const int FinP = round_up<int>(Fin > 0 ? Fin : 1, kBK);
-  return align_bytes((int64_t)2 * FinP * proj_bn(Fout) * 4);
+  const int64_t simt = align_bytes((int64_t)2 * FinP * proj_bn(Fout) * 4);
+  const int64_t tcb = project_forward_tc_ws_bytes(Fin, Fout);
+  return simt > tcb ? simt : tcb;
 }
 
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -254,6 +256,9 @@ int project_forward_launch(const float* agg, const float* x, int64_t N, int32_t 
   SLDM_REQUIRE(Fout <= 256, SLDM_EUNSUPPORTED, "projection: Fout=%d > 256 is not covered by the kernels", Fout);
   SLDM_REQUIRE(ws_bytes >= project_forward_ws_bytes(N, Fin, Fout) && ws != nullptr, SLDM_EWORKSPACE,
                "projection: workspace too small");
+  if (project_forward_tc_eligible(N, Fin, Fout, agg, x, out, xhat))
+    return project_forward_tc_launch(agg, x, N, Fin, Fout, W_l, b_l, W_r, ln_w, ln_b, eps, slope, out, xhat, rstd,
+                                     ws, ws_bytes, s);
   const int FinP = round_up<int>(Fin, kBK);
   const int BN = proj_bn(Fout);
   float* Wt = static_cast<float*>(ws);
