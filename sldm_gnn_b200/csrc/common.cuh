@@ -101,6 +101,17 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
                           void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t layer_backward_ws_bytes(int64_t N, int32_t Fin, int32_t Fout);
 
+bool dgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* dagg, const float* dxroot);
+int64_t dgrad_tc_ws_bytes(int32_t Fin, int32_t Fout);
+int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const float* W_l, const float* W_r,
+                    const int32_t* rowptr_dst, float* dagg, float* dxroot, void* ws, int64_t ws_bytes,
+                    cudaStream_t s);
+
+bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* agg, const float* x);
+int64_t wgrad_tc_ws_bytes(int32_t Fin, int32_t Fout);
+int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
+                    float* part, int* nparts, cudaStream_t s);
+
 // ---- device helpers -----------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

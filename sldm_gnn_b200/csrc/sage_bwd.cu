@@ -373,7 +373,7 @@ k_reduce_parts(const float* __restrict__ part, int S, int64_t stride, int64_t co
 }
 
 // ------------------------------------------------------------------ launch --
-struct BwdPlan { int grid1; int S; int64_t rows_per_slab; int MB, NB; int64_t colpart_off, part_off, total; };
+struct BwdPlan { int grid1; int S; int64_t rows_per_slab; int MB, NB; int64_t colpart_off, part_off, tc_off, wg_off, total; };
 
 static BwdPlan bwd_plan(int64_t N, int Fin, int Fout) {
   BwdPlan p;
@@ -390,6 +390,8 @@ static BwdPlan bwd_plan(int64_t N, int Fin, int Fout) {
   int64_t o = 0;
   p.colpart_off = o; o += align_bytes((int64_t)p.grid1 * 3 * Fout * 4);
   p.part_off = o;    o += align_bytes((int64_t)p.S * 2 * Fout * Fin * 4);
+  p.tc_off = o;      o += dgrad_tc_ws_bytes(Fin, Fout);
+  p.wg_off = o;      o += wgrad_tc_ws_bytes(Fin, Fout);
   p.total = o;
   return p;
 }
@@ -453,10 +455,14 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
   size_t smem_az = (size_t)64 * (KP + 4) * 4;
   size_t smem_cp = (size_t)8 * 3 * 32 * Q * 4;
   size_t smem = std::max(smem_az, smem_cp) + (size_t)2 * kBKb * bn * 4;
+  // tensor path: the SIMT kernel only does the LayerNorm/activation backward (dz + column partials),
+  // the two data-gradient GEMMs run on tcgen05 (sage_tc.cu, MODE_DGRAD)
+  const bool tc_dgrad = need_dx && dgrad_tc_eligible(N, Fin, Fout, dz, dagg, dxroot);
+  const bool simt_dx = need_dx && !tc_dgrad;
   int rc;
 #define SLDM_B1(TX, TN, TM) \
   rc = launch_b1<TX, TN, TM>(p.grid1, smem, s, dout, xhat, rstd, ln_w, ln_b, slope, N, Fin, Fout, KP, W_l, W_r, \
-                             rowptr_dst, dz, dagg, dxroot, colpart, need_dx ? 1 : 0, vec_w, vec_o)
+                             rowptr_dst, dz, dagg, dxroot, colpart, simt_dx ? 1 : 0, vec_w, vec_o)
   switch (bn) {
     case 32: SLDM_B1(8, 4, 2); break;
     case 64: SLDM_B1(16, 4, 4); break;
@@ -465,8 +471,17 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
   }
 #undef SLDM_B1
   if (rc) return rc;
+  if (tc_dgrad) {
+    rc = dgrad_tc_launch(dz, N, Fin, Fout, W_l, W_r, rowptr_dst, dagg, dxroot, static_cast<char*>(ws) + p.tc_off,
+                         p.total - p.tc_off, s);
+    if (rc) return rc;
+  }
 
-  {
+  int nparts = p.S;
+  if (wgrad_tc_eligible(N, Fin, Fout, dz, agg, x)) {
+    part = reinterpret_cast<float*>(static_cast<char*>(ws) + p.wg_off);
+    if ((rc = wgrad_tc_launch(dz, agg, x, N, Fin, Fout, part, &nparts, s))) return rc;
+  } else {
     dim3 grid(p.S, 2 * p.MB * p.NB);
     const int vec_m = (Fout % 4 == 0) && b16(dz);
     const int vec_n = (Fin % 4 == 0) && b16(agg) && b16(x);
@@ -475,7 +490,7 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
   }
   {
     const int64_t count = 2 * wcount;
-    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(count, 256), 256, 0, s>>>(part, p.S, 2 * wcount, count,
+    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(count, 256), 256, 0, s>>>(part, nparts, 2 * wcount, count,
                                                                          dW_l, wcount, dW_r, count, nullptr);
     SLDM_LAUNCH_CHECK("k_reduce_parts(dW)");
     const int64_t c3 = 3 * (int64_t)Fout;

@@ -1,0 +1,719 @@
+// sage_tc.cu -- tensor-core (tcgen05) GEMM engine of the SageBlock layer, two uses:
+//   FWD   : z = agg W_l^T + b_l + x W_r^T ; out = act(LN(z))   (same contract as k_sage_proj_fwd, sage_fwd.cu;
+//           src/models/blocks/sageblock.py:18-19)
+//   DGRAD : dagg = (dz W_l) / max(deg,1) ; dxroot = dz W_r      (the data-gradient GEMMs of sage_bwd.cu)
+//
+// Why it can be used under an fp32 parity bar.  Plain TF32 keeps 11 significand bits
+// (measured: the hardware TRUNCATES fp32 operands, tools/tc_probe.cu) -- 1e-3 errors.  Here
+// every operand is split a = a_hi + a_lo (a_hi = what the hardware keeps, a_lo = a - a_hi,
+// rounded to tf32) and three products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi are issued, the small
+// ones FIRST.  The tensor core adds into its fp32 accumulator with round-toward-zero
+// (measured bias), so the TMEM accumulator only ever holds ONE 32-wide K chunk (12 MMAs) and
+// is flushed into fp32 registers on the CUDA cores (round-to-nearest adds).  Measured against
+// fp64 (tools/tc_probe2.cu, K=128): max 3.2e-7 / rms 7.3e-8 versus 7.8e-7 / 1.1e-7 for a
+// sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
+//
+// Pipeline (one persistent CTA per SM, 320 threads, 128 rows x Fout per tile):
+//   warp 0      TMA producer : per K chunk (32 floats) loads A raw [128 x 32] (agg, then x) and the
+//                              pre-split weight tiles B_hi, B_lo [Fout x 32] into a 3-stage ring
+//   warps 2-5   converter    : A_lo = rna_tf32(a - trunc_tf32(a)) written beside the raw tile
+//   warp 1      MMA issuer   : 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8) per chunk into one of
+//                              two TMEM accumulators; tcgen05.commit frees the smem stage and
+//                              signals the epilogue
+//   warps 6-13  epilogue     : tcgen05.ld the chunk accumulator (thread = row x half of the columns), add
+//                              into registers; after the last chunk: + bias, LayerNorm (row statistics
+//                              combined across the two column halves through smem), (Leaky)ReLU,
+//                              store out / xhat / rstd
+// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes); shared-memory bandwidth is the second limit.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sldm {
+using namespace tc;
+
+constexpr int kTcThreads = 512;   // 4 warpgroups: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} {epilogue x4}
+constexpr int kTcStages = 3;
+constexpr int kTcBM = 128;
+constexpr int kTcAcc = 4;          // TMEM accumulator ring (one K chunk each)
+constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
+
+// One work item = (128-row tile, output group).  Its K loop runs over nsrc A sources x Kc 32-wide chunks.
+//   FWD  : nsrc = 2 (agg, x), ngroups = 1, Nout = Fout, Kc = Fin/32
+//   DGRAD: nsrc = 1 (dz),     ngroups = 2 (W_l -> dagg, W_r -> dxroot), Nout = Fin, Kc = Fout/32
+// Weight tiles come from one packed array [4 * Nout][K]: block (2*(g*nsrc+src) + lo) holds the hi / lo part.
+struct TcProblem { int64_t N; int Kc, nsrc, ngroups, Nout; };
+
+__global__ void __launch_bounds__(256)
+k_split_weights(const float* __restrict__ W_l, const float* __restrict__ W_r, int count, float* __restrict__ out) {
+  // out = [W_l hi | W_l lo | W_r hi | W_r lo], each `count` floats; hi = rna_tf32(w), lo = rna_tf32(w - hi)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * count; i += gridDim.x * blockDim.x) {
+    const float w = i < count ? W_l[i] : W_r[i - count];
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(w));
+    const float hf = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(w - hf));
+    const int base = i < count ? i : (i - count) + 2 * count;
+    out[base] = hf;
+    out[base + count] = __uint_as_float(l);
+  }
+}
+
+__device__ __forceinline__ float tf32_lo(float a) {
+  const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);  // what the tensor core keeps
+  // a - hi is exact; round it to tf32 (nearest, ties away) with integer ops: add half an ulp, truncate
+  return __uint_as_float((__float_as_uint(a - hi) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// debug timeline (SLDM_TC_TRACE=<file>): CTA 0 stamps clock64() per role / chunk / event
+constexpr int kTraceIts = 96, kTraceEv = 20;
+#define TC_TRACE(ev, itv) \
+  do { if (trace != nullptr && blockIdx.x == 0 && (itv) < kTraceIts) trace[(itv) * kTraceEv + (ev)] = clock64(); } while (0)
+
+struct EpiArgs {
+  int64_t N; int Fout; int64_t ntiles; int nchunks; int ngroups; float eps, slope;
+  float* out; float* xhat; float* rstd; const int32_t* rowptr; uint32_t tmem_base;
+  uint64_t* bar_acc_full; uint64_t* bar_acc_empty;
+  const float* s_bias; const float* s_gamma; const float* s_beta;
+  float* s_sum; float* s_var; float* s_stage; long long* trace;
+};
+
+// Epilogue role: 8 warps (256 threads).  Thread (quadrant q, lane, half HF) owns tile row q*32+lane and the
+// columns [HF*16*NT, (HF+1)*16*NT).  FULL = (Fout == 32*NT): no column masking needed.
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+
+template <int NT, int HF, bool FULL, int MODE>
+__device__ __forceinline__ void epilogue_role(const EpiArgs a) {
+  constexpr int HC = 16 * NT;
+  constexpr int C_LO = HF * HC;
+  constexpr int ACC_COLS = 32 * NT;
+  long long* trace = a.trace;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;
+  const int rloc = q * 32 + lane;
+  const int ew = warp - 8;                 // 0..7
+  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + C_LO;
+  const float fF = (float)a.Fout;
+  const int Fout = a.Fout;
+  float* s_stage_row = a.s_stage + rloc * 33;
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+   for (int grp = 0; grp < a.ngroups; ++grp) {
+    float z[HC];
+    for (int c = 0; c < a.nchunks; ++c, ++it) {
+      const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
+      if (tid == 256) TC_TRACE(8, it);
+      mbar_wait(&a.bar_acc_full[ab], aph);
+      if (tid == 256) TC_TRACE(9, it);
+      tc_fence_after();
+#pragma unroll
+      for (int g0 = 0; g0 < NT; g0 += 2) {
+        uint32_t rr[2][16];
+        tmem_ld_32x16(tq + ab * ACC_COLS + g0 * 16, rr[0]);
+        if (g0 + 1 < NT) tmem_ld_32x16(tq + ab * ACC_COLS + (g0 + 1) * 16, rr[1]);
+        tmem_ld_wait();
+        if (g0 + 2 >= NT) {   // last load of this accumulator: values are in registers, release it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a.bar_acc_empty[ab]);
+          if (tid == 256) TC_TRACE(10, it);
+        }
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          if (g0 + gg < NT) {
+            if (c == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[(g0 + gg) * 16 + j] = __uint_as_float(rr[gg][j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[(g0 + gg) * 16 + j] += __uint_as_float(rr[gg][j]);
+            }
+          }
+        }
+      }
+    }
+    if (tid == 256) TC_TRACE(11, it - 1);
+    const int64_t row = tile * kTcBM + rloc;
+    if constexpr (MODE == MODE_FWD) {
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+      z[j] += a.s_bias[C_LO + j];
+      sum += (FULL || C_LO + j < Fout) ? z[j] : 0.f;
+    }
+    a.s_sum[HF * 128 + rloc] = sum;
+    named_bar_sync(1, 256);
+    const float mean = __fdiv_rn(a.s_sum[rloc] + a.s_sum[128 + rloc], fF);
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+      z[j] -= mean;
+      var += (FULL || C_LO + j < Fout) ? z[j] * z[j] : 0.f;
+    }
+    a.s_var[HF * 128 + rloc] = var;
+    named_bar_sync(1, 256);
+    const float rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(a.s_var[rloc] + a.s_var[128 + rloc], fF) + a.eps));
+    if (row < a.N && a.rstd != nullptr && HF == 0) a.rstd[row] = rs;
+    if (tid == 256) TC_TRACE(14, it - 1);
+    // ---- stores: 32-column blocks staged through smem so every warp store is one 128-byte row segment ----
+    const int npass = a.xhat ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {     // pass 0: out = act(xhat*gamma+beta), pass 1: xhat
+      float* __restrict__ dst = pass == 0 ? a.out : a.xhat;
+#pragma unroll
+      for (int cb = 0; cb < NT; ++cb) {
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          // after unrolling, (cb, j, C_LO) are constants: only this thread's columns of block cb remain
+          if (C_LO + j >= 32 * cb && C_LO + j < 32 * cb + 32) {
+            float v = z[j] * rs;
+            if (pass == 0) {
+              const float y = fmaf(v, a.s_gamma[C_LO + j], a.s_beta[C_LO + j]);
+              v = y > 0.f ? y : a.slope * y;
+            }
+            s_stage_row[C_LO + j - 32 * cb] = v;
+          }
+        }
+        named_bar_sync(1, 256);
+        const int gcol = 32 * cb + lane;
+        if (FULL || gcol < Fout) {
+          const int64_t grow0 = tile * kTcBM + ew * 16;
+          const float* sp = a.s_stage + (ew * 16) * 33 + lane;
+          float* dp = dst + grow0 * Fout + gcol;
+          const int nr = (grow0 + 16 <= a.N) ? 16 : (int)(a.N > grow0 ? a.N - grow0 : 0);
+#pragma unroll 4
+          for (int rr = 0; rr < nr; ++rr) dp[(int64_t)rr * Fout] = sp[rr * 33];
+        }
+        named_bar_sync(1, 256);
+      }
+      if (tid == 256 && pass == 0) TC_TRACE(19, it - 1);
+    }
+      } else {
+      // ---- DGRAD: group 0 -> dagg = acc / max(deg,1) (the mean's backward), group 1 -> dxroot = acc ----
+      float scale_cnt = 1.f;
+      if (grp == 0 && row < a.N) {
+        int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+        deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
+        scale_cnt = (float)deg;
+      }
+      float* __restrict__ dst = grp == 0 ? a.out : a.xhat;
+#pragma unroll
+      for (int cb = 0; cb < NT; ++cb) {
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          if (C_LO + j >= 32 * cb && C_LO + j < 32 * cb + 32)
+            s_stage_row[C_LO + j - 32 * cb] = (grp == 0) ? __fdiv_rn(z[j], scale_cnt) : z[j];
+        }
+        named_bar_sync(1, 256);
+        const int gcol = 32 * cb + lane;
+        if (FULL || gcol < Fout) {
+          const int64_t grow0 = tile * kTcBM + ew * 16;
+          const float* sp = a.s_stage + (ew * 16) * 33 + lane;
+          float* dp = dst + grow0 * Fout + gcol;
+          const int nr = (grow0 + 16 <= a.N) ? 16 : (int)(a.N > grow0 ? a.N - grow0 : 0);
+#pragma unroll 4
+          for (int rr = 0; rr < nr; ++rr) dp[(int64_t)rr * Fout] = sp[rr * 33];
+        }
+        named_bar_sync(1, 256);
+      }
+    }
+   }
+  }
+}
+
+template <int NT, int MODE>  // NT = ceil(Nout / 32) in 1..4
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CUtensorMap tm_x,
+          const __grid_constant__ CUtensorMap tm_w, const TcProblem pb,
+          const float* __restrict__ b_l, const float* __restrict__ gamma,
+          const float* __restrict__ beta, float eps, float slope,
+          float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
+          const int32_t* __restrict__ rowptr, long long* __restrict__ trace) {
+  const int64_t N = pb.N;
+  const int Fout = pb.Nout;   // MMA N / output width of this problem
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full[kTcStages], bar_conv[kTcStages], bar_empty[kTcStages];
+  __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[128], s_gamma[128], s_beta[128];
+  __shared__ float s_sum[2][128], s_var[2][128];
+  __shared__ float s_stage[128][33];   // one 32-column block of the output tile (bank-conflict-free both ways)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_bytes = kTcBM * 128;
+  const uint32_t b_bytes = (uint32_t)Fout * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  constexpr int ACC_COLS = 32 * NT;
+  constexpr uint32_t TMEM_COLS = (kTcAcc * ACC_COLS <= 128) ? 128 : ((kTcAcc * ACC_COLS <= 256) ? 256 : 512);
+
+  const int half = pb.Kc;
+  const int nchunks = pb.nsrc * pb.Kc;
+  const int ngroups = pb.ngroups;
+  const int64_t ntiles = (N + kTcBM - 1) / kTcBM;
+
+  if (MODE == MODE_FWD && tid < 128) {
+    const bool cv = tid < Fout;
+    s_bias[tid] = cv ? b_l[tid] : 0.f;
+    s_gamma[tid] = cv ? gamma[tid] : 0.f;
+    s_beta[tid] = cv ? beta[tid] : 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_conv[s], 4);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int a = 0; a < kTcAcc; ++a) {
+      mbar_init(&bar_acc_full[a], 1);
+      mbar_init(&bar_acc_empty[a], 8);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_agg);
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // warpgroups 0 and 1 hand registers to the two epilogue warpgroups (setmaxnreg is per warpgroup)
+  if (warp < 4) {
+   reg_dec<96>();
+   if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer --
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * kTcBM);
+        for (int g = 0; g < ngroups; ++g) {
+          for (int c = 0; c < nchunks; ++c, ++it) {
+            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+            TC_TRACE(0, it);
+            mbar_wait(&bar_empty[s], ph ^ 1);
+            TC_TRACE(1, it);
+            uint8_t* st = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(&bar_full[s], a_bytes + 2 * b_bytes);
+            const int src = c / half;
+            const int k0 = (c - src * half) * 32;
+            const int wrow = 2 * (g * pb.nsrc + src) * Fout;
+            tma_load_2d(st, src == 0 ? &tm_agg : &tm_x, k0, row0, &bar_full[s]);
+            tma_load_2d(st + 2 * a_bytes, &tm_w, k0, wrow, &bar_full[s]);
+            tma_load_2d(st + 2 * a_bytes + b_bytes, &tm_w, k0, wrow + Fout, &bar_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer --
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(kTcBM, Fout, 0, 0);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < ngroups * nchunks; ++c, ++it) {
+          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+          const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
+          TC_TRACE(2, it);
+          mbar_wait(&bar_acc_empty[ab], aph ^ 1);   // epilogue drained this accumulator (two chunks ago)
+          TC_TRACE(3, it);
+          mbar_wait(&bar_conv[s], ph);              // converter done => TMA data landed too (it waited on bar_full)
+          TC_TRACE(4, it);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          // descriptors differ only in the 14-bit start-address field (bytes >> 4)
+          const uint64_t d_a_hi = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t d_a_lo = d_a_hi + (a_bytes >> 4);
+          const uint64_t d_b_hi = d_a_hi + ((2 * a_bytes) >> 4);
+          const uint64_t d_b_lo = d_b_hi + (b_bytes >> 4);
+          const uint32_t d = tmem_base + ab * ACC_COLS;
+          // small products first: the accumulator rounds toward zero
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_lo + 2 * ks, d_b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 2 * ks, d_b_lo + 2 * ks, idesc, 1u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 2 * ks, d_b_hi + 2 * ks, idesc, 1u);
+          mma_commit(&bar_empty[s]);       // smem stage reusable once these MMAs have read it
+          mma_commit(&bar_acc_full[ab]);   // chunk accumulator complete
+          TC_TRACE(5, it);
+        }
+      }
+    }
+   }  // warps 2 (TMEM allocator) and 3 idle until teardown
+  } else if (warp < 8) {
+    reg_dec<96>();
+    // --------------------------------------------------------------- converter --
+    const int r = tid - 128;  // tile row 0..127
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < ngroups * nchunks; ++c, ++it) {
+        const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+        mbar_wait(&bar_full[s], ph);
+        if (tid == 128) TC_TRACE(6, it);
+        const uint32_t a_raw = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = lds128(a_raw + (uint32_t)((j ^ (r & 7)) << 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 l;
+          l.x = tf32_lo(v[j].x); l.y = tf32_lo(v[j].y); l.z = tf32_lo(v[j].z); l.w = tf32_lo(v[j].w);
+          sts128(a_raw + a_bytes + (uint32_t)((j ^ (r & 7)) << 4), l);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_conv[s]);
+        if (tid == 128) TC_TRACE(7, it);
+      }
+    }
+  } else {
+    reg_inc<160>();
+    // ---------------------------------------------------------------- epilogue --
+    EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
+               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0], &s_stage[0][0], trace};
+    const bool full = (Fout == 32 * NT);
+    if (warp < 12) { if (full) epilogue_role<NT, 0, true, MODE>(ea); else epilogue_role<NT, 0, false, MODE>(ea); }
+    else           { if (full) epilogue_role<NT, 1, true, MODE>(ea); else epilogue_role<NT, 1, false, MODE>(ea); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ================================================================== weight gradient ==
+// dW_l = dz^T agg, dW_r = dz^T x as one GEMM  D[m][n] = sum_r dz[r][m] * [agg | x][r][n]   (M = Fout <= 128 lanes,
+// N = 2*32*NB columns, K = node rows).  Both operands have the reduction index as their slow dimension, i.e. they are
+// "MN-major": the tiles are TMA-loaded as [32 rows][32 floats] boxes with the 128B_ATOM_32B swizzle and described with
+// layout SWIZZLE_128B_BASE32B (lbo = 4096 between 32-column blocks, sbo = 512, 1024 bytes per K=8 step) -- found with
+// tools/tc_probe.cu.  Split precision as in the forward: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, small terms first.
+// Every CTA owns a contiguous slab of rows; the TMEM accumulator is flushed into fp32 registers every kWgFlush chunks
+// (the tensor core accumulates with round-toward-zero) and the per-CTA partial is written once at the end;
+// k_reduce_parts sums the partials in CTA order (deterministic).
+constexpr int kWgStages = 2;
+constexpr int kWgFlush = 4;      // 32-row chunks per TMEM accumulator (128 rows)
+
+template <int NB>   // NB = ceil(Fin / 32) in 1..4
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_agg,
+           const __grid_constant__ CUtensorMap tm_x, int64_t N, int Fin, int Fout, int chunks_per_cta,
+           float* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full[kWgStages], bar_conv[kWgStages], bar_empty[kWgStages];
+  __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t A_BYTES = 4 * 4096;              // dz chunk: 32 rows x 128 columns
+  constexpr uint32_t B_BYTES = 2 * NB * 4096;         // [agg | x] chunk: 32 rows x 2*32*NB columns
+  constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t STAGE_BYTES = 2 * RAW_BYTES;     // raw (= hi) followed by lo, same layout
+  constexpr int NCOLS = 64 * NB;                      // accumulator columns
+  constexpr uint32_t TMEM_COLS = (2 * NCOLS <= 128) ? 128 : ((2 * NCOLS <= 256) ? 256 : 512);
+
+  const int64_t total_chunks = (N + 31) / 32;
+  const int64_t c_beg = (int64_t)blockIdx.x * chunks_per_cta;
+  int64_t c_end = c_beg + chunks_per_cta;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int nch = c_end > c_beg ? (int)(c_end - c_beg) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 4); mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_acc_full[a], 1); mbar_init(&bar_acc_empty[a], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_dz); tma_prefetch_desc(&tm_agg); tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    reg_dec<72>();
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer --
+      for (int it = 0; it < nch; ++it) {
+        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&bar_full[s], RAW_BYTES);
+        const int r0 = (int)((c_beg + it) * 32);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &tm_dz, b * 32, r0, &bar_full[s]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + b * 4096, &tm_agg, b * 32, r0, &bar_full[s]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + (NB + b) * 4096, &tm_x, b * 32, r0, &bar_full[s]);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer --
+      const uint32_t idesc = make_idesc_tf32(128, NCOLS, 1, 1);
+      for (int it = 0; it < nch; ++it) {
+        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
+        const uint32_t fl = it / kWgFlush, ab = fl & 1, aph = (fl >> 1) & 1;
+        const bool first = (it % kWgFlush) == 0;
+        if (first) mbar_wait(&bar_acc_empty[ab], aph ^ 1);
+        mbar_wait(&bar_conv[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t d_a_hi = make_smem_desc(sa, 4096, 512, 1);
+        const uint64_t d_b_hi = d_a_hi + (A_BYTES >> 4);
+        const uint64_t d_a_lo = d_a_hi + (RAW_BYTES >> 4);
+        const uint64_t d_b_lo = d_b_hi + (RAW_BYTES >> 4);
+        const uint32_t d = tmem_base + ab * NCOLS;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_lo + 64 * ks, d_b_hi + 64 * ks, idesc, (first && ks == 0) ? 0u : 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_hi + 64 * ks, idesc, 1u);
+        mma_commit(&bar_empty[s]);
+        if ((it % kWgFlush) == kWgFlush - 1 || it == nch - 1) mma_commit(&bar_acc_full[ab]);
+      }
+    }
+  } else if (warp < 8) {
+    reg_dec<72>();
+    // ------------------------------------------------------------------- converter --
+    const int t = tid - 128;
+    for (int it = 0; it < nch; ++it) {
+      const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
+      mbar_wait(&bar_full[s], ph);
+      const uint32_t raw = smem_u32(smem + (size_t)s * STAGE_BYTES);
+      constexpr int NV = RAW_BYTES / 16 / 128;   // float4 per thread
+#pragma unroll 4
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t off = (uint32_t)(t + i * 128) * 16;
+        const float4 v = lds128(raw + off);
+        float4 l;
+        l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+        sts128(raw + RAW_BYTES + off, l);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_conv[s]);
+    }
+  } else {
+    reg_inc<184>();
+    // -------------------------------------------------------------------- epilogue --
+    constexpr int HC = 32 * NB;              // columns per thread: half of the accumulator
+    const int q = warp & 3;
+    const int hf = (warp - 8) >> 2;          // 0: agg half (dW_l), 1: x half (dW_r)
+    const int m = q * 32 + lane;             // output feature (row of dW)
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + hf * HC;
+    float acc[HC];
+#pragma unroll
+    for (int j = 0; j < HC; ++j) acc[j] = 0.f;
+    const int nfl = (nch + kWgFlush - 1) / kWgFlush;
+    for (int fl = 0; fl < nfl; ++fl) {
+      const uint32_t ab = fl & 1, aph = (fl >> 1) & 1;
+      mbar_wait(&bar_acc_full[ab], aph);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < HC / 16; ++g) {
+        uint32_t rr[16];
+        tmem_ld_32x16(tq + ab * NCOLS + g * 16, rr);
+        tmem_ld_wait();
+        if (g == HC / 16 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[g * 16 + j] += __uint_as_float(rr[j]);
+      }
+    }
+    // partial of this CTA: part[cta][hf][m][n], n < Fin
+    if (m < Fout) {
+      float* dst = part + (((int64_t)blockIdx.x * 2 + hf) * Fout + m) * Fin;
+#pragma unroll
+      for (int j = 0; j < HC; ++j)
+        if (j < Fin) dst[j] = acc[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------ host --
+static bool tc_disabled() {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("SLDM_DISABLE_TC"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  return disabled != 0;
+}
+static bool p16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool project_forward_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* agg, const float* x,
+                                 const float* out, const float* xhat) {
+  return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fin % 32 == 0 && Fin >= 32 && Fout % 16 == 0 &&
+         Fout >= 16 && Fout <= 128 && p16(agg) && p16(x) && p16(out) && p16(xhat);
+}
+bool dgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* dagg, const float* dxroot) {
+  return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fout % 32 == 0 && Fout >= 32 && Fin % 16 == 0 &&
+         Fin >= 16 && Fin <= 128 && p16(dz) && p16(dagg) && p16(dxroot);
+}
+
+int64_t project_forward_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64_t)4 * Fin * Fout * 4); }
+int64_t dgrad_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64_t)4 * Fin * Fout * 4); }
+
+// transposed split for DGRAD: out block b in {W_l^T hi, W_l^T lo, W_r^T hi, W_r^T lo}, each [Fin][Fout]
+__global__ void __launch_bounds__(256)
+k_split_weights_t(const float* __restrict__ W_l, const float* __restrict__ W_r, int Fin, int Fout,
+                  float* __restrict__ out) {
+  const int count = Fin * Fout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * count; i += gridDim.x * blockDim.x) {
+    const int which = i >= count;
+    const int j = which ? i - count : i;      // index into the transposed [Fin][Fout] matrix
+    const int n = j / Fout, k = j % Fout;     // n = input feature, k = output feature
+    const float w = (which ? W_r : W_l)[(int64_t)k * Fin + n];
+    const float hf = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+    const float lf = __uint_as_float((__float_as_uint(w - hf) + 0x1000u) & 0xFFFFE000u);
+    out[(int64_t)(2 * which) * count + j] = hf;
+    out[(int64_t)(2 * which + 1) * count + j] = lf;
+  }
+}
+
+template <int NT, int MODE>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
+                     const float* b_l, const float* g, const float* b, float eps, float slope,
+                     float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
+  const size_t smem = (size_t)kTcStages * (2 * kTcBM * 128 + 2 * (size_t)pb.Nout * 128) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SLDM_CUDA(cudaFuncSetAttribute(k_sage_tc<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kTcStages * (2 * kTcBM * 128 + 2 * 128 * 128) + 1024));
+    attr_done = true;
+  }
+  const int64_t ntiles = ceil_div<int64_t>(pb.N, kTcBM);
+  const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+  long long* trace = nullptr;
+  const char* tf = getenv("SLDM_TC_TRACE");
+  if (tf && tf[0]) {
+    SLDM_CUDA(cudaMalloc(&trace, sizeof(long long) * kTraceIts * kTraceEv));
+    SLDM_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * kTraceIts * kTraceEv, s));
+  }
+  k_sage_tc<NT, MODE><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
+  SLDM_LAUNCH_CHECK("k_sage_tc");
+  if (trace) {
+    static long long h[kTraceIts * kTraceEv];
+    SLDM_CUDA(cudaStreamSynchronize(s));
+    SLDM_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    FILE* f = fopen(tf, "w");
+    if (f) {
+      fprintf(f, "# cycles from t0; ev: 0 tma_wait_empty 1 tma_got_empty 2 mma_top 3 mma_accempty 4 mma_conv 5 mma_committed "
+                 "6 conv_full 7 conv_done 8 epi_wait 9 epi_accfull 10 epi_released 11 epi_finalize 14 stats_done 19 pass0_done\n");
+      const long long t0 = h[0];
+      for (int i = 0; i < kTraceIts; ++i) {
+        fprintf(f, "%d", i);
+        for (int e = 0; e < kTraceEv; ++e) fprintf(f, " %lld", h[i * kTraceEv + e] ? h[i * kTraceEv + e] - t0 : -1);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+  return SLDM_OK;
+}
+
+template <int MODE>
+static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
+                       const float* b_l, const float* g, const float* b, float eps, float slope,
+                       float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
+  switch (ceil_div(pb.Nout, 32)) {
+    case 1: return launch_tc<1, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 2: return launch_tc<2, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 3: return launch_tc<3, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    default: return launch_tc<4, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+  }
+}
+
+int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
+                              const float* W_l, const float* b_l, const float* W_r,
+                              const float* ln_w, const float* ln_b, float eps, float slope,
+                              float* out, float* xhat, float* rstd, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  SLDM_REQUIRE(ws != nullptr && ws_bytes >= project_forward_tc_ws_bytes(Fin, Fout), SLDM_EWORKSPACE,
+               "projection (tensor path): workspace too small");
+  float* wsplit = static_cast<float*>(ws);
+  const int count = Fin * Fout;
+  k_split_weights<<<ceil_div(2 * count, 256 * 4), 256, 0, s>>>(W_l, W_r, count, wsplit);
+  SLDM_LAUNCH_CHECK("k_split_weights");
+  CUtensorMap ma, mx, mw;
+  int rc;
+  if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
+  TcProblem pb{N, Fin / 32, 2, 1, Fout};
+  return dispatch_tc<MODE_FWD>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
+}
+
+// dagg[N,Fin] = (dz W_l) / max(deg,1) ; dxroot[N,Fin] = dz W_r          (dz is [N,Fout])
+int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const float* W_l, const float* W_r,
+                    const int32_t* rowptr_dst, float* dagg, float* dxroot, void* ws, int64_t ws_bytes,
+                    cudaStream_t s) {
+  SLDM_REQUIRE(ws != nullptr && ws_bytes >= dgrad_tc_ws_bytes(Fin, Fout), SLDM_EWORKSPACE,
+               "dgrad (tensor path): workspace too small");
+  float* wsplit = static_cast<float*>(ws);
+  k_split_weights_t<<<ceil_div(2 * Fin * Fout, 256 * 4), 256, 0, s>>>(W_l, W_r, Fin, Fout, wsplit);
+  SLDM_LAUNCH_CHECK("k_split_weights_t");
+  CUtensorMap mz, mw;
+  int rc;
+  if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kTcBM, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fin, Fout, Fout, Fin, 32))) return rc;
+  TcProblem pb{N, Fout / 32, 1, 2, Fin};
+  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
+}
+
+bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* agg, const float* x) {
+  return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fin % 4 == 0 && Fout % 4 == 0 && Fin >= 16 &&
+         Fin <= 128 && Fout >= 16 && Fout <= 128 && p16(dz) && p16(agg) && p16(x);
+}
+int wgrad_tc_grid() { return num_sms(); }
+int64_t wgrad_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64_t)wgrad_tc_grid() * 2 * Fin * Fout * 4); }
+
+template <int NB>
+static int launch_wgrad(const CUtensorMap& mz, const CUtensorMap& ma, const CUtensorMap& mx, int64_t N, int Fin,
+                        int Fout, int cpc, int grid, float* part, cudaStream_t s) {
+  const size_t smem = (size_t)kWgStages * 2 * (4 + 2 * NB) * 4096 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SLDM_CUDA(cudaFuncSetAttribute(k_wgrad_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_wgrad_tc<NB><<<grid, kTcThreads, smem, s>>>(mz, ma, mx, N, Fin, Fout, cpc, part);
+  SLDM_LAUNCH_CHECK("k_wgrad_tc");
+  return SLDM_OK;
+}
+
+// part[grid][2][Fout][Fin]; returns the number of partials through *nparts
+int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
+                    float* part, int* nparts, cudaStream_t s) {
+  CUtensorMap mz, ma, mx;
+  int rc;
+  if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, 32, 32, 1))) return rc;
+  if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, 32, 32, 1))) return rc;
+  if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, 32, 32, 1))) return rc;
+  const int64_t total_chunks = ceil_div<int64_t>(N, 32);
+  int grid = wgrad_tc_grid();
+  if (grid > total_chunks) grid = (int)total_chunks;
+  // whole flush groups per CTA keep the slab boundaries independent of the grid rounding
+  int64_t cpc = round_up<int64_t>(ceil_div<int64_t>(total_chunks, grid), kWgFlush);
+  grid = (int)ceil_div<int64_t>(total_chunks, cpc);
+  *nparts = grid;
+  switch (ceil_div(Fin, 32)) {
+    case 1: return launch_wgrad<1>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);
+    case 2: return launch_wgrad<2>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);
+    case 3: return launch_wgrad<3>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);
+    default: return launch_wgrad<4>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);
+  }
+}
+
+}  // namespace sldm
