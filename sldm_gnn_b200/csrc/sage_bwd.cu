@@ -264,6 +264,113 @@ k_ln_bwd_dgrad(const float* __restrict__ dout, const float* __restrict__ xhat,
   }
 }
 
+// ---- LayerNorm + activation backward alone (the tensor path does the GEMMs elsewhere) ----
+// Streaming kernel: a warp takes 4 consecutive rows per step, a lane holds VPL float4 column slices of each row.
+// dz is written, the column sums (dgamma, dbeta, db_l) are kept per lane and reduced per CTA in warp order.
+// Bound: HBM, 3*N*Fout*4 bytes.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+k_ln_bwd_rows(const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+              int64_t N, int Fout, float* __restrict__ dz, float* __restrict__ colpart) {
+  constexpr int R = 4;
+  __shared__ float cp[8][3][128 * VPL];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float fF = (float)Fout;
+  float4 g[VPL], be[VPL], pg[VPL], pb[VPL], pdb[VPL];
+  bool cv[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const int c = (lane + 32 * q) * 4;
+    cv[q] = c < Fout;
+    g[q] = cv[q] ? ldg4(gamma + c) : f4zero();
+    be[q] = cv[q] ? ldg4(beta + c) : f4zero();
+    pg[q] = pb[q] = pdb[q] = f4zero();
+  }
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * R; r0 < N; r0 += nwarps * R) {
+    float4 d[R][VPL], h[R][VPL];
+    float rs[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int64_t row = r0 + i;
+      const bool rv = row < N;
+      rs[i] = rv ? __ldg(rstd + row) : 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const bool v = rv && cv[q];
+        d[i][q] = v ? ldg4(dout + row * Fout + (lane + 32 * q) * 4) : f4zero();
+        h[i][q] = v ? ldg4(xhat + row * Fout + (lane + 32 * q) * 4) : f4zero();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int64_t row = r0 + i;
+      float s1 = 0.f, s2 = 0.f;
+      float4 t[VPL];
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const float* dd = reinterpret_cast<const float*>(&d[i][q]);
+        const float* hh = reinterpret_cast<const float*>(&h[i][q]);
+        const float* gg = reinterpret_cast<const float*>(&g[q]);
+        const float* bb = reinterpret_cast<const float*>(&be[q]);
+        float* tt = reinterpret_cast<float*>(&t[q]);
+        float* ppg = reinterpret_cast<float*>(&pg[q]);
+        float* ppb = reinterpret_cast<float*>(&pb[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y = fmaf(hh[e], gg[e], bb[e]);
+          const float dy = y > 0.f ? dd[e] : dd[e] * slope;
+          ppg[e] = fmaf(dy, hh[e], ppg[e]);
+          ppb[e] += dy;
+          tt[e] = dy * gg[e];
+          s1 += tt[e];
+          s2 = fmaf(tt[e], hh[e], s2);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float c1 = __fdiv_rn(s1, fF), c2 = __fdiv_rn(s2, fF);
+      if (row < N) {
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          if (cv[q]) {
+            const float* hh = reinterpret_cast<const float*>(&h[i][q]);
+            const float* tt = reinterpret_cast<const float*>(&t[q]);
+            float* pp = reinterpret_cast<float*>(&pdb[q]);
+            float4 o4;
+            float* oo = reinterpret_cast<float*>(&o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              oo[e] = rs[i] * (tt[e] - c1 - hh[e] * c2);
+              pp[e] += oo[e];
+            }
+            st4(dz + row * Fout + (lane + 32 * q) * 4, o4);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const int c = (lane + 32 * q) * 4;
+    st4(&cp[warp][0][c], pg[q]);
+    st4(&cp[warp][1][c], pb[q]);
+    st4(&cp[warp][2][c], pdb[q]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 3 * Fout; idx += 256) {
+    const int which = idx / Fout, c = idx % Fout;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += cp[w][which][c];
+    colpart[(int64_t)blockIdx.x * 3 * Fout + idx] = s;
+  }
+}
+
 // ---- weight gradient: part[s][which][m][n] = sum_{r in slab s} dz[r][m] * cat_which[r][n] ----
 __global__ void __launch_bounds__(256)
 k_wgrad(const float* __restrict__ dz, const float* __restrict__ agg, const float* __restrict__ x,
@@ -373,7 +480,7 @@ k_reduce_parts(const float* __restrict__ part, int S, int64_t stride, int64_t co
 }
 
 // ------------------------------------------------------------------ launch --
-struct BwdPlan { int grid1; int S; int64_t rows_per_slab; int MB, NB; int64_t colpart_off, part_off, tc_off, wg_off, total; };
+struct BwdPlan { int grid1; int grid_ln; int S; int64_t rows_per_slab; int MB, NB; int64_t colpart_off, part_off, tc_off, wg_off, total; };
 
 static BwdPlan bwd_plan(int64_t N, int Fin, int Fout) {
   BwdPlan p;
@@ -388,7 +495,8 @@ static BwdPlan bwd_plan(int64_t N, int Fin, int Fout) {
   p.rows_per_slab = round_up<int64_t>(ceil_div<int64_t>(N > 0 ? N : 1, p.S), kBKb);
   p.S = (int)ceil_div<int64_t>(N > 0 ? N : 1, p.rows_per_slab);
   int64_t o = 0;
-  p.colpart_off = o; o += align_bytes((int64_t)p.grid1 * 3 * Fout * 4);
+  p.grid_ln = (int)std::min<int64_t>(ceil_div<int64_t>(N > 0 ? N : 1, 32), (int64_t)sms * 4);
+  p.colpart_off = o; o += align_bytes((int64_t)std::max(p.grid1, p.grid_ln) * 3 * Fout * 4);
   p.part_off = o;    o += align_bytes((int64_t)p.S * 2 * Fout * Fin * 4);
   p.tc_off = o;      o += dgrad_tc_ws_bytes(Fin, Fout);
   p.wg_off = o;      o += wgrad_tc_ws_bytes(Fin, Fout);
@@ -459,7 +567,17 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
   // the two data-gradient GEMMs run on tcgen05 (sage_tc.cu, MODE_DGRAD)
   const bool tc_dgrad = need_dx && dgrad_tc_eligible(N, Fin, Fout, dz, dagg, dxroot);
   const bool simt_dx = need_dx && !tc_dgrad;
-  int rc;
+  int rc = SLDM_OK;
+  int ncolparts = p.grid1;
+  const bool ln_stream = !simt_dx && (Fout % 4 == 0) && b16(dout) && b16(xhat) && b16(dz) && b16(ln_w) && b16(ln_b);
+  if (ln_stream) {
+    ncolparts = p.grid_ln;
+    if (Fout <= 128)
+      k_ln_bwd_rows<1><<<p.grid_ln, 256, 0, s>>>(dout, xhat, rstd, ln_w, ln_b, slope, N, Fout, dz, colpart);
+    else
+      k_ln_bwd_rows<2><<<p.grid_ln, 256, 0, s>>>(dout, xhat, rstd, ln_w, ln_b, slope, N, Fout, dz, colpart);
+    SLDM_LAUNCH_CHECK("k_ln_bwd_rows");
+  } else {
 #define SLDM_B1(TX, TN, TM) \
   rc = launch_b1<TX, TN, TM>(p.grid1, smem, s, dout, xhat, rstd, ln_w, ln_b, slope, N, Fin, Fout, KP, W_l, W_r, \
                              rowptr_dst, dz, dagg, dxroot, colpart, simt_dx ? 1 : 0, vec_w, vec_o)
@@ -470,6 +588,7 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
     default: SLDM_B1(16, 8, 4); break;
   }
 #undef SLDM_B1
+  }
   if (rc) return rc;
   if (tc_dgrad) {
     rc = dgrad_tc_launch(dz, N, Fin, Fout, W_l, W_r, rowptr_dst, dagg, dxroot, static_cast<char*>(ws) + p.tc_off,
@@ -494,7 +613,7 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
                                                                          dW_l, wcount, dW_r, count, nullptr);
     SLDM_LAUNCH_CHECK("k_reduce_parts(dW)");
     const int64_t c3 = 3 * (int64_t)Fout;
-    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(c3, 256), 256, 0, s>>>(colpart, p.grid1, c3, c3,
+    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(c3, 256), 256, 0, s>>>(colpart, ncolparts, c3, c3,
                                                                       dln_w, Fout, dln_b, 2 * (int64_t)Fout, db_l);
     SLDM_LAUNCH_CHECK("k_reduce_parts(cols)");
   }
