@@ -73,7 +73,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
 }
 
 // debug timeline (SLDM_TC_TRACE=<file>): CTA 0 stamps clock64() per role / chunk / event
-constexpr int kTraceIts = 96, kTraceEv = 20;
+constexpr int kTraceIts = 96, kTraceEv = 32;
 #define TC_TRACE(ev, itv) \
   do { if (trace != nullptr && blockIdx.x == 0 && (itv) < kTraceIts) trace[(itv) * kTraceEv + (ev)] = clock64(); } while (0)
 
@@ -83,6 +83,7 @@ struct EpiArgs {
   uint64_t* bar_acc_full; uint64_t* bar_acc_empty;
   const float* s_bias; const float* s_gamma; const float* s_beta;
   float* s_sum; float* s_var; float* s_stage; long long* trace;
+  const CUtensorMap* tm_o0; const CUtensorMap* tm_o1;   // TMA store maps: FWD out / xhat, DGRAD dagg / dxroot
 };
 
 // Epilogue role: 8 warps (256 threads).  Thread (quadrant q, lane, half HF) owns tile row q*32+lane and the
@@ -103,7 +104,6 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
   const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + C_LO;
   const float fF = (float)a.Fout;
   const int Fout = a.Fout;
-  float* s_stage_row = a.s_stage + rloc * 33;
   uint32_t it = 0;
   for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
    for (int grp = 0; grp < a.ngroups; ++grp) {
@@ -142,96 +142,93 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
     }
     if (tid == 256) TC_TRACE(11, it - 1);
     const int64_t row = tile * kTcBM + rloc;
+    float rs = 1.f;            // FWD: rstd of the row;  DGRAD: unused
+    float cnt = 1.f;           // DGRAD group 0: max(deg,1)
     if constexpr (MODE == MODE_FWD) {
-    float sum = 0.f;
+      // ---- bias + LayerNorm statistics; the two column halves of a row live in warps (8+q) and (12+q):
+      //      they meet on a 64-thread named barrier, nobody else waits ----
+      float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < HC; ++j) {
-      z[j] += a.s_bias[C_LO + j];
-      sum += (FULL || C_LO + j < Fout) ? z[j] : 0.f;
-    }
-    a.s_sum[HF * 128 + rloc] = sum;
-    named_bar_sync(1, 256);
-    const float mean = __fdiv_rn(a.s_sum[rloc] + a.s_sum[128 + rloc], fF);
-    float var = 0.f;
-#pragma unroll
-    for (int j = 0; j < HC; ++j) {
-      z[j] -= mean;
-      var += (FULL || C_LO + j < Fout) ? z[j] * z[j] : 0.f;
-    }
-    a.s_var[HF * 128 + rloc] = var;
-    named_bar_sync(1, 256);
-    const float rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(a.s_var[rloc] + a.s_var[128 + rloc], fF) + a.eps));
-    if (row < a.N && a.rstd != nullptr && HF == 0) a.rstd[row] = rs;
-    if (tid == 256) TC_TRACE(14, it - 1);
-    // ---- stores: 32-column blocks staged through smem so every warp store is one 128-byte row segment ----
-    const int npass = a.xhat ? 2 : 1;
-    for (int pass = 0; pass < npass; ++pass) {     // pass 0: out = act(xhat*gamma+beta), pass 1: xhat
-      float* __restrict__ dst = pass == 0 ? a.out : a.xhat;
-#pragma unroll
-      for (int cb = 0; cb < NT; ++cb) {
-#pragma unroll
-        for (int j = 0; j < HC; ++j) {
-          // after unrolling, (cb, j, C_LO) are constants: only this thread's columns of block cb remain
-          if (C_LO + j >= 32 * cb && C_LO + j < 32 * cb + 32) {
-            float v = z[j] * rs;
-            if (pass == 0) {
-              const float y = fmaf(v, a.s_gamma[C_LO + j], a.s_beta[C_LO + j]);
-              v = y > 0.f ? y : a.slope * y;
-            }
-            s_stage_row[C_LO + j - 32 * cb] = v;
-          }
-        }
-        named_bar_sync(1, 256);
-        const int gcol = 32 * cb + lane;
-        if (FULL || gcol < Fout) {
-          const int64_t grow0 = tile * kTcBM + ew * 16;
-          const float* sp = a.s_stage + (ew * 16) * 33 + lane;
-          float* dp = dst + grow0 * Fout + gcol;
-          const int nr = (grow0 + 16 <= a.N) ? 16 : (int)(a.N > grow0 ? a.N - grow0 : 0);
-#pragma unroll 4
-          for (int rr = 0; rr < nr; ++rr) dp[(int64_t)rr * Fout] = sp[rr * 33];
-        }
-        named_bar_sync(1, 256);
+      for (int j = 0; j < HC; ++j) {
+        z[j] += a.s_bias[C_LO + j];
+        sum += (FULL || C_LO + j < Fout) ? z[j] : 0.f;
       }
-      if (tid == 256 && pass == 0) TC_TRACE(19, it - 1);
-    }
-      } else {
-      // ---- DGRAD: group 0 -> dagg = acc / max(deg,1) (the mean's backward), group 1 -> dxroot = acc ----
-      float scale_cnt = 1.f;
+      a.s_sum[HF * 128 + rloc] = sum;
+      named_bar_sync(2 + q, 64);
+      const float mean = __fdiv_rn(a.s_sum[rloc] + a.s_sum[128 + rloc], fF);
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < HC; ++j) {
+        z[j] -= mean;
+        var += (FULL || C_LO + j < Fout) ? z[j] * z[j] : 0.f;
+      }
+      a.s_var[HF * 128 + rloc] = var;
+      named_bar_sync(2 + q, 64);
+      rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(a.s_var[rloc] + a.s_var[128 + rloc], fF) + a.eps));
+      if (row < a.N && a.rstd != nullptr && HF == 0) a.rstd[row] = rs;
+#pragma unroll
+      for (int j = 0; j < HC; ++j) z[j] *= rs;      // z now holds xhat
+      if (tid == 256) TC_TRACE(14, it - 1);
+    } else {
       if (grp == 0 && row < a.N) {
         int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
         deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
-        scale_cnt = (float)deg;
+        cnt = (float)deg;
       }
-      float* __restrict__ dst = grp == 0 ? a.out : a.xhat;
+    }
+    // ---- stores.  Each warp owns a [32 rows x 16*NT columns] sub-tile and pushes it out 16 columns at a time:
+    //      4 conflict-free 128-bit smem stores per lane into a private 2 KB patch laid out as a 64B-swizzled
+    //      TMA box, then one cp.async.bulk.tensor store (the TMA engine clips rows >= N / columns >= Fout). ----
+    const uint32_t patch = smem_u32(a.s_stage + ew * 512);
+    const uint32_t prow = patch + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    const int grow0 = (int)(tile * kTcBM) + q * 32;       // first global row of this warp's sub-tile
+    const int npass = (MODE == MODE_FWD) ? (a.xhat ? 2 : 1) : 1;
+    for (int pass = 0; pass < npass; ++pass) {     // FWD: pass 0 = out (activation), pass 1 = xhat
+      const CUtensorMap* tm;
+      if constexpr (MODE == MODE_FWD) tm = pass == 0 ? a.tm_o0 : a.tm_o1;
+      else tm = grp == 0 ? a.tm_o0 : a.tm_o1;      // DGRAD: dagg / dxroot
 #pragma unroll
-      for (int cb = 0; cb < NT; ++cb) {
+      for (int hb = 0; hb < NT; ++hb) {
+        if (!FULL && C_LO + hb * 16 >= Fout) break;
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < HC; ++j) {
-          if (C_LO + j >= 32 * cb && C_LO + j < 32 * cb + 32)
-            s_stage_row[C_LO + j - 32 * cb] = (grp == 0) ? __fdiv_rn(z[j], scale_cnt) : z[j];
+        for (int j = 0; j < 16; ++j) {
+          const int jj = hb * 16 + j;
+          if constexpr (MODE == MODE_FWD) {
+            v[j] = z[jj];
+            if (pass == 0) {
+              const float y = fmaf(v[j], a.s_gamma[C_LO + jj], a.s_beta[C_LO + jj]);
+              v[j] = y > 0.f ? y : a.slope * y;
+            }
+          } else {
+            v[j] = (grp == 0) ? __fdiv_rn(z[jj], cnt) : z[jj];
+          }
         }
-        named_bar_sync(1, 256);
-        const int gcol = 32 * cb + lane;
-        if (FULL || gcol < Fout) {
-          const int64_t grow0 = tile * kTcBM + ew * 16;
-          const float* sp = a.s_stage + (ew * 16) * 33 + lane;
-          float* dp = dst + grow0 * Fout + gcol;
-          const int nr = (grow0 + 16 <= a.N) ? 16 : (int)(a.N > grow0 ? a.N - grow0 : 0);
-#pragma unroll 4
-          for (int rr = 0; rr < nr; ++rr) dp[(int64_t)rr * Fout] = sp[rr * 33];
+        if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading the patch
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sts128(prow + (uint32_t)((k ^ sw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm, a.s_stage + ew * 512, C_LO + hb * 16, grow0);
+          tma_store_commit();
         }
-        named_bar_sync(1, 256);
       }
+      if (tid == 256 && pass == 0) TC_TRACE(19, it - 1);
     }
    }
   }
+  if (lane == 0) tma_store_wait_all<0>();   // all global writes of this warp are complete before the CTA exits
 }
 
 template <int NT, int MODE>  // NT = ceil(Nout / 32) in 1..4
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CUtensorMap tm_x,
-          const __grid_constant__ CUtensorMap tm_w, const TcProblem pb,
+          const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_o0,
+          const __grid_constant__ CUtensorMap tm_o1, const TcProblem pb,
           const float* __restrict__ b_l, const float* __restrict__ gamma,
           const float* __restrict__ beta, float eps, float slope,
           float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
@@ -245,7 +242,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[128], s_gamma[128], s_beta[128];
   __shared__ float s_sum[2][128], s_var[2][128];
-  __shared__ float s_stage[128][33];   // one 32-column block of the output tile (bank-conflict-free both ways)
+  __shared__ __align__(1024) float s_stage[8][512];   // one private 2 KB TMA-store patch ([32 rows][16 cols], 64B swizzle) per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
@@ -379,7 +376,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     reg_inc<160>();
     // ---------------------------------------------------------------- epilogue --
     EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
-               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0], &s_stage[0][0], trace};
+               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0], &s_stage[0][0], trace, &tm_o0, &tm_o1};
     const bool full = (Fout == 32 * NT);
     if (warp < 12) { if (full) epilogue_role<NT, 0, true, MODE>(ea); else epilogue_role<NT, 0, false, MODE>(ea); }
     else           { if (full) epilogue_role<NT, 1, true, MODE>(ea); else epilogue_role<NT, 1, false, MODE>(ea); }
@@ -583,7 +580,8 @@ k_split_weights_t(const float* __restrict__ W_l, const float* __restrict__ W_r, 
 }
 
 template <int NT, int MODE>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mo0,
+                     const CUtensorMap& mo1, const TcProblem& pb,
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   const size_t smem = (size_t)kTcStages * (2 * kTcBM * 128 + 2 * (size_t)pb.Nout * 128) + 1024;
@@ -601,7 +599,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     SLDM_CUDA(cudaMalloc(&trace, sizeof(long long) * kTraceIts * kTraceEv));
     SLDM_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * kTraceIts * kTraceEv, s));
   }
-  k_sage_tc<NT, MODE><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
+  k_sage_tc<NT, MODE><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
   SLDM_LAUNCH_CHECK("k_sage_tc");
   if (trace) {
     static long long h[kTraceIts * kTraceEv];
@@ -625,14 +623,15 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
 }
 
 template <int MODE>
-static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
+static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mo0,
+                       const CUtensorMap& mo1, const TcProblem& pb,
                        const float* b_l, const float* g, const float* b, float eps, float slope,
                        float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   switch (ceil_div(pb.Nout, 32)) {
-    case 1: return launch_tc<1, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 2: return launch_tc<2, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 3: return launch_tc<3, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    default: return launch_tc<4, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 1: return launch_tc<1, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 2: return launch_tc<2, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 3: return launch_tc<3, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    default: return launch_tc<4, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
   }
 }
 
@@ -651,8 +650,11 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
+  CUtensorMap mo0, mo1;
+  if ((rc = make_tmap_2d_f32(&mo0, out, (uint64_t)N, Fout, Fout, 32, 16, 2))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo1, xhat ? xhat : out, (uint64_t)N, Fout, Fout, 32, 16, 2))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
-  return dispatch_tc<MODE_FWD>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
+  return dispatch_tc<MODE_FWD>(ma, mx, mw, mo0, mo1, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
 }
 
 // dagg[N,Fin] = (dz W_l) / max(deg,1) ; dxroot[N,Fin] = dz W_r          (dz is [N,Fout])
@@ -668,8 +670,11 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
   int rc;
   if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fin, Fout, Fout, Fin, 32))) return rc;
+  CUtensorMap mo0, mo1;
+  if ((rc = make_tmap_2d_f32(&mo0, dagg, (uint64_t)N, Fin, Fin, 32, 16, 2))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo1, dxroot, (uint64_t)N, Fin, Fin, 32, 16, 2))) return rc;
   TcProblem pb{N, Fout / 32, 1, 2, Fin};
-  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
+  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, mo0, mo1, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
 }
 
 bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* agg, const float* x) {

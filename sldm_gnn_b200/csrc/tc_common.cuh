@@ -73,6 +73,10 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // ---- TMEM --------------------------------------------------------------------------
 // whole-warp, power-of-two columns >= 32; writes the base address to *dst_smem
@@ -172,6 +176,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
 // ---- host: tensor maps ----------------------------------------------------------------
 // 2-D row-major fp32 matrix [rows][cols] (cols contiguous), box = box_rows x 32 fp32, 128-byte swizzle.
 int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                     uint32_t box_rows, uint32_t box_cols, int swizzle_atom32 = 0);
+                     uint32_t box_rows, uint32_t box_cols, int swizzle_atom32 = 0);  // 0: 128B, 1: 128B_ATOM_32B, 2: 64B
 
 }  // namespace sldm
