@@ -36,6 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# anything NCCL prints (its version banner at init) must not land on stdout: stdout carries ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 

@@ -85,12 +85,9 @@ class GraphDataParallel(nn.Module):
             p.grad = v
         if not self._ready():
             return
-        world = dist.get_world_size(self.process_group)
-        if local_weight is None:
-            self._flat_grad[-1] = 1.0
-        else:
-            self._flat_grad[:-1].mul_(float(local_weight))
-            self._flat_grad[-1] = float(local_weight)
+        w = 1.0 if local_weight is None else float(local_weight)
+        if w != 1.0:
+            self._flat_grad[:-1].mul_(w)
+        self._flat_grad[-1:].fill_(w)          # device-side fill: no host copy, no sync
         dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
         self._flat_grad[:-1].div_(self._flat_grad[-1])
-        del world
