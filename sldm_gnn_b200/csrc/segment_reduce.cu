@@ -15,9 +15,12 @@
 // summed by one CTA (fixed sub-ranges per group, fixed combine order) into a
 // partial slot, then recombined in piece order: deterministic, no atomics.
 //
+// Measured (B200, batch workload F=128, profiles/r01b_*): generic kernel 0.38 ms (issue-bound, 362 warp instr/row),
+// lean kernel 0.27 ms; config-4 graph 1.20 -> 0.91 ms (6.2 TB/s algorithmic).
 // Bound: HBM.  Algorithmic bytes per call = E*(F*4 + 4) + 4(N+1) + N*F*4 (+N*F*4 addend).
 #include "common.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace sldm {
 
@@ -124,6 +127,119 @@ k_segment_rows(const VT* __restrict__ src, int64_t FV,
   }
 }
 
+// ---- lean row kernel (128-bit path, FV <= LPR) ------------------------------------------------------------------
+// The generic kernel above is issue-bound on low-degree graphs (ncu, profiles/r01b_*: 362 warp instructions per row at
+// mean degree 5: padded 8-wide predicated slots, a shuffle and 64-bit index arithmetic per edge, four IEEE divisions
+// per lane per row).  This one spends ~7 instructions per edge:
+//   * a warp owns 32 CONSECUTIVE rows: their row pointers are two coalesced loads, their column indices one
+//     contiguous range of `col` that is copied into a per-warp shared-memory window (coalesced) and then read back
+//     as broadcasts -- no shuffles, no per-row dependent index loads;
+//   * the edge loop issues exactly deg loads in pieces of 8/4/2/1 (no predicated padding), adds in edge order;
+//   * the mean divides with IEEE division only when the count is not a power of two (x * 2^-k is the same
+//     correctly rounded value as x / 2^k).
+// A group of LPR lanes owns a row (LPR = 32: the whole warp, nothing diverges).  Results are bit-identical to the
+// generic kernel: same values, same order of additions.
+__device__ __forceinline__ int ldg_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// address of source row c: one IMAD.WIDE (32 x 32 -> 64 bit product added to the 64-bit lane base)
+__device__ __forceinline__ const float4* row_ptr(const char* __restrict__ pb, int c, int row_bytes) {
+  return reinterpret_cast<const float4*>(pb + (int64_t)c * row_bytes);
+}
+template <int U>
+__device__ __forceinline__ void gather_piece(const char* __restrict__ pb, int row_bytes, const int* w, float4& acc) {
+  float4 v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) v[u] = __ldg(row_ptr(pb, w[u], row_bytes));
+#pragma unroll
+  for (int u = 0; u < U; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+}
+
+template <int LPR, int UMAX>
+__global__ void __launch_bounds__(256)
+k_segment_rows_lean(const float4* __restrict__ src, int64_t FV,
+                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    int64_t N, int mean, const float4* __restrict__ addend, float4* __restrict__ out) {
+  constexpr int RPW = 32 / LPR;            // rows in flight per warp
+  constexpr int CH = RPW <= 4 ? 256 * RPW : 1024;   // window: RPW consecutive non-hub rows fit (RPW <= 4); only a cache
+  __shared__ int s_win[8][CH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / LPR, lig = lane % LPR;
+  int* win = s_win[warp];
+  const int64_t wbase = (int64_t)blockIdx.x * kRowsPerCta + warp * 32;
+  if (wbase >= N) return;
+  const int64_t myrow = wbase + lane;
+  const int rb = __ldg(rowptr + (myrow < N ? myrow : N));
+  const int re = __ldg(rowptr + (myrow + 1 < N ? myrow + 1 : N));
+  const int e_last = __shfl_sync(0xffffffffu, re, 31);      // end of this warp's edge range
+  const bool cvalid = lig < FV;
+  const char* __restrict__ pb = reinterpret_cast<const char*>(src + (cvalid ? lig : 0));
+  const int row_bytes = (int)FV * 16;
+  int ws = -CH - 1;                        // window covers col[ws, ws + CH)
+#pragma unroll 1
+  for (int it = 0; it < 32 / RPW; ++it) {
+    const int rfirst = it * RPW;
+    if (wbase + rfirst >= N) break;
+    const int ibeg = __shfl_sync(0xffffffffu, rb, rfirst);
+    const int iend = __shfl_sync(0xffffffffu, re, rfirst + RPW - 1);
+    if (iend > ws + CH) {                  // refill from the first edge of this iteration's rows
+      __syncwarp();
+      ws = ibeg;
+#pragma unroll
+      for (int q = 0; q < CH / 32; ++q) {
+        const int e = ws + lane + 32 * q;
+        if (e < e_last) win[lane + 32 * q] = ldg_stream_i32(col + e);
+      }
+      __syncwarp();
+    }
+    const int beg = __shfl_sync(0xffffffffu, rb, rfirst + g);
+    const int end = __shfl_sync(0xffffffffu, re, rfirst + g);
+    const int64_t row = wbase + rfirst + g;
+    const int deg = end - beg;
+    if (row >= N || deg > SLDM_HUB_DEGREE) continue;        // split rows: k_segment_hub_*
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg >= ws && end <= ws + CH) {
+      const int* w = win + (beg - ws);
+      int rem = deg;
+      if constexpr (UMAX >= 8) {
+        for (; rem >= 8; rem -= 8, w += 8) gather_piece<8>(pb, row_bytes, w, acc);
+        if (rem >= 4) { gather_piece<4>(pb, row_bytes, w, acc); rem -= 4; w += 4; }
+      } else {
+        for (; rem >= 4; rem -= 4, w += 4) gather_piece<4>(pb, row_bytes, w, acc);
+      }
+      if (rem >= 2) { gather_piece<2>(pb, row_bytes, w, acc); rem -= 2; w += 2; }
+      if (rem >= 1) gather_piece<1>(pb, row_bytes, w, acc);
+    } else {                               // row not covered by the window (next to a hub row, RPW > 1): direct index loads
+#pragma unroll 1
+      for (int k = beg; k < end; ++k) {
+        const float4 v = __ldg(row_ptr(pb, __ldg(col + k), row_bytes));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (cvalid) {
+      if (mean && deg > 1) {
+        if ((deg & (deg - 1)) == 0) {
+          const float rc = __fdiv_rn(1.f, (float)deg);       // exact: deg is a power of two
+          acc.x *= rc; acc.y *= rc; acc.z *= rc; acc.w *= rc;
+        } else {
+          acc = Vec<float4>::div(acc, ref_count(deg));
+        }
+      }
+      if (addend != nullptr) { float4 a = ldg_stream_f4(addend + row * FV + lig); Vec<float4>::add(a, acc); acc = a; }
+      out[row * FV + lig] = acc;
+    }
+  }
+}
+
 template <typename VT, int LPR, int VPL, int UNR>
 __global__ void __launch_bounds__(256)
 k_segment_hub_chunks(const VT* __restrict__ src, int64_t FV,
@@ -199,7 +315,17 @@ static int launch_all(const float* src, int64_t N, int64_t FV,
   VT* vout = reinterpret_cast<VT*>(out);
   VT* vpart = reinterpret_cast<VT*>(partials);
   const int64_t grid = ceil_div<int64_t>(N, kRowsPerCta);
-  k_segment_rows<VT, LPR, VPL, UNR><<<(unsigned)grid, 256, 0, s>>>(vsrc, FV, rowptr, col, N, mean ? 1 : 0, vadd, vout);
+  if constexpr (std::is_same<VT, float4>::value && VPL == 1) {
+    static const int lean = [] { const char* e = getenv("SLDM_SEG_LEAN"); return e ? atoi(e) : 4; }();   // 0: generic kernel, 4|8: lean kernel with that many loads per piece
+    if (lean == 4 || lean == 1)
+      k_segment_rows_lean<LPR, 4><<<(unsigned)grid, 256, 0, s>>>(vsrc, FV, rowptr, col, N, mean ? 1 : 0, vadd, vout);
+    else if (lean != 0)
+      k_segment_rows_lean<LPR, 8><<<(unsigned)grid, 256, 0, s>>>(vsrc, FV, rowptr, col, N, mean ? 1 : 0, vadd, vout);
+    else
+      k_segment_rows<VT, LPR, VPL, UNR><<<(unsigned)grid, 256, 0, s>>>(vsrc, FV, rowptr, col, N, mean ? 1 : 0, vadd, vout);
+  } else {
+    k_segment_rows<VT, LPR, VPL, UNR><<<(unsigned)grid, 256, 0, s>>>(vsrc, FV, rowptr, col, N, mean ? 1 : 0, vadd, vout);
+  }
   SLDM_LAUNCH_CHECK("k_segment_rows");
   if (hub_cap > 0 && hub_list != nullptr) {
     const int cap = (int)hub_cap;
