@@ -13,14 +13,14 @@
 // fp64 (tools/tc_probe2.cu, K=128): max 3.2e-7 / rms 7.3e-8 versus 7.8e-7 / 1.1e-7 for a
 // sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
 //
-// Pipeline (one persistent CTA per SM, 320 threads, 128 rows x Fout per tile):
+// Pipeline (one persistent CTA per SM, 768 threads, 128 rows x Fout per tile; setmaxnreg 40 / 56 / 96 of the 80 x 768 pool):
 //   warp 0      TMA producer : per K chunk (32 floats) loads A raw [128 x 32] (agg, then x) and the
 //                              pre-split weight tiles B_hi, B_lo [Fout x 32] into a 3-stage ring
-//   warps 2-5   converter    : A_lo = rna_tf32(a - trunc_tf32(a)) written beside the raw tile
+//   warps 4-7   converter    : A_lo = rna_tf32(a - trunc_tf32(a)) written beside the raw tile
 //   warp 1      MMA issuer   : 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8) per chunk into one of
 //                              two TMEM accumulators; tcgen05.commit frees the smem stage and
 //                              signals the epilogue
-//   warps 6-13  epilogue     : tcgen05.ld the chunk accumulator (thread = row x half of the columns), add
+//   warps 8-23  epilogue     : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add
 //                              into registers; after the last chunk: + bias, LayerNorm (row statistics
 //                              combined across the two column halves through smem), (Leaky)ReLU,
 //                              store out / xhat / rstd
@@ -31,7 +31,8 @@
 namespace sldm {
 using namespace tc;
 
-constexpr int kTcThreads = 512;   // 4 warpgroups: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} {epilogue x4}
+constexpr int kTcThreads = 768;   // 6 warpgroups: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 4
+constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
 constexpr int kTcStages = 3;
 constexpr int kTcBM = 128;
 constexpr int kTcAcc = 4;          // TMEM accumulator ring (one K chunk each)
@@ -86,24 +87,29 @@ struct EpiArgs {
   const CUtensorMap* tm_o0; const CUtensorMap* tm_o1;   // TMA store maps: FWD out / xhat, DGRAD dagg / dxroot
 };
 
-// Epilogue role: 8 warps (256 threads).  Thread (quadrant q, lane, half HF) owns tile row q*32+lane and the
-// columns [HF*16*NT, (HF+1)*16*NT).  FULL = (Fout == 32*NT): no column masking needed.
+// Epilogue role: 16 warps (512 threads).  Thread (quadrant q, lane, column quarter CQ) owns tile row q*32+lane and the
+// columns [CQ*8*NT, (CQ+1)*8*NT).  The role is latency bound per warp (TMEM round trips, smem parameter reads, store
+// fences), so it is spread over many warps.  FULL = (Fout == 32*NT): no column masking needed.
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
-template <int NT, int HF, bool FULL, int MODE>
+template <int NT, bool FULL, int MODE>
 __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
-  constexpr int HC = 16 * NT;
-  constexpr int C_LO = HF * HC;
+  constexpr int HC = 8 * NT;               // columns per thread
   constexpr int ACC_COLS = 32 * NT;
   long long* trace = a.trace;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3;
+  const int q = warp & 3;                  // TMEM lane quadrant of this warp
   const int rloc = q * 32 + lane;
-  const int ew = warp - 8;                 // 0..7
-  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + C_LO;
+  const int ew = warp - 8;                 // 0..15
+  const int cq = ew >> 2;                  // column quarter
+  const int c_lo = cq * HC;
+  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + c_lo;
   const float fF = (float)a.Fout;
   const int Fout = a.Fout;
+  const float* const bias = a.s_bias + c_lo;
+  const float* const gam = a.s_gamma + c_lo;
+  const float* const bet = a.s_beta + c_lo;
   uint32_t it = 0;
   for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
    for (int grp = 0; grp < a.ngroups; ++grp) {
@@ -114,30 +120,24 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
       mbar_wait(&a.bar_acc_full[ab], aph);
       if (tid == 256) TC_TRACE(9, it);
       tc_fence_after();
+      uint32_t rr[NT][8];
 #pragma unroll
-      for (int g0 = 0; g0 < NT; g0 += 2) {
-        uint32_t rr[2][16];
-        tmem_ld_32x16(tq + ab * ACC_COLS + g0 * 16, rr[0]);
-        if (g0 + 1 < NT) tmem_ld_32x16(tq + ab * ACC_COLS + (g0 + 1) * 16, rr[1]);
-        tmem_ld_wait();
-        if (g0 + 2 >= NT) {   // last load of this accumulator: values are in registers, release it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a.bar_acc_empty[ab]);
-          if (tid == 256) TC_TRACE(10, it);
-        }
+      for (int g0 = 0; g0 < NT; ++g0) tmem_ld_32x8(tq + ab * ACC_COLS + g0 * 8, rr[g0]);
+      tmem_ld_wait();
+      tc_fence_before();                   // values are in registers: release the accumulator
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a.bar_acc_empty[ab]);
+      if (tid == 256) TC_TRACE(10, it);
+      if (c == 0) {
 #pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          if (g0 + gg < NT) {
-            if (c == 0) {
+        for (int g0 = 0; g0 < NT; ++g0)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) z[(g0 + gg) * 16 + j] = __uint_as_float(rr[gg][j]);
-            } else {
+          for (int j = 0; j < 8; ++j) z[g0 * 8 + j] = __uint_as_float(rr[g0][j]);
+      } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) z[(g0 + gg) * 16 + j] += __uint_as_float(rr[gg][j]);
-            }
-          }
-        }
+        for (int g0 = 0; g0 < NT; ++g0)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[g0 * 8 + j] += __uint_as_float(rr[g0][j]);
       }
     }
     if (tid == 256) TC_TRACE(11, it - 1);
@@ -145,27 +145,27 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
     float rs = 1.f;            // FWD: rstd of the row;  DGRAD: unused
     float cnt = 1.f;           // DGRAD group 0: max(deg,1)
     if constexpr (MODE == MODE_FWD) {
-      // ---- bias + LayerNorm statistics; the two column halves of a row live in warps (8+q) and (12+q):
-      //      they meet on a 64-thread named barrier, nobody else waits ----
+      // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q:
+      //      they meet on a 128-thread named barrier, nobody else waits ----
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < HC; ++j) {
-        z[j] += a.s_bias[C_LO + j];
-        sum += (FULL || C_LO + j < Fout) ? z[j] : 0.f;
+        z[j] += bias[j];
+        sum += (FULL || c_lo + j < Fout) ? z[j] : 0.f;
       }
-      a.s_sum[HF * 128 + rloc] = sum;
-      named_bar_sync(2 + q, 64);
-      const float mean = __fdiv_rn(a.s_sum[rloc] + a.s_sum[128 + rloc], fF);
+      a.s_sum[cq * 128 + rloc] = sum;
+      named_bar_sync(2 + q, 128);
+      const float mean = __fdiv_rn((a.s_sum[rloc] + a.s_sum[128 + rloc]) + (a.s_sum[256 + rloc] + a.s_sum[384 + rloc]), fF);
       float var = 0.f;
 #pragma unroll
       for (int j = 0; j < HC; ++j) {
         z[j] -= mean;
-        var += (FULL || C_LO + j < Fout) ? z[j] * z[j] : 0.f;
+        var += (FULL || c_lo + j < Fout) ? z[j] * z[j] : 0.f;
       }
-      a.s_var[HF * 128 + rloc] = var;
-      named_bar_sync(2 + q, 64);
-      rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(a.s_var[rloc] + a.s_var[128 + rloc], fF) + a.eps));
-      if (row < a.N && a.rstd != nullptr && HF == 0) a.rstd[row] = rs;
+      a.s_var[cq * 128 + rloc] = var;
+      named_bar_sync(2 + q, 128);
+      rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn((a.s_var[rloc] + a.s_var[128 + rloc]) + (a.s_var[256 + rloc] + a.s_var[384 + rloc]), fF) + a.eps));
+      if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
 #pragma unroll
       for (int j = 0; j < HC; ++j) z[j] *= rs;      // z now holds xhat
       if (tid == 256) TC_TRACE(14, it - 1);
@@ -176,12 +176,12 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
         cnt = (float)deg;
       }
     }
-    // ---- stores.  Each warp owns a [32 rows x 16*NT columns] sub-tile and pushes it out 16 columns at a time:
-    //      4 conflict-free 128-bit smem stores per lane into a private 2 KB patch laid out as a 64B-swizzled
-    //      TMA box, then one cp.async.bulk.tensor store (the TMA engine clips rows >= N / columns >= Fout). ----
-    const uint32_t patch = smem_u32(a.s_stage + ew * 512);
-    const uint32_t prow = patch + lane * 64;
-    const int sw = (lane >> 1) & 3;
+    // ---- stores.  Each warp owns a [32 rows x 8*NT columns] sub-tile and pushes it out 8 columns at a time through a
+    //      private 1 KB patch ([32 rows][8 cols], plain layout: a lane writes its row's 32 bytes, conflict free) and one
+    //      cp.async.bulk.tensor store per patch (the TMA engine clips rows >= N / columns >= Fout).  While one warp
+    //      waits for the engine to drain its patch the other 15 keep going. ----
+    float* const patch = a.s_stage + ew * 256;
+    const uint32_t prow = smem_u32(patch) + lane * 32;
     const int grow0 = (int)(tile * kTcBM) + q * 32;       // first global row of this warp's sub-tile
     const int npass = (MODE == MODE_FWD) ? (a.xhat ? 2 : 1) : 1;
     for (int pass = 0; pass < npass; ++pass) {     // FWD: pass 0 = out (activation), pass 1 = xhat
@@ -190,15 +190,15 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
       else tm = grp == 0 ? a.tm_o0 : a.tm_o1;      // DGRAD: dagg / dxroot
 #pragma unroll
       for (int hb = 0; hb < NT; ++hb) {
-        if (!FULL && C_LO + hb * 16 >= Fout) break;
-        float v[16];
+        if (!FULL && c_lo + hb * 8 >= Fout) break;
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int jj = hb * 16 + j;
+        for (int j = 0; j < 8; ++j) {
+          const int jj = hb * 8 + j;
           if constexpr (MODE == MODE_FWD) {
             v[j] = z[jj];
             if (pass == 0) {
-              const float y = fmaf(v[j], a.s_gamma[C_LO + jj], a.s_beta[C_LO + jj]);
+              const float y = fmaf(v[j], gam[jj], bet[jj]);
               v[j] = y > 0.f ? y : a.slope * y;
             }
           } else {
@@ -207,13 +207,12 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
         }
         if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading the patch
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          sts128(prow + (uint32_t)((k ^ sw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        sts128(prow, make_float4(v[0], v[1], v[2], v[3]));
+        sts128(prow + 16, make_float4(v[4], v[5], v[6], v[7]));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(tm, a.s_stage + ew * 512, C_LO + hb * 16, grow0);
+          tma_store_2d(tm, patch, c_lo + hb * 8, grow0);
           tma_store_commit();
         }
       }
@@ -241,8 +240,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[128], s_gamma[128], s_beta[128];
-  __shared__ float s_sum[2][128], s_var[2][128];
-  __shared__ __align__(1024) float s_stage[8][512];   // one private 2 KB TMA-store patch ([32 rows][16 cols], 64B swizzle) per epilogue warp
+  __shared__ float s_sum[4][128], s_var[4][128];
+  __shared__ __align__(1024) float s_stage[16][256];  // one private 1 KB TMA-store patch ([32 rows][8 cols]) per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
@@ -270,7 +269,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     }
     for (int a = 0; a < kTcAcc; ++a) {
       mbar_init(&bar_acc_full[a], 1);
-      mbar_init(&bar_acc_empty[a], 8);
+      mbar_init(&bar_acc_empty[a], 16);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tm_agg);
@@ -285,7 +284,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
 
   // warpgroups 0 and 1 hand registers to the two epilogue warpgroups (setmaxnreg is per warpgroup)
   if (warp < 4) {
-   reg_dec<96>();
+   reg_dec<40>();
    if (warp == 0) {
     // ------------------------------------------------------------ TMA producer --
     if (lane == 0) {
@@ -347,7 +346,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     }
    }  // warps 2 (TMEM allocator) and 3 idle until teardown
   } else if (warp < 8) {
-    reg_dec<96>();
+    reg_dec<56>();
     // --------------------------------------------------------------- converter --
     const int r = tid - 128;  // tile row 0..127
     uint32_t it = 0;
@@ -373,13 +372,12 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       }
     }
   } else {
-    reg_inc<160>();
+    reg_inc<96>();
     // ---------------------------------------------------------------- epilogue --
     EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
                bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0], &s_stage[0][0], trace, &tm_o0, &tm_o1};
     const bool full = (Fout == 32 * NT);
-    if (warp < 12) { if (full) epilogue_role<NT, 0, true, MODE>(ea); else epilogue_role<NT, 0, false, MODE>(ea); }
-    else           { if (full) epilogue_role<NT, 1, true, MODE>(ea); else epilogue_role<NT, 1, false, MODE>(ea); }
+    if (full) epilogue_role<NT, true, MODE>(ea); else epilogue_role<NT, false, MODE>(ea);
   }
   tc_fence_before();
   __syncthreads();
@@ -399,7 +397,7 @@ constexpr int kWgStages = 2;
 constexpr int kWgFlush = 4;      // 32-row chunks per TMEM accumulator (128 rows)
 
 template <int NB>   // NB = ceil(Fin / 32) in 1..4
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_agg,
            const __grid_constant__ CUtensorMap tm_x, int64_t N, int Fin, int Fout, int chunks_per_cta,
            float* __restrict__ part) {
@@ -651,8 +649,8 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
   CUtensorMap mo0, mo1;
-  if ((rc = make_tmap_2d_f32(&mo0, out, (uint64_t)N, Fout, Fout, 32, 16, 2))) return rc;
-  if ((rc = make_tmap_2d_f32(&mo1, xhat ? xhat : out, (uint64_t)N, Fout, Fout, 32, 16, 2))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo0, out, (uint64_t)N, Fout, Fout, 32, 8, 3))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo1, xhat ? xhat : out, (uint64_t)N, Fout, Fout, 32, 8, 3))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
   return dispatch_tc<MODE_FWD>(ma, mx, mw, mo0, mo1, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
 }
@@ -671,8 +669,8 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
   if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fin, Fout, Fout, Fin, 32))) return rc;
   CUtensorMap mo0, mo1;
-  if ((rc = make_tmap_2d_f32(&mo0, dagg, (uint64_t)N, Fin, Fin, 32, 16, 2))) return rc;
-  if ((rc = make_tmap_2d_f32(&mo1, dxroot, (uint64_t)N, Fin, Fin, 32, 16, 2))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo0, dagg, (uint64_t)N, Fin, Fin, 32, 8, 3))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo1, dxroot, (uint64_t)N, Fin, Fin, 32, 8, 3))) return rc;
   TcProblem pb{N, Fout / 32, 1, 2, Fin};
   return dispatch_tc<MODE_DGRAD>(mz, mz, mw, mo0, mo1, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
 }
@@ -693,7 +691,7 @@ static int launch_wgrad(const CUtensorMap& mz, const CUtensorMap& ma, const CUte
     SLDM_CUDA(cudaFuncSetAttribute(k_wgrad_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_wgrad_tc<NB><<<grid, kTcThreads, smem, s>>>(mz, ma, mx, N, Fin, Fout, cpc, part);
+  k_wgrad_tc<NB><<<grid, kWgThreads, smem, s>>>(mz, ma, mx, N, Fin, Fout, cpc, part);
   SLDM_LAUNCH_CHECK("k_wgrad_tc");
   return SLDM_OK;
 }

@@ -106,6 +106,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // 32 lanes x 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -176,6 +184,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
 // ---- host: tensor maps ----------------------------------------------------------------
 // 2-D row-major fp32 matrix [rows][cols] (cols contiguous), box = box_rows x 32 fp32, 128-byte swizzle.
 int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                     uint32_t box_rows, uint32_t box_cols, int swizzle_atom32 = 0);  // 0: 128B, 1: 128B_ATOM_32B, 2: 64B
+                     uint32_t box_rows, uint32_t box_cols, int swizzle_atom32 = 0);  // 0: 128B, 1: 128B_ATOM_32B, 2: 64B, 3: none
 
 }  // namespace sldm
