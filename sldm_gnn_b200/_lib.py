@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsldm_sage.so")
+# SLDM_LIB_PATH: load another build of the same library (A/B timing of kernel variants); default is the in-tree build
+LIB_PATH = os.environ.get("SLDM_LIB_PATH") or os.path.join(_HERE, "lib", "libsldm_sage.so")
 
 OK, EINVAL, ESHAPE, ECUDA, EWORKSPACE, EUNSUPPORTED, ENODEVICE = range(7)
 HUB_DEGREE = 256

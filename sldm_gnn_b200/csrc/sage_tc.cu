@@ -13,18 +13,25 @@
 // fp64 (tools/tc_probe2.cu, K=128): max 3.2e-7 / rms 7.3e-8 versus 7.8e-7 / 1.1e-7 for a
 // sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
 //
-// Pipeline (one persistent CTA per SM, 768 threads, 128 rows x Fout per tile; setmaxnreg 40 / 56 / 96 of the 80 x 768 pool):
-//   warp 0      TMA producer : per K chunk (32 floats) loads A raw [128 x 32] (agg, then x) and the
-//                              pre-split weight tiles B_hi, B_lo [Fout x 32] into a 3-stage ring
-//   warps 4-7   converter    : A_lo = rna_tf32(a - trunc_tf32(a)) written beside the raw tile
-//   warp 1      MMA issuer   : 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8) per chunk into one of
-//                              two TMEM accumulators; tcgen05.commit frees the smem stage and
-//                              signals the epilogue
-//   warps 8-23  epilogue     : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add
-//                              into registers; after the last chunk: + bias, LayerNorm (row statistics
-//                              combined across the two column halves through smem), (Leaky)ReLU,
-//                              store out / xhat / rstd
-// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes); shared-memory bandwidth is the second limit.
+// Pipeline (one persistent CTA per SM, 768 threads, 128 rows x Fout per tile; setmaxnreg 40 / 72 / 88 of the 80 x 768 pool):
+//   warp 0        TMA producer : per K chunk (32 floats) loads A raw [128 x 32] (agg, then x) and the pre-split
+//                                weight tiles B_hi, B_lo [Fout x 32] into a 3-stage shared-memory ring
+//   warps 4-7     converter    : reads its row of the raw tile, splits every value into a_hi (what the tensor core
+//                                keeps) and a_lo = rna_tf32(a - a_hi) and parks both in TENSOR MEMORY with tcgen05.st
+//                                (lane = row, column = k; one 64-column slot per stage) -- the MMAs take A from TMEM,
+//                                so shared memory only carries the raw tile once and the weights
+//   warps 1, 3    MMA issuers  : alternate K chunks; 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8), A from TMEM, B
+//                                from smem descriptors, into one of two TMEM accumulators; tcgen05.commit frees the
+//                                smem stage + TMEM slot and signals the epilogue
+//   warps 8-23    epilogue     : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add into
+//                                registers; after the last chunk: + bias, LayerNorm (row statistics combined across
+//                                the four column quarters through smem), xhat out, (Leaky)ReLU, out -- through
+//                                swizzled full-row patches and cp.async.bulk.tensor stores
+// Tensor memory (512 columns): accumulators [0, 256), A slots [256, 448).
+// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  Measured (profiles/r01c): 15.5k cycles per tile = 6.3k epilogue
+// tail (statistics 1.9k, two TMA pushes that queue behind the operand loads) + 9.2k drain paced by the MMA stream
+// (two accumulators of look-ahead); the HBM floor is 11.4k.  An SS-mode variant (A_hi/A_lo in shared memory, four
+// accumulators, 8 epilogue warps) measured the same 0.40 ms; this one uses 48 KB less shared memory.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -35,7 +42,9 @@ constexpr int kTcThreads = 768;   // 6 warpgroups: {TMA, MMA, alloc, idle} {conv
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
 constexpr int kTcStages = 3;
 constexpr int kTcBM = 128;
-constexpr int kTcAcc = 4;          // TMEM accumulator ring (one K chunk each)
+constexpr int kTcAcc = 2;          // TMEM accumulator ring (one K chunk each), columns [0, 2*32*NT)
+constexpr int kTcPatchBytes = 16 * 4 * 1024;   // TMA-store patches: 16 epilogue warps x 4 x [32 rows][8 cols]
+constexpr int kTcACol0 = 256;      // TMEM columns of the A ring: kTcStages x {A_hi[32] | A_lo[32]}
 constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
 
 // One work item = (128-row tile, output group).  Its K loop runs over nsrc A sources x Kc 32-wide chunks.
@@ -146,23 +155,29 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
     float cnt = 1.f;           // DGRAD group 0: max(deg,1)
     if constexpr (MODE == MODE_FWD) {
       // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q:
-      //      they meet on a 128-thread named barrier, nobody else waits ----
-      float sum = 0.f;
+      //      they meet on a 128-thread named barrier, nobody else waits.  Sums run as four interleaved chains. ----
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < HC; ++j) {
-        z[j] += bias[j];
-        sum += (FULL || c_lo + j < Fout) ? z[j] : 0.f;
+      for (int j4 = 0; j4 < HC / 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j4);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          z[j] += bb[e];
+          ps[e] += (FULL || c_lo + j < Fout) ? z[j] : 0.f;
+        }
       }
-      a.s_sum[cq * 128 + rloc] = sum;
+      a.s_sum[cq * 128 + rloc] = (ps[0] + ps[1]) + (ps[2] + ps[3]);
       named_bar_sync(2 + q, 128);
       const float mean = __fdiv_rn((a.s_sum[rloc] + a.s_sum[128 + rloc]) + (a.s_sum[256 + rloc] + a.s_sum[384 + rloc]), fF);
-      float var = 0.f;
+      float pv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < HC; ++j) {
         z[j] -= mean;
-        var += (FULL || c_lo + j < Fout) ? z[j] * z[j] : 0.f;
+        pv[j & 3] += (FULL || c_lo + j < Fout) ? z[j] * z[j] : 0.f;
       }
-      a.s_var[cq * 128 + rloc] = var;
+      a.s_var[cq * 128 + rloc] = (pv[0] + pv[1]) + (pv[2] + pv[3]);
       named_bar_sync(2 + q, 128);
       rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn((a.s_var[rloc] + a.s_var[128 + rloc]) + (a.s_var[256 + rloc] + a.s_var[384 + rloc]), fF) + a.eps));
       if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
@@ -176,47 +191,57 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
         cnt = (float)deg;
       }
     }
-    // ---- stores.  Each warp owns a [32 rows x 8*NT columns] sub-tile and pushes it out 8 columns at a time through a
-    //      private 1 KB patch ([32 rows][8 cols], plain layout: a lane writes its row's 32 bytes, conflict free) and one
-    //      cp.async.bulk.tensor store per patch (the TMA engine clips rows >= N / columns >= Fout).  While one warp
-    //      waits for the engine to drain its patch the other 15 keep going. ----
-    float* const patch = a.s_stage + ew * 256;
-    const uint32_t prow = smem_u32(patch) + lane * 32;
+    // ---- stores.  Each warp owns a [32 rows x 8*NT columns] sub-tile and pushes it out through ONE private patch
+    //      ([32 rows][8*NT cols], rows of 32*NT bytes, TMA-swizzled so that the 128-bit writes of a quarter warp hit
+    //      distinct banks) with a single cp.async.bulk.tensor store: full 128-byte rows at NT = 4.  (Narrow 32-byte
+    //      boxes made the TMA engine the bottleneck: 4x the requests, 1.9k cycles to issue them; plain coalesced
+    //      global stores read back from the patch were slower still -- traces in profiles/r01c.)  FWD stores xhat
+    //      first and computes the activation in place while the engine drains the patch; the engine clips
+    //      rows >= N / columns >= Fout. ----
+    float* const patch = a.s_stage + ew * (4 * 256);
+    const uint32_t prow = smem_u32(patch) + lane * (32 * NT);
+    const uint32_t swz = (NT == 4) ? (uint32_t)(lane & 7) : (NT == 2) ? (uint32_t)((lane >> 1) & 3)
+                         : (NT == 1) ? (uint32_t)((lane >> 2) & 1) : 0u;
     const int grow0 = (int)(tile * kTcBM) + q * 32;       // first global row of this warp's sub-tile
-    const int npass = (MODE == MODE_FWD) ? (a.xhat ? 2 : 1) : 1;
-    for (int pass = 0; pass < npass; ++pass) {     // FWD: pass 0 = out (activation), pass 1 = xhat
-      const CUtensorMap* tm;
-      if constexpr (MODE == MODE_FWD) tm = pass == 0 ? a.tm_o0 : a.tm_o1;
-      else tm = grp == 0 ? a.tm_o0 : a.tm_o1;      // DGRAD: dagg / dxroot
+    const bool any_col = FULL || c_lo < Fout;
+    auto push = [&](const CUtensorMap* tm, int ev0) {
+      if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading the patch
+      __syncwarp();
+      if (tid == 256) TC_TRACE(ev0, it - 1);
 #pragma unroll
-      for (int hb = 0; hb < NT; ++hb) {
-        if (!FULL && c_lo + hb * 8 >= Fout) break;
-        float v[8];
+      for (int c = 0; c < 2 * NT; ++c)
+        sts128(prow + (((uint32_t)c ^ swz) << 4), make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
+      if (tid == 256) TC_TRACE(ev0 + 1, it - 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (tid == 256) TC_TRACE(ev0 + 2, it - 1);
+      if (lane == 0 && any_col) {
+        tma_store_2d(tm, patch, c_lo, grow0);
+        tma_store_commit();
+      }
+      if (tid == 256) TC_TRACE(ev0 + 3, it - 1);
+    };
+    if constexpr (MODE == MODE_FWD) {
+      if (a.xhat != nullptr) push(a.tm_o1, 20);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int jj = hb * 8 + j;
-          if constexpr (MODE == MODE_FWD) {
-            v[j] = z[jj];
-            if (pass == 0) {
-              const float y = fmaf(v[j], gam[jj], bet[jj]);
-              v[j] = y > 0.f ? y : a.slope * y;
-            }
-          } else {
-            v[j] = (grp == 0) ? __fdiv_rn(z[jj], cnt) : z[jj];
-          }
-        }
-        if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading the patch
-        __syncwarp();
-        sts128(prow, make_float4(v[0], v[1], v[2], v[3]));
-        sts128(prow + 16, make_float4(v[4], v[5], v[6], v[7]));
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(tm, patch, c_lo + hb * 8, grow0);
-          tma_store_commit();
+      for (int j4 = 0; j4 < HC / 4; ++j4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gam + 4 * j4);
+        const float4 b4 = *reinterpret_cast<const float4*>(bet + 4 * j4);
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y = fmaf(z[4 * j4 + e], gg[e], bb[e]);
+          z[4 * j4 + e] = y > 0.f ? y : a.slope * y;
         }
       }
-      if (tid == 256 && pass == 0) TC_TRACE(19, it - 1);
+      if (tid == 256) TC_TRACE(19, it - 1);
+      push(a.tm_o0, 24);
+    } else {
+      if (grp == 0) {
+#pragma unroll
+        for (int j = 0; j < HC; ++j) z[j] = __fdiv_rn(z[j], cnt);
+      }
+      push(grp == 0 ? a.tm_o0 : a.tm_o1, 24);      // DGRAD: dagg / dxroot
     }
    }
   }
@@ -239,16 +264,16 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   __shared__ uint64_t bar_full[kTcStages], bar_conv[kTcStages], bar_empty[kTcStages];
   __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[128], s_gamma[128], s_beta[128];
+  __shared__ __align__(16) float s_bias[128], s_gamma[128], s_beta[128];
   __shared__ float s_sum[4][128], s_var[4][128];
-  __shared__ __align__(1024) float s_stage[16][256];  // one private 1 KB TMA-store patch ([32 rows][8 cols]) per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
   const uint32_t b_bytes = (uint32_t)Fout * 128;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t stage_bytes = a_bytes + 2 * b_bytes;   // raw A tile | B_hi | B_lo  (A_hi / A_lo live in tensor memory)
   constexpr int ACC_COLS = 32 * NT;
-  constexpr uint32_t TMEM_COLS = (kTcAcc * ACC_COLS <= 128) ? 128 : ((kTcAcc * ACC_COLS <= 256) ? 256 : 512);
+  constexpr uint32_t TMEM_COLS = 512;                   // accumulators [0, 256) + A ring [256, 256 + 64*kTcStages)
+  static_assert(kTcAcc * 128 <= kTcACol0 && kTcACol0 + 64 * kTcStages <= 512, "TMEM budget");
 
   const int half = pb.Kc;
   const int nchunks = pb.nsrc * pb.Kc;
@@ -303,21 +328,28 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
             const int k0 = (c - src * half) * 32;
             const int wrow = 2 * (g * pb.nsrc + src) * Fout;
             tma_load_2d(st, src == 0 ? &tm_agg : &tm_x, k0, row0, &bar_full[s]);
-            tma_load_2d(st + 2 * a_bytes, &tm_w, k0, wrow, &bar_full[s]);
-            tma_load_2d(st + 2 * a_bytes + b_bytes, &tm_w, k0, wrow + Fout, &bar_full[s]);
+            // (re-streaming the weight tiles from L2 for every chunk is NOT the limiter: skipping these two loads
+            //  changed the kernel time by < 5% on B200)
+            tma_load_2d(st + a_bytes, &tm_w, k0, wrow, &bar_full[s]);
+            tma_load_2d(st + a_bytes + b_bytes, &tm_w, k0, wrow + Fout, &bar_full[s]);
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer --
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------- MMA issuers --
+    // Two issuing threads alternate K chunks (warp 1: even, warp 3: odd).  A chunk has its own accumulator, smem stage
+    // and TMEM A slot, so the two streams are independent; while one thread sits in the barrier waits of its next
+    // chunk the tensor pipe is fed by the other (one issuer left ~35% bubbles: profiles/r01c trace).
     if (lane == 0) {
+      const uint32_t my_parity = (warp == 3) ? 1u : 0u;
       const uint32_t idesc = make_idesc_tf32(kTcBM, Fout, 0, 0);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < ngroups * nchunks; ++c, ++it) {
           const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
           const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
+          if ((it & 1u) != my_parity) continue;
           TC_TRACE(2, it);
           mbar_wait(&bar_acc_empty[ab], aph ^ 1);   // epilogue drained this accumulator (two chunks ago)
           TC_TRACE(3, it);
@@ -325,28 +357,28 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           TC_TRACE(4, it);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          // descriptors differ only in the 14-bit start-address field (bytes >> 4)
-          const uint64_t d_a_hi = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t d_a_lo = d_a_hi + (a_bytes >> 4);
-          const uint64_t d_b_hi = d_a_hi + ((2 * a_bytes) >> 4);
+          // B descriptors differ only in the 14-bit start-address field (bytes >> 4); A comes from tensor memory
+          const uint64_t d_b_hi = make_smem_desc_sw128(sa + a_bytes, 16, 1024);
           const uint64_t d_b_lo = d_b_hi + (b_bytes >> 4);
+          const uint32_t a_hi = tmem_base + kTcACol0 + s * 64;
+          const uint32_t a_lo = a_hi + 32;
           const uint32_t d = tmem_base + ab * ACC_COLS;
           // small products first: the accumulator rounds toward zero
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_lo + 2 * ks, d_b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_lo + 8 * ks, d_b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 2 * ks, d_b_lo + 2 * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_lo + 2 * ks, idesc, 1u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 2 * ks, d_b_hi + 2 * ks, idesc, 1u);
-          mma_commit(&bar_empty[s]);       // smem stage reusable once these MMAs have read it
+          for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_hi + 2 * ks, idesc, 1u);
+          mma_commit(&bar_empty[s]);       // smem stage and TMEM A slot reusable once these MMAs have read them
           mma_commit(&bar_acc_full[ab]);   // chunk accumulator complete
           TC_TRACE(5, it);
         }
       }
     }
-   }  // warps 2 (TMEM allocator) and 3 idle until teardown
+   }  // warp 2 (TMEM allocator) idles until teardown
   } else if (warp < 8) {
-    reg_dec<56>();
+    reg_dec<72>();
     // --------------------------------------------------------------- converter --
     const int r = tid - 128;  // tile row 0..127
     uint32_t it = 0;
@@ -356,26 +388,41 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
         mbar_wait(&bar_full[s], ph);
         if (tid == 128) TC_TRACE(6, it);
         const uint32_t a_raw = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
-        float4 v[8];
+        // this thread's row of the chunk: split every value into the part the tensor core keeps (hi) and the
+        // rounded remainder (lo) and park both in the stage's tensor-memory slot (lane = row, column = k).
+        // The slot is free: TMA only refilled this stage after the MMAs that read the slot had committed.
+        const uint32_t t_hi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcACol0 + s * 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = lds128(a_raw + (uint32_t)((j ^ (r & 7)) << 4));
+        for (int h = 0; h < 2; ++h) {
+          float4 v[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 l;
-          l.x = tf32_lo(v[j].x); l.y = tf32_lo(v[j].y); l.z = tf32_lo(v[j].z); l.w = tf32_lo(v[j].w);
-          sts128(a_raw + a_bytes + (uint32_t)((j ^ (r & 7)) << 4), l);
+          for (int j = 0; j < 4; ++j) v[j] = lds128(a_raw + (uint32_t)(((4 * h + j) ^ (r & 7)) << 4));
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * j + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
+              lo[4 * j + e] = __float_as_uint(tf32_lo(f[e]));
+            }
+          }
+          tmem_st_32x16(t_hi + 16 * h, hi);
+          tmem_st_32x16(t_hi + 32 + 16 * h, lo);
         }
-        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_conv[s]);
         if (tid == 128) TC_TRACE(7, it);
       }
     }
   } else {
-    reg_inc<96>();
+    reg_inc<88>();
     // ---------------------------------------------------------------- epilogue --
     EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
-               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0], &s_stage[0][0], trace, &tm_o0, &tm_o1};
+               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0],
+               reinterpret_cast<float*>(smem + (size_t)kTcStages * stage_bytes), trace, &tm_o0, &tm_o1};
     const bool full = (Fout == 32 * NT);
     if (full) epilogue_role<NT, true, MODE>(ea); else epilogue_role<NT, false, MODE>(ea);
   }
@@ -582,11 +629,11 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
                      const CUtensorMap& mo1, const TcProblem& pb,
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
-  const size_t smem = (size_t)kTcStages * (2 * kTcBM * 128 + 2 * (size_t)pb.Nout * 128) + 1024;
+  const size_t smem = (size_t)kTcStages * (kTcBM * 128 + 2 * (size_t)pb.Nout * 128) + kTcPatchBytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     SLDM_CUDA(cudaFuncSetAttribute(k_sage_tc<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kTcStages * (2 * kTcBM * 128 + 2 * 128 * 128) + 1024));
+                                   kTcStages * (kTcBM * 128 + 2 * 128 * 128) + kTcPatchBytes + 1024));
     attr_done = true;
   }
   const int64_t ntiles = ceil_div<int64_t>(pb.N, kTcBM);
@@ -607,7 +654,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     FILE* f = fopen(tf, "w");
     if (f) {
       fprintf(f, "# cycles from t0; ev: 0 tma_wait_empty 1 tma_got_empty 2 mma_top 3 mma_accempty 4 mma_conv 5 mma_committed "
-                 "6 conv_full 7 conv_done 8 epi_wait 9 epi_accfull 10 epi_released 11 epi_finalize 14 stats_done 19 pass0_done\n");
+                 "6 conv_full 7 conv_done 8 epi_wait 9 epi_accfull 10 epi_released 11 epi_finalize 14 stats_done 19 act_done "
+                 "20-23 / 24-27 push: waited, filled, fenced, issued\n");
       const long long t0 = h[0];
       for (int i = 0; i < kTraceIts; ++i) {
         fprintf(f, "%d", i);
@@ -633,6 +681,9 @@ static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUten
   }
 }
 
+// swizzle mode of the epilogue store patches: rows of 32*NT bytes (make_tmap_2d_f32: 0 = 128B, 2 = 64B, 4 = 32B, 3 = none)
+static int store_swizzle(int nt) { return nt == 4 ? 0 : (nt == 2 ? 2 : (nt == 1 ? 4 : 3)); }
+
 int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
                               const float* W_l, const float* b_l, const float* W_r,
                               const float* ln_w, const float* ln_b, float eps, float slope,
@@ -649,8 +700,9 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
   CUtensorMap mo0, mo1;
-  if ((rc = make_tmap_2d_f32(&mo0, out, (uint64_t)N, Fout, Fout, 32, 8, 3))) return rc;
-  if ((rc = make_tmap_2d_f32(&mo1, xhat ? xhat : out, (uint64_t)N, Fout, Fout, 32, 8, 3))) return rc;
+  const int nt = ceil_div(Fout, 32);
+  if ((rc = make_tmap_2d_f32(&mo0, out, (uint64_t)N, Fout, Fout, 32, 8 * nt, store_swizzle(nt)))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo1, xhat ? xhat : out, (uint64_t)N, Fout, Fout, 32, 8 * nt, store_swizzle(nt)))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
   return dispatch_tc<MODE_FWD>(ma, mx, mw, mo0, mo1, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
 }
@@ -669,8 +721,9 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
   if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fin, Fout, Fout, Fin, 32))) return rc;
   CUtensorMap mo0, mo1;
-  if ((rc = make_tmap_2d_f32(&mo0, dagg, (uint64_t)N, Fin, Fin, 32, 8, 3))) return rc;
-  if ((rc = make_tmap_2d_f32(&mo1, dxroot, (uint64_t)N, Fin, Fin, 32, 8, 3))) return rc;
+  const int nt = ceil_div(Fin, 32);
+  if ((rc = make_tmap_2d_f32(&mo0, dagg, (uint64_t)N, Fin, Fin, 32, 8 * nt, store_swizzle(nt)))) return rc;
+  if ((rc = make_tmap_2d_f32(&mo1, dxroot, (uint64_t)N, Fin, Fin, 32, 8 * nt, store_swizzle(nt)))) return rc;
   TcProblem pb{N, Fout / 32, 1, 2, Fin};
   return dispatch_tc<MODE_DGRAD>(mz, mz, mw, mo0, mo1, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
 }

@@ -124,6 +124,17 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+// registers -> tensor memory: thread i of the warp writes lane (base+i), 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -137,6 +148,17 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same with the A operand read from tensor memory (lane = row of the M=128 tile, one 32-bit column per K element)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // all previously issued MMAs of this thread arrive on `bar` when they complete
@@ -184,6 +206,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
 // ---- host: tensor maps ----------------------------------------------------------------
 // 2-D row-major fp32 matrix [rows][cols] (cols contiguous), box = box_rows x 32 fp32, 128-byte swizzle.
 int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                     uint32_t box_rows, uint32_t box_cols, int swizzle_atom32 = 0);  // 0: 128B, 1: 128B_ATOM_32B, 2: 64B, 3: none
+                     uint32_t box_rows, uint32_t box_cols, int swizzle_atom32 = 0);  // 0: 128B, 1: 128B_ATOM_32B, 2: 64B, 3: none, 4: 32B
 
 }  // namespace sldm

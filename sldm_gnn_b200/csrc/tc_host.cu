@@ -38,7 +38,8 @@ int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_atom32 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                   : (swizzle_atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
-                  : (swizzle_atom32 == 3 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B)),
+                  : (swizzle_atom32 == 3 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                  : (swizzle_atom32 == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B))),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SLDM_REQUIRE(r == CUDA_SUCCESS, SLDM_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
