@@ -77,6 +77,25 @@ def make_inputs(wl, seed):
     return x, ei, N, graphs
 
 
+# CUDA kernel behind each timed group, and how many times it runs per layer and step (fwd+bwd)
+KERNEL_NAMES = {"segment_mean_fwd": "k_segment_rows_lean", "project_ln_act_fwd": "k_sage_tc<NT, MODE_FWD>",
+                "segment_sum_bwd": "k_segment_rows_lean (transpose CSR)", "ln_bwd": "k_ln_bwd_rows",
+                "csr_build": "k_convert + k_digit_hist + k_onesweep_pass x3 + k_rowptr_from_sorted",
+                "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean"}
+KERNEL_LAUNCHES_PER_LAYER = {"segment_mean_fwd": 1, "project_ln_act_fwd": 1, "segment_sum_bwd": 1}
+
+
+def measured_traffic(workload, group):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if group is None or not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path)).get(workload, {}).get(group)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ byte models --
 def layer_bytes_fwd_bwd(N, E, Fin, Fout, s=4):
     """2E(Fin s + 4) + N s (6 Fin + 5 Fout) + 28 N per layer, fwd+bwd (training)."""
@@ -309,7 +328,7 @@ def main_ours(args, wl):
     # 10-step run measured 6.1 ms/step cold against 4.5 warm).  The per-kernel-group timing runs first on every rank
     # (~0.5 s of the same kernels, untimed for the headline), then the W warm-up steps, then the K timed steps.
     peak_gbs, peak_src = measured_peaks()
-    kern = time_kernels(blk, batches[0]["x"].detach(), batches[0]["ei"], N, E, hdims, peak_gbs)
+    kern = None if args.skip_kernel_timing else time_kernels(blk, batches[0]["x"].detach(), batches[0]["ei"], N, E, hdims, peak_gbs)
     for i in range(max(3, args.warmup)):
         step(batches[i % 2])
     barrier()
@@ -381,7 +400,14 @@ def main_ours(args, wl):
         value = E_all * L / (ms_step * 1e-3)
         e2e_ms = e2e_ms_total / e2e_steps
         step_bytes = sum(layer_bytes_fwd_bwd(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
-        top = max((k for k in kern if k != "csr_build"), key=lambda k: kern[k]["ms"])
+        if kern is None:
+            kern, top = {}, None
+        else:
+            # the dominant KERNEL: the largest single-kernel group (layer_backward is a sequence of kernels and is
+            # reported under "kernels" only)
+            single = [k for k in kern if k not in ("csr_build", "layer_backward")]
+            top = max(single, key=lambda k: kern[k]["ms"] * KERNEL_LAUNCHES_PER_LAYER[k])
+        traffic = measured_traffic(args.workload, top)
         line = {
             "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
@@ -395,9 +421,11 @@ def main_ours(args, wl):
                     "graphs_per_sec": graphs_all / (e2e_ms * 1e-3)},
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
-            "roofline": {"bound": "hbm", "kernel": top, "achieved": kern[top]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                         "frac": kern[top]["frac_hbm"], "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": kern[top]["algorithmic_bytes"], "ms_per_launch": kern[top]["ms"]},
+            "roofline": None if top is None else {
+                "bound": "hbm", "kernel": top, "cuda_kernel": KERNEL_NAMES[top], "achieved": kern[top]["gbs"], "peak": peak_gbs,
+                "unit": "GB/s", "frac": kern[top]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kern[top]["algorithmic_bytes"], "ms_per_launch": kern[top]["ms"],
+                "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None},
             "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / ms_step / 1e6,
                               "peak": peak_gbs, "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / peak_gbs,
                               "model": "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)"},
@@ -422,6 +450,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="batch")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-kernel-timing", action="store_true",
+                    help="skip the per-kernel-group timing (used for the ncu launch list: only whole steps are launched)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

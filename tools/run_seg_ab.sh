@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
 {
-for F in 128 96 64 32; do for L in 0 4 8; do
-SLDM_SEG_LEAN=$L python tools/seg_ab.py batch $F 2>&1 | tail -1
-done; done
-for L in 0 4 8; do SLDM_SEG_LEAN=$L python tools/seg_ab.py c4 128 2>&1 | tail -1; done
-} > gpurun_out/seg_ab3.log 2>&1
-cat gpurun_out/seg_ab3.log
+for C in 8 6 5 4 3 2; do
+SLDM_SEG_CTAS=$C python tools/seg_ab.py batch 128 2>&1 | tail -1 | sed "s/^/ctas=$C /"
+done
+for C in 8 4; do SLDM_SEG_CTAS=$C python tools/seg_ab.py c4 128 2>&1 | tail -1 | sed "s/^/ctas=$C /"; done
+for C in 8 4; do SLDM_SEG_CTAS=$C python tools/seg_ab.py batch 64 2>&1 | tail -1 | sed "s/^/ctas=$C /"; done
+} > gpurun_out/seg_ab4.log 2>&1
+cat gpurun_out/seg_ab4.log
