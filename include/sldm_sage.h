@@ -99,6 +99,13 @@ int     sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
                        int32_t* csr, void* workspace, int64_t workspace_bytes,
                        sldm_stream_t stream);
 
+/* Same build from two separate int64 rows.  edge_src == NULL means source ids 0..E-1: the result is then a
+ * membership list (row k of rowptr_dst / col_src = the positions e with edge_dst[e] == k, ascending), which is how
+ * the graph readout below obtains the nodes of every graph from PyG's `batch` vector. */
+int     sldm_csr_build_pairs(const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int64_t N,
+                             int32_t* csr, void* workspace, int64_t workspace_bytes,
+                             sldm_stream_t stream);
+
 /* ---- segment mean (the aggregation alone) --------------------------------
  * out[i,:] = (sum over k in segment i of src[col[k],:]) / max(deg_i,1)   (mean=1)
  * out[i,:] = addend[i,:] + sum ...                                       (mean=0)
@@ -160,6 +167,24 @@ int     sldm_sage_layer_backward(const float* dout, const float* x, const float*
                                  float* dz, float* dagg, float* dxroot,
                                  void* workspace, int64_t workspace_bytes,
                                  sldm_stream_t stream);
+
+/* ---- graph readout (the consumer of the SageBlock output) -----------------
+ * Replaces global_mean_pool / global_max_pool of PyG 2.7.0 (nn/pool/glob.py -> utils/_scatter.py::scatter with
+ * reduce='mean' / 'max') as used at src/models/grusage.py:113-120 (choice) and :185 (x = self.global_pool(x, batch)):
+ *   mean[g,:] = sum_{i: batch[i]=g} x[i,:] / max(count_g,1)      max[g,:] = max_{i: batch[i]=g} x[i,:]
+ *   empty graph -> 0 in both.  'double' = [mean | max] concatenated: pass the two halves of one [G,2F] buffer, ld = 2F.
+ * csr is the membership CSR: sldm_csr_build_pairs(NULL, batch, N, csr_nodes = max(N,G), ...), so `batch` need not be
+ * sorted.  backward: dx[i,:] = dmean[g,:]/max(count_g,1) + [x[i,:]==max[g,:]] * dmax[g,:]/ties[g,:]  (torch's amax
+ * backward shares the gradient evenly among tied maxima).  Either output / gradient view may be NULL.
+ */
+int64_t sldm_readout_workspace_bytes(int64_t G, int32_t F);
+int     sldm_readout_forward(const float* x, int64_t N, int32_t F, const int32_t* csr, int64_t csr_nodes,
+                             int64_t G, float* out_mean, float* out_max, int64_t ld, sldm_stream_t stream);
+int     sldm_readout_backward(const float* x, int64_t N, int32_t F, const int64_t* batch,
+                              const int32_t* csr, int64_t csr_nodes, int64_t G,
+                              const float* out_max, int64_t ld_max,
+                              const float* dmean, const float* dmax, int64_t ld_d,
+                              float* dx, void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
 
 /* ---- whole block, host buffers in / host buffers out -----------------------
  * For hosts that own no device memory (the reference-side stub in

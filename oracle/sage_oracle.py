@@ -158,3 +158,33 @@ def csr_oracle(edge_index: torch.Tensor, num_nodes: int):
     rp_d, col_s = one(dst, src)
     rp_s, col_d = one(src, dst)
     return rp_d, col_s, rp_s, col_d
+
+
+# ---------------------------------------------------------------- graph readout --
+# Restates torch_geometric 2.7.0 nn/pool/glob.py as called at src/models/grusage.py:113-120,185:
+#   global_mean_pool(x, batch, size) = scatter(x, batch, dim=-2, dim_size=size, reduce='mean')
+#   global_max_pool(x, batch, size)  = scatter(x, batch, dim=-2, dim_size=size, reduce='max')
+#   batch is None -> x.mean(dim=-2, keepdim=True) / x.max(dim=-2, keepdim=True)[0]
+# and utils/_scatter.py::scatter: 'mean' as above (count, clamp(min=1), scatter_add_, divide);
+# 'max' = src.new_zeros(size).scatter_reduce_(dim, index, src, reduce='amax', include_self=False)
+# (rows that receive nothing keep the 0 they were created with); dim_size = int(index.max()) + 1 when None.
+def global_mean_pool_oracle(x, batch, size=None):
+    if batch is None:
+        return x.mean(dim=-2, keepdim=True)
+    if size is None:
+        size = int(batch.max()) + 1 if batch.numel() > 0 else 0
+    return scatter_mean(x, batch, size)
+
+
+def global_max_pool_oracle(x, batch, size=None):
+    if batch is None:
+        return x.max(dim=-2, keepdim=True)[0]
+    if size is None:
+        size = int(batch.max()) + 1 if batch.numel() > 0 else 0
+    index = batch.view(-1, 1).expand(-1, x.size(1))
+    return x.new_zeros((size, x.size(1))).scatter_reduce_(0, index, x, reduce="amax", include_self=False)
+
+
+def global_double_pool_oracle(x, batch, size=None):
+    """src/models/grusage.py:119."""
+    return torch.cat([global_mean_pool_oracle(x, batch, size), global_max_pool_oracle(x, batch, size)], dim=1)

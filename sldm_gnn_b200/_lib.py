@@ -38,6 +38,7 @@ _PROTOS = {
     "sldm_csr_layout": (C.c_int, [_i64, _i64, C.POINTER(_i64)]),
     "sldm_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "sldm_csr_build": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p]),
+    "sldm_csr_build_pairs": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _p]),
     "sldm_segment_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "sldm_segment_reduce": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p]),
     "sldm_sage_project_workspace_bytes": (_i64, [_i64, _i32, _i32]),
@@ -49,6 +50,9 @@ _PROTOS = {
     "sldm_sage_layer_bwd_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),
     "sldm_sage_layer_backward": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _f,
                                            _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "sldm_readout_workspace_bytes": (_i64, [_i64, _i32]),
+    "sldm_readout_forward": (C.c_int, [_p, _i64, _i32, _p, _i64, _i64, _p, _p, _i64, _p]),
+    "sldm_readout_backward": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _p, _p, _i64, _p]),
     "sldm_sage_block_forward_host": (C.c_int, [_p, _p, _i64, _i64, C.POINTER(_i32), _i32, C.POINTER(_p), _f, _f, _p]),
     "sldm_sage_block_train_host": (C.c_int, [_p, _p, _i64, _i64, C.POINTER(_i32), _i32, C.POINTER(_p), _f, _f,
                                              _p, _p, _p, C.POINTER(_p)]),

@@ -147,15 +147,15 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* spin
 // int64 [2,E] -> two int32 arrays; range check (reported through meta, indices clamped) and the two
 // "already non-decreasing" flags.  Pure streaming: 16E bytes read, 8E written.
 __global__ void __launch_bounds__(256)
-k_convert(const int64_t* __restrict__ ei, int64_t E, int32_t N,
+k_convert(const int64_t* __restrict__ ei_src, const int64_t* __restrict__ ei_dst, int64_t E, int32_t N,
           int32_t* __restrict__ src32, int32_t* __restrict__ dst32, int32_t* __restrict__ meta) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool bad = false, us = false, ud = false;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
-    int64_t s = ei[e], d = ei[E + e];
+    int64_t s = ei_src ? ei_src[e] : e, d = ei_dst[e];   // ei_src == NULL: source ids are 0..E-1 (membership lists)
     if (e > 0) {
-      us |= ei[e - 1] > s;
-      ud |= ei[E + e - 1] > d;
+      us |= ei_src != nullptr && ei_src[e - 1] > s;
+      ud |= ei_dst[e - 1] > d;
     }
     if (s < 0 || s >= N || d < 0 || d >= N) {
       bad = true;  // reported through meta; clamped so nothing goes out of bounds
@@ -509,13 +509,20 @@ extern "C" int64_t sldm_csr_workspace_bytes(int64_t N, int64_t E) {
 extern "C" int sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
                               int32_t* csr, void* workspace, int64_t workspace_bytes,
                               sldm_stream_t stream) {
+  SLDM_REQUIRE(E == 0 || edge_index != nullptr, SLDM_EINVAL, "sldm_csr_build: edge_index is NULL");
+  return sldm_csr_build_pairs(edge_index, edge_index ? edge_index + E : nullptr, E, N, csr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int sldm_csr_build_pairs(const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int64_t N,
+                                    int32_t* csr, void* workspace, int64_t workspace_bytes,
+                                    sldm_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t kMax = ((int64_t)1 << 31) - ((int64_t)1 << 20);
   SLDM_REQUIRE(N >= 0 && E >= 0, SLDM_EINVAL, "sldm_csr_build: negative N (%lld) or E (%lld)", (long long)N, (long long)E);
   SLDM_REQUIRE(N < kMax && E < kMax, SLDM_EUNSUPPORTED, "sldm_csr_build: N=%lld / E=%lld exceed the int32 CSR", (long long)N, (long long)E);
   SLDM_REQUIRE(!(E > 0 && N == 0), SLDM_EINVAL, "sldm_csr_build: %lld edges but 0 nodes", (long long)E);
   SLDM_REQUIRE(csr != nullptr, SLDM_EINVAL, "sldm_csr_build: csr is NULL");
-  SLDM_REQUIRE(E == 0 || edge_index != nullptr, SLDM_EINVAL, "sldm_csr_build: edge_index is NULL");
+  SLDM_REQUIRE(E == 0 || edge_dst != nullptr, SLDM_EINVAL, "sldm_csr_build: the destination row is NULL");
   CsrLayout L = csr_layout(N, E);
   CsrWs W = csr_ws_layout(N, E);
   SLDM_REQUIRE(E == 0 || (workspace != nullptr && workspace_bytes >= W.total), SLDM_EWORKSPACE,
@@ -549,7 +556,7 @@ extern "C" int sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
 
   {
     int grid = (int)std::min<int64_t>(ceil_div<int64_t>(E, 256 * 4), (int64_t)num_sms() * 8);
-    k_convert<<<grid, 256, 0, s>>>(edge_index, E, (int32_t)N, src32, dst32, meta);
+    k_convert<<<grid, 256, 0, s>>>(edge_src, edge_dst, E, (int32_t)N, src32, dst32, meta);
     SLDM_LAUNCH_CHECK("k_convert");
   }
   int rc;

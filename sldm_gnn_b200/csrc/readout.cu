@@ -1,0 +1,212 @@
+// readout.cu -- graph-level readout that consumes the SageBlock output:
+//   global_mean_pool(x, batch), global_max_pool(x, batch) and their concatenation ('double'),
+//   src/models/grusage.py:113-120 (choice of pooling) and :185 (x = self.global_pool(x, batch)).
+// PyG 2.7.0 semantics restated (nn/pool/glob.py + utils/_scatter.py):
+//   mean[g,:] = sum_{i: batch[i]=g} x[i,:] / max(count_g, 1)          (empty graph -> 0)
+//   max[g,:]  = max_{i: batch[i]=g} x[i,:]   via scatter_reduce_(amax, include_self=False) into zeros
+//               (empty graph -> 0)
+//   backward : dx[i,:] = dmean[g,:]/max(count_g,1) + [x[i,:] == max[g,:]] * dmax[g,:] / ties[g,:]
+//               (torch's amax backward shares the gradient evenly among the elements equal to the maximum)
+// The reference path does a host sync (batch.max().item()) and four scatter passes; here the graph segments come
+// from the same device-side CSR machinery as the aggregation (members of graph g = one CSR row, in node order, so an
+// unsorted batch vector is handled too), one CTA per graph streams its rows once for both statistics, and the backward
+// is two streaming kernels.  No atomics: every result is deterministic.
+//
+// Bound: HBM.  Algorithmic bytes: forward N*F*4 read + G*2F*4 written; backward 2*N*F*4 read + N*F*4 written.
+#include "common.cuh"
+#include <algorithm>
+#include <math.h>
+
+namespace sldm {
+
+constexpr int kRoThreads = 256;
+constexpr int kRoWarps = kRoThreads / 32;
+
+// out_mean / out_max: [G, ld] row-major views (ld >= F), either may be NULL.
+// members[ptr[g] .. ptr[g+1]) are the node ids of graph g (ascending: the CSR build is stable).
+template <bool VEC>
+__global__ void __launch_bounds__(kRoThreads)
+k_readout_fwd(const float* __restrict__ x, int32_t F, const int32_t* __restrict__ ptr,
+              const int32_t* __restrict__ members, float* __restrict__ out_mean, float* __restrict__ out_max,
+              int64_t ld) {
+  extern __shared__ float sm[];                 // [kRoWarps][2][F]
+  const int g = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int beg = __ldg(ptr + g), end = __ldg(ptr + g + 1);
+  const int W = VEC ? 4 : 1;                    // floats per lane per column step
+  for (int c0 = 0; c0 < F; c0 += 32 * W * 2) { // two column slices per lane per sweep
+    float s[2][4], m[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s[q][e] = 0.f; m[q][e] = -INFINITY; }
+    for (int i = beg + warp; i < end; i += kRoWarps) {
+      const float* row = x + (int64_t)__ldg(members + i) * F;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = c0 + (q * 32 + lane) * W;
+        if (c < F) {
+          if (VEC) {
+            const float4 v = ldg4(row + c);
+            s[q][0] += v.x; s[q][1] += v.y; s[q][2] += v.z; s[q][3] += v.w;
+            m[q][0] = fmaxf(m[q][0], v.x); m[q][1] = fmaxf(m[q][1], v.y);
+            m[q][2] = fmaxf(m[q][2], v.z); m[q][3] = fmaxf(m[q][3], v.w);
+          } else {
+            const float v = __ldg(row + c);
+            s[q][0] += v; m[q][0] = fmaxf(m[q][0], v);
+          }
+        }
+      }
+    }
+    // combine the 8 warps in warp order (fixed: deterministic)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = (q * 32 + lane) * W;       // column inside this sweep
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (e < W && c0 + c + e < F) {
+          sm[(warp * 2 + 0) * F + c0 + c + e] = s[q][e];
+          sm[(warp * 2 + 1) * F + c0 + c + e] = m[q][e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = end - beg;
+  const float fc = (float)(cnt < 1 ? 1 : cnt);
+  for (int c = threadIdx.x; c < F; c += kRoThreads) {
+    float s = sm[c], m = sm[F + c];
+#pragma unroll
+    for (int w = 1; w < kRoWarps; ++w) { s += sm[(w * 2) * F + c]; m = fmaxf(m, sm[(w * 2 + 1) * F + c]); }
+    if (out_mean) out_mean[(int64_t)g * ld + c] = __fdiv_rn(s, fc);
+    if (out_max) out_max[(int64_t)g * ld + c] = cnt > 0 ? m : 0.f;
+  }
+}
+
+// NaN handling: fmaxf drops NaNs while torch's amax propagates them; features reaching the readout are finite
+// (LayerNorm + (Leaky)ReLU outputs), the parity tests use finite inputs.
+
+// ties[g,c] = #{i in graph g : x[i,c] == max[g,c]}
+__global__ void __launch_bounds__(kRoThreads)
+k_readout_ties(const float* __restrict__ x, int32_t F, const int32_t* __restrict__ ptr,
+               const int32_t* __restrict__ members, const float* __restrict__ out_max, int64_t ld,
+               float* __restrict__ ties) {
+  extern __shared__ float sm[];                 // [kRoWarps][F]
+  const int g = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int beg = __ldg(ptr + g), end = __ldg(ptr + g + 1);
+  for (int c = lane; c < F; c += 32) {
+    const float mx = __ldg(out_max + (int64_t)g * ld + c);
+    float n = 0.f;
+    for (int i = beg + warp; i < end; i += kRoWarps)
+      n += (__ldg(x + (int64_t)__ldg(members + i) * F + c) == mx) ? 1.f : 0.f;
+    sm[warp * F + c] = n;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += kRoThreads) {
+    float n = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRoWarps; ++w) n += sm[w * F + c];
+    ties[(int64_t)g * F + c] = n;
+  }
+}
+
+// dx[i,c] = dmean[g,c]/max(cnt_g,1) + (x[i,c]==max[g,c] ? dmax[g,c]/ties[g,c] : 0);  one warp per node row
+__global__ void __launch_bounds__(256)
+k_readout_bwd(const float* __restrict__ x, int64_t N, int32_t F, const int64_t* __restrict__ batch, int64_t G,
+              const int32_t* __restrict__ ptr, const float* __restrict__ out_max, int64_t ld_max,
+              const float* __restrict__ dmean, const float* __restrict__ dmax, int64_t ld_d,
+              const float* __restrict__ ties, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < N; i += nw) {
+    int64_t g = batch ? batch[i] : 0;
+    const bool ok = g >= 0 && g < G;            // out-of-range graph ids take no gradient (flagged at build time)
+    g = ok ? g : 0;
+    const int cnt = __ldg(ptr + g + 1) - __ldg(ptr + g);
+    const float fc = (float)(cnt < 1 ? 1 : cnt);
+    for (int c = lane; c < F; c += 32) {
+      float r = 0.f;
+      if (ok) {
+        if (dmean) r = __fdiv_rn(__ldg(dmean + g * ld_d + c), fc);
+        if (dmax) {
+          const float xv = __ldg(x + i * F + c);
+          if (xv == __ldg(out_max + g * ld_max + c)) r += __fdiv_rn(__ldg(dmax + g * ld_d + c), __ldg(ties + g * F + c));
+        }
+      }
+      dx[i * F + c] = r;
+    }
+  }
+}
+
+}  // namespace sldm
+
+using namespace sldm;
+
+extern "C" int64_t sldm_readout_workspace_bytes(int64_t G, int32_t F) {
+  if (G < 0 || F < 0) return -1;
+  return align_bytes((G > 0 ? G : 1) * (int64_t)F * 4);
+}
+
+// csr: membership CSR built by sldm_csr_build_pairs(NULL, batch, N, max(N,G)): row g of (rowptr_dst, col_src) lists the
+// nodes of graph g.  out_mean / out_max are [G, ld] views (pass the two halves of one [G,2F] buffer with ld = 2F for
+// the 'double' readout); either may be NULL.
+extern "C" int sldm_readout_forward(const float* x, int64_t N, int32_t F, const int32_t* csr, int64_t csr_nodes,
+                                    int64_t G, float* out_mean, float* out_max, int64_t ld, sldm_stream_t stream) {
+  SLDM_REQUIRE(N >= 0 && G >= 0 && F >= 1, SLDM_EINVAL, "sldm_readout_forward: bad sizes N=%lld G=%lld F=%d",
+               (long long)N, (long long)G, F);
+  SLDM_REQUIRE(csr_nodes >= G && csr_nodes >= N, SLDM_ESHAPE, "sldm_readout_forward: membership CSR covers %lld rows, need %lld",
+               (long long)csr_nodes, (long long)(G > N ? G : N));
+  SLDM_REQUIRE(ld >= F, SLDM_ESHAPE, "sldm_readout_forward: ld=%lld < F=%d", (long long)ld, F);
+  SLDM_REQUIRE(F <= 1024, SLDM_EUNSUPPORTED, "sldm_readout_forward: F=%d > 1024", F);
+  if (G == 0) return SLDM_OK;
+  SLDM_REQUIRE(csr != nullptr && (N == 0 || x != nullptr), SLDM_EINVAL, "sldm_readout_forward: NULL pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CsrLayout L = csr_layout(csr_nodes, N);
+  const int32_t* ptr = csr + L.off[SLDM_CSR_ROWPTR_DST];
+  const int32_t* members = csr + L.off[SLDM_CSR_COL_SRC];
+  const size_t smem = (size_t)kRoWarps * 2 * F * sizeof(float);
+  const bool vec = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+  if (vec) {
+    static bool attr = false;
+    if (!attr) { SLDM_CUDA(cudaFuncSetAttribute(k_readout_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    k_readout_fwd<true><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_mean, out_max, ld);
+  } else {
+    static bool attr = false;
+    if (!attr) { SLDM_CUDA(cudaFuncSetAttribute(k_readout_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    k_readout_fwd<false><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_mean, out_max, ld);
+  }
+  SLDM_LAUNCH_CHECK("k_readout_fwd");
+  return SLDM_OK;
+}
+
+// dmean / dmax are [G, ld_d] views of the upstream gradient (either may be NULL); out_max is the forward result
+// ([G, ld_max] view; required iff dmax != NULL).  dx [N,F] is overwritten.
+extern "C" int sldm_readout_backward(const float* x, int64_t N, int32_t F, const int64_t* batch,
+                                     const int32_t* csr, int64_t csr_nodes, int64_t G,
+                                     const float* out_max, int64_t ld_max,
+                                     const float* dmean, const float* dmax, int64_t ld_d,
+                                     float* dx, void* workspace, int64_t workspace_bytes, sldm_stream_t stream) {
+  SLDM_REQUIRE(N >= 0 && G >= 0 && F >= 1, SLDM_EINVAL, "sldm_readout_backward: bad sizes");
+  SLDM_REQUIRE(F <= 1024, SLDM_EUNSUPPORTED, "sldm_readout_backward: F=%d > 1024", F);
+  if (N == 0) return SLDM_OK;
+  SLDM_REQUIRE(x && csr && dx, SLDM_EINVAL, "sldm_readout_backward: NULL pointer");
+  SLDM_REQUIRE(dmax == nullptr || out_max != nullptr, SLDM_EINVAL, "sldm_readout_backward: dmax without out_max");
+  SLDM_REQUIRE(G >= 1, SLDM_ESHAPE, "sldm_readout_backward: %lld nodes but 0 graphs", (long long)N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CsrLayout L = csr_layout(csr_nodes, N);
+  const int32_t* ptr = csr + L.off[SLDM_CSR_ROWPTR_DST];
+  const int32_t* members = csr + L.off[SLDM_CSR_COL_SRC];
+  float* ties = nullptr;
+  if (dmax != nullptr) {
+    SLDM_REQUIRE(workspace != nullptr && workspace_bytes >= sldm_readout_workspace_bytes(G, F), SLDM_EWORKSPACE,
+                 "sldm_readout_backward: workspace too small");
+    ties = static_cast<float*>(workspace);
+    k_readout_ties<<<(unsigned)G, kRoThreads, (size_t)kRoWarps * F * sizeof(float), s>>>(x, F, ptr, members, out_max, ld_max, ties);
+    SLDM_LAUNCH_CHECK("k_readout_ties");
+  }
+  const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(N, 8), (int64_t)num_sms() * 16);
+  k_readout_bwd<<<grid, 256, 0, s>>>(x, N, F, batch, G, ptr, out_max, ld_max, dmean, dmax, ld_d, ties, dx);
+  SLDM_LAUNCH_CHECK("k_readout_bwd");
+  return SLDM_OK;
+}

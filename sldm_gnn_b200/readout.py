@@ -1,0 +1,109 @@
+"""Graph-level readout on the SageBlock output: drop-ins for torch_geometric.nn.global_mean_pool /
+global_max_pool as the reference uses them (src/models/grusage.py:5 import, :113-120 choice, :185 call), plus the
+fused 'double' readout `cat([mean, max], dim=1)` of grusage.py:119.
+
+Same signature `(x, batch, size=None)`, same results (empty graph -> 0, duplicates counted, any order of `batch`),
+same `batch is None` behaviour (one graph).  When `size` is None PyG reads `int(batch.max()) + 1` on the host; so do
+we -- pass `size` (PyG's `Batch.num_graphs`) to stay sync-free.  CUDA only: the kernels are libsldm_sage.so
+(sldm_readout_forward / _backward over a device-built membership CSR); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+from .ops import Csr, _ptr, _require_cuda, _stream
+
+
+def _membership_csr(batch: torch.Tensor, N: int, G: int) -> Csr:
+    """CSR whose row g lists the nodes of graph g in ascending order (built on the device, stable; unsorted `batch` ok)."""
+    if batch.dtype != torch.long:
+        raise ValueError(f"Expected 'batch' to be of dtype torch.long (got '{batch.dtype}')")
+    if batch.dim() != 1 or batch.numel() != N:
+        raise RuntimeError(f"batch must be a 1-D tensor with one entry per node ({N}), got shape {tuple(batch.shape)}")
+    batch = batch.contiguous()
+    nodes = max(N, G, 1)
+    dev = batch.device
+    layout = _lib.csr_layout(nodes, N)
+    with torch.cuda.device(dev):
+        buf = torch.empty(layout["total"], dtype=torch.int32, device=dev)
+        wsb = int(lib.sldm_csr_workspace_bytes(nodes, N))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if N > 0 else None
+        check(lib.sldm_csr_build_pairs(None, batch.data_ptr() if N > 0 else None, N, nodes, buf.data_ptr(), _ptr(ws),
+                                       wsb if N > 0 else 0, _stream(dev)))
+    return Csr(buf, nodes, N, layout)
+
+
+class _ReadoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, batch, G, want_mean, want_max):
+        N, F = x.shape
+        dev = x.device
+        csr = _membership_csr(batch, N, G)
+        width = F * (int(want_mean) + int(want_max))
+        with torch.cuda.device(dev):
+            out = torch.empty((G, width), dtype=torch.float32, device=dev)
+            o_mean = out.data_ptr() if want_mean else None
+            o_max = (out.data_ptr() + (4 * F if want_mean else 0)) if want_max else None
+            check(lib.sldm_readout_forward(x.data_ptr() if N > 0 else None, N, F, csr.buf.data_ptr(), csr.N, G,
+                                           o_mean, o_max, width, _stream(dev)))
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(x, batch, out)
+            ctx.csr, ctx.G, ctx.want = csr, G, (want_mean, want_max)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, batch, out = ctx.saved_tensors
+        want_mean, want_max = ctx.want
+        N, F = x.shape
+        G, csr, dev = ctx.G, ctx.csr, x.device
+        dout = dout.contiguous()
+        width = out.size(1)
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x)
+            wsb = int(lib.sldm_readout_workspace_bytes(G, F))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            off = 4 * F if want_mean else 0
+            check(lib.sldm_readout_backward(
+                x.data_ptr() if N > 0 else None, N, F, batch.data_ptr() if N > 0 else None, csr.buf.data_ptr(), csr.N, G,
+                (out.data_ptr() + off) if want_max else None, width,
+                dout.data_ptr() if want_mean else None, (dout.data_ptr() + off) if want_max else None, width,
+                dx.data_ptr() if N > 0 else None, ws.data_ptr(), wsb, _stream(dev)))
+        return dx, None, None, None, None
+
+
+def _pool(x, batch, size, want_mean, want_max):
+    if not isinstance(x, torch.Tensor) or x.dim() != 2:
+        raise RuntimeError("readout: x must be a 2-D [num_nodes, features] tensor")
+    _require_cuda(x, "x")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"readout: expected float32 features, got {x.dtype}")
+    x = x.contiguous()
+    N = x.size(0)
+    if batch is None:                      # PyG: one graph, keepdim -> [1, F]
+        batch = torch.zeros(N, dtype=torch.long, device=x.device)
+        size = 1
+    else:
+        _require_cuda(batch, "batch")
+        if batch.device != x.device:
+            raise RuntimeError(f"readout: x is on {x.device} but batch is on {batch.device}")
+    if size is None:                       # same host sync as PyG's scatter (dim_size = int(index.max()) + 1)
+        size = int(batch.max()) + 1 if batch.numel() > 0 else 0
+    return _ReadoutFn.apply(x, batch, int(size), want_mean, want_max)
+
+
+def global_mean_pool(x, batch, size=None):
+    """torch_geometric.nn.global_mean_pool (src/models/grusage.py:5,115)."""
+    return _pool(x, batch, size, True, False)
+
+
+def global_max_pool(x, batch, size=None):
+    """torch_geometric.nn.global_max_pool (src/models/grusage.py:5,117)."""
+    return _pool(x, batch, size, False, True)
+
+
+def global_mean_max_pool(x, batch, size=None):
+    """The 'double' readout of src/models/grusage.py:119: cat([mean_pool, max_pool], dim=1), one pass over x."""
+    return _pool(x, batch, size, True, True)

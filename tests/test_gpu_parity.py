@@ -73,6 +73,18 @@ def edge_cases(kind, N, E, seed):
         m2 = torch.rand(E, generator=g) < 0.3
         ei[0, m2] = 5 % N
         return ei
+    if kind == "sorted_dst":
+        ei = torch.randint(0, N, (2, E), generator=g)
+        order = torch.sort(ei[1] * N + ei[0], stable=True).indices
+        return ei[:, order].contiguous()
+    if kind == "sorted_both":  # both rows non-decreasing: neither sort runs on the device
+        a = torch.sort(torch.randint(0, N, (E,), generator=g)).values
+        b = torch.sort(torch.randint(0, N, (E,), generator=g)).values
+        return torch.stack([a, b]).contiguous()
+    if kind == "one_dst":      # every edge lands on one node: a single digit value in every radix pass, across many tiles
+        ei = torch.randint(0, N, (2, E), generator=g)
+        ei[1] = N // 2
+        return ei
     if kind == "dup_self":
         ei = torch.randint(0, N, (2, E), generator=g)
         ei[1, ::3] = ei[0, ::3]          # self loops
@@ -86,6 +98,10 @@ def edge_cases(kind, N, E, seed):
     ("random", 1, 0), ("random", 1, 5), ("random", 7, 3), ("random", 200, 1000), ("random", 257, 4097),
     ("sorted_src", 6400, 32000), ("random", 70000, 300000), ("hub", 5000, 200000), ("dup_self", 300, 5000),
     ("random", 100, 0), ("hub", 66000, 50000),
+    # onesweep sort: tile boundaries (4096 keys per tile), 1 / 2 / 3 / 4 radix passes, skipped sorts, one-digit keys
+    ("random", 50, 4096), ("random", 300, 8192), ("random", 300, 8193), ("random", 255, 20000), ("random", 256, 20000),
+    ("random", 65536, 100000), ("random", 65537, 100000), ("random", (1 << 24) + 5, 60000),
+    ("sorted_dst", 5000, 70000), ("sorted_both", 5000, 70000), ("one_dst", 1000, 50000),
 ])
 def test_csr_bit_exact(dev, kind, N, E):
     ei = edge_cases(kind, N, E, seed=N + E)

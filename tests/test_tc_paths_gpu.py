@@ -42,3 +42,40 @@ def test_tc_kernels_are_in_the_library():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
+
+
+GATHER_SCRIPT = r"""
+import hashlib, torch
+import sldm_gnn_b200 as sg
+from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+dev = torch.device("cuda:0")
+out = []
+for kind, F in (("batch", 128), ("batch", 96), ("batch", 64), ("batch", 32), ("batch", 16), ("skew", 128), ("skew", 40)):
+    if kind == "batch":
+        ei, _, N = unit_map_graphs(64, seed=3)
+    else:
+        N = 20000
+        ei = skewed_graph(N, 300000, seed=3)
+    ei = ei.to(dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(N, F, device=dev, generator=g)
+    y = torch.randn(N, F, device=dev, generator=g)
+    csr = sg.build_csr(ei, N)
+    a = sg.segment_reduce(x, csr)
+    b = sg.segment_reduce(y, csr, transpose=True, mean=False, addend=x)
+    out.append(hashlib.sha1(a.cpu().numpy().tobytes() + b.cpu().numpy().tobytes()).hexdigest())
+print("HASHES " + " ".join(out))
+"""
+
+
+def test_lean_and_generic_gather_are_bit_identical():
+    """The lean gather (per-warp column window, exact-count load pieces, exact power-of-two mean) must produce the
+    same bytes as the generic kernel: same values, same order of additions (SLDM_SEG_LEAN=0 selects the generic one)."""
+    res = []
+    for lean in ("0", "4", "8"):
+        env = dict(os.environ, SLDM_SEG_LEAN=lean)
+        r = subprocess.run([sys.executable, "-c", GATHER_SCRIPT], env=env, capture_output=True, text=True, timeout=600,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0 and "HASHES" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+        res.append(r.stdout.strip().splitlines()[-1])
+    assert res[0] == res[1] == res[2], res
