@@ -67,21 +67,22 @@ def make_inputs(wl, seed):
     from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
     g = torch.Generator().manual_seed(1000 + seed)
     if wl["kind"] == "graphs":
-        ei, _, N = unit_map_graphs(wl["graphs"], seed=seed)
+        ei, bv, N = unit_map_graphs(wl["graphs"], seed=seed)
         graphs = wl["graphs"]
     else:
         N = wl["nodes"]
         ei = skewed_graph(N, wl["edges"], seed=seed)
-        graphs = 1
+        graphs, bv = 1, None
     x = torch.randn(N, wl["hdims"][0], generator=g)
-    return x, ei, N, graphs
+    return x, ei, N, graphs, bv
 
 
 # CUDA kernel behind each timed group, and how many times it runs per layer and step (fwd+bwd)
 KERNEL_NAMES = {"segment_mean_fwd": "k_segment_rows_lean", "project_ln_act_fwd": "k_sage_tc<NT, MODE_FWD>",
                 "segment_sum_bwd": "k_segment_rows_lean (transpose CSR)", "ln_bwd": "k_ln_bwd_rows",
                 "csr_build": "k_convert + k_digit_hist + k_onesweep_pass x3 + k_rowptr_from_sorted",
-                "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean"}
+                "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean",
+                "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_ties + k_readout_bwd"}
 KERNEL_LAUNCHES_PER_LAYER = {"segment_mean_fwd": 1, "project_ln_act_fwd": 1, "segment_sum_bwd": 1}
 
 
@@ -233,7 +234,7 @@ def workload_config(name, wl, N, E, graphs):
 
 
 # -------------------------------------------------------------------- GPU leg --
-def time_kernels(blk, x, ei, N, E, hdims, peak_gbs):
+def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=None):
     """Per-kernel-group CUDA-event timing of layer 0 (through the C-ABI, on torch's current stream)."""
     import sldm_gnn_b200 as sg
     from sldm_gnn_b200 import ops
@@ -265,6 +266,16 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs):
         "segment_sum_bwd": (lambda: sg.segment_reduce(agg, csr, transpose=True, mean=False, addend=x),
                             E * (Fin * s + 4) + 4 * (N + 1) + 2 * N * Fin * s),
     }
+    if batch_vec is not None:
+        # graph readout on the block's output: membership CSR + fused mean|max forward, and its backward
+        G = int(num_graphs)
+        bv = batch_vec.to(x.device)
+        Fo = out.size(1)
+        xo = out.detach().clone().requires_grad_(True)
+        ro = sg.global_mean_max_pool(xo, bv, G)
+        dro = torch.randn_like(ro)
+        groups["readout_mean_max_fwd"] = (lambda: sg.global_mean_max_pool(out, bv, G), N * Fo * s + G * 2 * Fo * s + 8 * N)
+        groups["readout_bwd"] = (lambda: torch.autograd.grad(ro, xo, dro, retain_graph=True), 2 * N * Fo * s + N * Fo * s + 8 * N)
     res = {}
     for k, (fn, nbytes) in groups.items():
         fn(); torch.cuda.synchronize()
@@ -294,8 +305,8 @@ def main_ours(args, wl):
     batches = []
     for j in range(2):
         seed = (rank * 2 + j) if args.workload != "c4" else j
-        x_h, ei_h, N, graphs = make_inputs(wl, seed)
-        batches.append(dict(x_h=x_h.pin_memory(), ei_h=ei_h.pin_memory(), N=N, E=ei_h.size(1), graphs=graphs))
+        x_h, ei_h, N, graphs, bv = make_inputs(wl, seed)
+        batches.append(dict(x_h=x_h.pin_memory(), ei_h=ei_h.pin_memory(), N=N, E=ei_h.size(1), graphs=graphs, bv=bv))
     for b in batches:
         b["x"] = b["x_h"].to(dev).requires_grad_(True)
         b["ei"] = b["ei_h"].to(dev)
@@ -328,7 +339,7 @@ def main_ours(args, wl):
     # 10-step run measured 6.1 ms/step cold against 4.5 warm).  The per-kernel-group timing runs first on every rank
     # (~0.5 s of the same kernels, untimed for the headline), then the W warm-up steps, then the K timed steps.
     peak_gbs, peak_src = measured_peaks()
-    kern = None if args.skip_kernel_timing else time_kernels(blk, batches[0]["x"].detach(), batches[0]["ei"], N, E, hdims, peak_gbs)
+    kern = None if args.skip_kernel_timing else time_kernels(blk, batches[0]["x"].detach(), batches[0]["ei"], N, E, hdims, peak_gbs, batches[0]["bv"], batches[0]["graphs"])
     for i in range(max(3, args.warmup)):
         step(batches[i % 2])
     barrier()
@@ -405,7 +416,7 @@ def main_ours(args, wl):
         else:
             # the dominant KERNEL: the largest single-kernel group (layer_backward is a sequence of kernels and is
             # reported under "kernels" only)
-            single = [k for k in kern if k not in ("csr_build", "layer_backward")]
+            single = [k for k in KERNEL_LAUNCHES_PER_LAYER if k in kern]
             top = max(single, key=lambda k: kern[k]["ms"] * KERNEL_LAUNCHES_PER_LAYER[k])
         traffic = measured_traffic(args.workload, top)
         line = {

@@ -101,7 +101,8 @@ int     sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
 
 /* Same build from two separate int64 rows.  edge_src == NULL means source ids 0..E-1: the result is then a
  * membership list (row k of rowptr_dst / col_src = the positions e with edge_dst[e] == k, ascending), which is how
- * the graph readout below obtains the nodes of every graph from PyG's `batch` vector. */
+ * the graph readout below obtains the nodes of every graph from PyG's `batch` vector.  In that mode N only bounds
+ * edge_dst (N = number of graphs) and the transpose sections (rowptr_src, col_dst, hub_src) are not written. */
 int     sldm_csr_build_pairs(const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int64_t N,
                              int32_t* csr, void* workspace, int64_t workspace_bytes,
                              sldm_stream_t stream);
@@ -173,7 +174,7 @@ int     sldm_sage_layer_backward(const float* dout, const float* x, const float*
  * reduce='mean' / 'max') as used at src/models/grusage.py:113-120 (choice) and :185 (x = self.global_pool(x, batch)):
  *   mean[g,:] = sum_{i: batch[i]=g} x[i,:] / max(count_g,1)      max[g,:] = max_{i: batch[i]=g} x[i,:]
  *   empty graph -> 0 in both.  'double' = [mean | max] concatenated: pass the two halves of one [G,2F] buffer, ld = 2F.
- * csr is the membership CSR: sldm_csr_build_pairs(NULL, batch, N, csr_nodes = max(N,G), ...), so `batch` need not be
+ * csr is the membership CSR: sldm_csr_build_pairs(NULL, batch, N, csr_nodes >= G, ...), so `batch` need not be
  * sorted.  backward: dx[i,:] = dmean[g,:]/max(count_g,1) + [x[i,:]==max[g,:]] * dmax[g,:]/ties[g,:]  (torch's amax
  * backward shares the gradient evenly among tied maxima).  Either output / gradient view may be NULL.
  */

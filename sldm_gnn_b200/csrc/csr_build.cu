@@ -157,9 +157,9 @@ k_convert(const int64_t* __restrict__ ei_src, const int64_t* __restrict__ ei_dst
       us |= ei_src != nullptr && ei_src[e - 1] > s;
       ud |= ei_dst[e - 1] > d;
     }
-    if (s < 0 || s >= N || d < 0 || d >= N) {
+    if ((ei_src != nullptr && (s < 0 || s >= N)) || d < 0 || d >= N) {
       bad = true;  // reported through meta; clamped so nothing goes out of bounds
-      s = s < 0 ? 0 : (s >= N ? N - 1 : s);
+      if (ei_src != nullptr) s = s < 0 ? 0 : (s >= N ? N - 1 : s);
       d = d < 0 ? 0 : (d >= N ? N - 1 : d);
     }
     src32[e] = (int32_t)s;
@@ -385,12 +385,35 @@ k_copy_if_sorted(const int32_t* __restrict__ vals, int64_t n, int32_t* __restric
 __global__ void __launch_bounds__(256)
 k_rowptr_from_sorted(const int32_t* __restrict__ keys_if_sorted, const int32_t* __restrict__ keys_after_sort,
                      int64_t n, int32_t N, int32_t* __restrict__ rowptr, const int32_t* __restrict__ unsorted_flag) {
+  // Position i writes rowptr[k] = i for every k in (keys[i-1], keys[i]].  Runs of absent keys are normally short; a long
+  // one (trailing isolated nodes, membership lists whose keys only span the graphs) is parked in shared memory and
+  // filled by the whole CTA, so no single thread ever writes more than kInline entries in a row.
+  constexpr int kInline = 16, kMaxGaps = 64;
+  __shared__ int g_lo[kMaxGaps], g_hi[kMaxGaps], g_val[kMaxGaps];
+  __shared__ int g_n;
   const int32_t* __restrict__ keys = (*unsorted_flag == 0) ? keys_if_sorted : keys_after_sort;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
-    const int lo = (i == 0) ? -1 : keys[i - 1];
-    const int hi = (i == n) ? N : keys[i];
-    for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = ceil_div<int64_t>(n + 1, stride);
+  for (int64_t r = 0; r < rounds; ++r) {
+    if (threadIdx.x == 0) g_n = 0;
+    __syncthreads();
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) {
+      const int lo = (i == 0) ? -1 : keys[i - 1];
+      const int hi = (i == n) ? N : keys[i];
+      if (hi - lo <= kInline) {
+        for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;
+      } else {
+        const int slot = atomicAdd(&g_n, 1);
+        if (slot < kMaxGaps) { g_lo[slot] = lo; g_hi[slot] = hi; g_val[slot] = (int32_t)i; }
+        else for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;   // list full: fall back to the serial fill
+      }
+    }
+    __syncthreads();
+    const int ng = min(g_n, kMaxGaps);
+    for (int q = 0; q < ng; ++q)
+      for (int kk = g_lo[q] + 1 + threadIdx.x; kk <= g_hi[q]; kk += blockDim.x) rowptr[kk] = g_val[q];
+    __syncthreads();
   }
 }
 
@@ -570,10 +593,11 @@ extern "C" int sldm_csr_build_pairs(const int64_t* edge_src, const int64_t* edge
     k_rowptr_from_sorted<<<grid, 256, 0, s>>>(dst32, sorted_d, E, (int32_t)N, rp_d, meta + 4);
     SLDM_LAUNCH_CHECK("k_rowptr_from_sorted(dst)");
   }
-  // by source (transpose): keys = src, payload = dst -> col_dst.  The ping-pong buffers are reused: stream order
-  // guarantees the row pointers above were derived before they are overwritten.
-  if ((rc = radix_sort_pairs(src32, dst32, E, npass, key_bits(N), kA, vA, kB, vB, col_d, Ws, &sorted_s, meta + 3, s))) return rc;
-  {
+  const bool membership = (edge_src == nullptr);   // only (rowptr_dst, col_src) are produced; source ids may exceed N
+  if (!membership) {
+    // by source (transpose): keys = src, payload = dst -> col_dst.  The ping-pong buffers are reused: stream order
+    // guarantees the row pointers above were derived before they are overwritten.
+    if ((rc = radix_sort_pairs(src32, dst32, E, npass, key_bits(N), kA, vA, kB, vB, col_d, Ws, &sorted_s, meta + 3, s))) return rc;
     int grid = (int)std::min<int64_t>(ceil_div<int64_t>(E + 1, 256), (int64_t)num_sms() * 16);
     k_rowptr_from_sorted<<<grid, 256, 0, s>>>(src32, sorted_s, E, (int32_t)N, rp_s, meta + 3);
     SLDM_LAUNCH_CHECK("k_rowptr_from_sorted(src)");
@@ -583,7 +607,9 @@ extern "C" int sldm_csr_build_pairs(const int64_t* edge_src, const int64_t* edge
   int grid = (int)ceil_div<int64_t>(N, 256);
   k_plan_hubs<<<grid, 256, 0, s>>>(rp_d, (int32_t)N, hub_d, meta + 0, cap);
   SLDM_LAUNCH_CHECK("k_plan_hubs(dst)");
-  k_plan_hubs<<<grid, 256, 0, s>>>(rp_s, (int32_t)N, hub_s, meta + 1, cap);
-  SLDM_LAUNCH_CHECK("k_plan_hubs(src)");
+  if (!membership) {
+    k_plan_hubs<<<grid, 256, 0, s>>>(rp_s, (int32_t)N, hub_s, meta + 1, cap);
+    SLDM_LAUNCH_CHECK("k_plan_hubs(src)");
+  }
   return SLDM_OK;
 }

@@ -10,7 +10,7 @@
 // The reference path does a host sync (batch.max().item()) and four scatter passes; here the graph segments come
 // from the same device-side CSR machinery as the aggregation (members of graph g = one CSR row, in node order, so an
 // unsorted batch vector is handled too), one CTA per graph streams its rows once for both statistics, and the backward
-// is two streaming kernels.  No atomics: every result is deterministic.
+// is two streaming kernels (per-graph coefficients, then one pass over the nodes).  No atomics: every result is deterministic.
 //
 // Bound: HBM.  Algorithmic bytes: forward N*F*4 read + G*2F*4 written; backward 2*N*F*4 read + N*F*4 written.
 #include "common.cuh"
@@ -86,55 +86,83 @@ k_readout_fwd(const float* __restrict__ x, int32_t F, const int32_t* __restrict_
 // NaN handling: fmaxf drops NaNs while torch's amax propagates them; features reaching the readout are finite
 // (LayerNorm + (Leaky)ReLU outputs), the parity tests use finite inputs.
 
-// ties[g,c] = #{i in graph g : x[i,c] == max[g,c]}
+// Per-graph backward coefficients, one CTA per graph (same row walk as the forward):
+//   coef[g, c]     = dmean[g,c] / max(count_g, 1)
+//   coef[g, F + c] = dmax[g,c] / ties[g,c],   ties[g,c] = #{i in graph g : x[i,c] == max[g,c]}
+template <bool VEC>
 __global__ void __launch_bounds__(kRoThreads)
-k_readout_ties(const float* __restrict__ x, int32_t F, const int32_t* __restrict__ ptr,
-               const int32_t* __restrict__ members, const float* __restrict__ out_max, int64_t ld,
-               float* __restrict__ ties) {
+k_readout_coef(const float* __restrict__ x, int32_t F, const int32_t* __restrict__ ptr,
+               const int32_t* __restrict__ members, const float* __restrict__ out_max, int64_t ld_max,
+               const float* __restrict__ dmean, const float* __restrict__ dmax, int64_t ld_d,
+               float* __restrict__ coef) {
   extern __shared__ float sm[];                 // [kRoWarps][F]
   const int g = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int beg = __ldg(ptr + g), end = __ldg(ptr + g + 1);
-  for (int c = lane; c < F; c += 32) {
-    const float mx = __ldg(out_max + (int64_t)g * ld + c);
-    float n = 0.f;
-    for (int i = beg + warp; i < end; i += kRoWarps)
-      n += (__ldg(x + (int64_t)__ldg(members + i) * F + c) == mx) ? 1.f : 0.f;
-    sm[warp * F + c] = n;
+  constexpr int W = VEC ? 4 : 1;
+  if (dmax != nullptr) {
+    for (int c = lane * W; c < F; c += 32 * W) {
+      float mx[4], n[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < W; ++e) mx[e] = __ldg(out_max + (int64_t)g * ld_max + c + e);
+      for (int i = beg + warp; i < end; i += kRoWarps) {
+        const float* row = x + (int64_t)__ldg(members + i) * F + c;
+        if (VEC) {
+          const float4 v = ldg4(row);
+          n[0] += v.x == mx[0] ? 1.f : 0.f; n[1] += v.y == mx[1] ? 1.f : 0.f;
+          n[2] += v.z == mx[2] ? 1.f : 0.f; n[3] += v.w == mx[3] ? 1.f : 0.f;
+        } else {
+          n[0] += __ldg(row) == mx[0] ? 1.f : 0.f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < W; ++e) sm[warp * F + c + e] = n[e];
+    }
   }
   __syncthreads();
+  const int cnt = end - beg;
+  const float fc = (float)(cnt < 1 ? 1 : cnt);
   for (int c = threadIdx.x; c < F; c += kRoThreads) {
-    float n = 0.f;
+    coef[(int64_t)g * 2 * F + c] = dmean ? __fdiv_rn(__ldg(dmean + (int64_t)g * ld_d + c), fc) : 0.f;
+    float b = 0.f;
+    if (dmax != nullptr) {
+      float n = 0.f;
 #pragma unroll
-    for (int w = 0; w < kRoWarps; ++w) n += sm[w * F + c];
-    ties[(int64_t)g * F + c] = n;
+      for (int w = 0; w < kRoWarps; ++w) n += sm[w * F + c];
+      b = n > 0.f ? __fdiv_rn(__ldg(dmax + (int64_t)g * ld_d + c), n) : 0.f;
+    }
+    coef[(int64_t)g * 2 * F + F + c] = b;
   }
 }
 
-// dx[i,c] = dmean[g,c]/max(cnt_g,1) + (x[i,c]==max[g,c] ? dmax[g,c]/ties[g,c] : 0);  one warp per node row
+// dx[i,c] = coef[g,c] + (x[i,c] == max[g,c] ? coef[g,F+c] : 0);  one warp per node row, 128-bit accesses when aligned
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_readout_bwd(const float* __restrict__ x, int64_t N, int32_t F, const int64_t* __restrict__ batch, int64_t G,
-              const int32_t* __restrict__ ptr, const float* __restrict__ out_max, int64_t ld_max,
-              const float* __restrict__ dmean, const float* __restrict__ dmax, int64_t ld_d,
-              const float* __restrict__ ties, float* __restrict__ dx) {
+              const float* __restrict__ out_max, int64_t ld_max, const float* __restrict__ coef, int use_max,
+              float* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
+  constexpr int W = VEC ? 4 : 1;
   const int64_t nw = (int64_t)gridDim.x * 8;
   for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < N; i += nw) {
     int64_t g = batch ? batch[i] : 0;
-    const bool ok = g >= 0 && g < G;            // out-of-range graph ids take no gradient (flagged at build time)
+    const bool ok = g >= 0 && g < G;            // out-of-range graph ids take no gradient
     g = ok ? g : 0;
-    const int cnt = __ldg(ptr + g + 1) - __ldg(ptr + g);
-    const float fc = (float)(cnt < 1 ? 1 : cnt);
-    for (int c = lane; c < F; c += 32) {
-      float r = 0.f;
-      if (ok) {
-        if (dmean) r = __fdiv_rn(__ldg(dmean + g * ld_d + c), fc);
-        if (dmax) {
-          const float xv = __ldg(x + i * F + c);
-          if (xv == __ldg(out_max + g * ld_max + c)) r += __fdiv_rn(__ldg(dmax + g * ld_d + c), __ldg(ties + g * F + c));
+    const float* ca = coef + g * 2 * F;
+    for (int c = lane * W; c < F; c += 32 * W) {
+      if (VEC) {
+        float4 r = ok ? ldg4(ca + c) : f4zero();
+        if (ok && use_max) {
+          const float4 xv = ldg4(x + i * F + c), mx = ldg4(out_max + g * ld_max + c), b = ldg4(ca + F + c);
+          r.x += xv.x == mx.x ? b.x : 0.f; r.y += xv.y == mx.y ? b.y : 0.f;
+          r.z += xv.z == mx.z ? b.z : 0.f; r.w += xv.w == mx.w ? b.w : 0.f;
         }
+        st4(dx + i * F + c, r);
+      } else {
+        float r = ok ? __ldg(ca + c) : 0.f;
+        if (ok && use_max && __ldg(x + i * F + c) == __ldg(out_max + g * ld_max + c)) r += __ldg(ca + F + c);
+        dx[i * F + c] = r;
       }
-      dx[i * F + c] = r;
     }
   }
 }
@@ -145,18 +173,18 @@ using namespace sldm;
 
 extern "C" int64_t sldm_readout_workspace_bytes(int64_t G, int32_t F) {
   if (G < 0 || F < 0) return -1;
-  return align_bytes((G > 0 ? G : 1) * (int64_t)F * 4);
+  return align_bytes((G > 0 ? G : 1) * (int64_t)F * 2 * 4);   // per-graph backward coefficients [G, 2F]
 }
 
-// csr: membership CSR built by sldm_csr_build_pairs(NULL, batch, N, max(N,G)): row g of (rowptr_dst, col_src) lists the
+// csr: membership CSR built by sldm_csr_build_pairs(NULL, batch, N, csr_nodes >= G): row g of (rowptr_dst, col_src) lists the
 // nodes of graph g.  out_mean / out_max are [G, ld] views (pass the two halves of one [G,2F] buffer with ld = 2F for
 // the 'double' readout); either may be NULL.
 extern "C" int sldm_readout_forward(const float* x, int64_t N, int32_t F, const int32_t* csr, int64_t csr_nodes,
                                     int64_t G, float* out_mean, float* out_max, int64_t ld, sldm_stream_t stream) {
   SLDM_REQUIRE(N >= 0 && G >= 0 && F >= 1, SLDM_EINVAL, "sldm_readout_forward: bad sizes N=%lld G=%lld F=%d",
                (long long)N, (long long)G, F);
-  SLDM_REQUIRE(csr_nodes >= G && csr_nodes >= N, SLDM_ESHAPE, "sldm_readout_forward: membership CSR covers %lld rows, need %lld",
-               (long long)csr_nodes, (long long)(G > N ? G : N));
+  SLDM_REQUIRE(csr_nodes >= G, SLDM_ESHAPE, "sldm_readout_forward: membership CSR covers %lld rows, need %lld",
+               (long long)csr_nodes, (long long)G);
   SLDM_REQUIRE(ld >= F, SLDM_ESHAPE, "sldm_readout_forward: ld=%lld < F=%d", (long long)ld, F);
   SLDM_REQUIRE(F <= 1024, SLDM_EUNSUPPORTED, "sldm_readout_forward: F=%d > 1024", F);
   if (G == 0) return SLDM_OK;
@@ -197,16 +225,18 @@ extern "C" int sldm_readout_backward(const float* x, int64_t N, int32_t F, const
   CsrLayout L = csr_layout(csr_nodes, N);
   const int32_t* ptr = csr + L.off[SLDM_CSR_ROWPTR_DST];
   const int32_t* members = csr + L.off[SLDM_CSR_COL_SRC];
-  float* ties = nullptr;
-  if (dmax != nullptr) {
-    SLDM_REQUIRE(workspace != nullptr && workspace_bytes >= sldm_readout_workspace_bytes(G, F), SLDM_EWORKSPACE,
-                 "sldm_readout_backward: workspace too small");
-    ties = static_cast<float*>(workspace);
-    k_readout_ties<<<(unsigned)G, kRoThreads, (size_t)kRoWarps * F * sizeof(float), s>>>(x, F, ptr, members, out_max, ld_max, ties);
-    SLDM_LAUNCH_CHECK("k_readout_ties");
-  }
+  SLDM_REQUIRE(workspace != nullptr && workspace_bytes >= sldm_readout_workspace_bytes(G, F), SLDM_EWORKSPACE,
+               "sldm_readout_backward: workspace too small");
+  float* coef = static_cast<float*>(workspace);
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool vec = (F % 4 == 0) && a16(x) && a16(dx) && a16(out_max) && (ld_max % 4 == 0);
+  const size_t smem = (size_t)kRoWarps * F * sizeof(float);
+  if (vec) k_readout_coef<true><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_max, ld_max, dmean, dmax, ld_d, coef);
+  else     k_readout_coef<false><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_max, ld_max, dmean, dmax, ld_d, coef);
+  SLDM_LAUNCH_CHECK("k_readout_coef");
   const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(N, 8), (int64_t)num_sms() * 16);
-  k_readout_bwd<<<grid, 256, 0, s>>>(x, N, F, batch, G, ptr, out_max, ld_max, dmean, dmax, ld_d, ties, dx);
+  if (vec) k_readout_bwd<true><<<grid, 256, 0, s>>>(x, N, F, batch, G, out_max, ld_max, coef, dmax != nullptr, dx);
+  else     k_readout_bwd<false><<<grid, 256, 0, s>>>(x, N, F, batch, G, out_max, ld_max, coef, dmax != nullptr, dx);
   SLDM_LAUNCH_CHECK("k_readout_bwd");
   return SLDM_OK;
 }

@@ -23,7 +23,7 @@ def _membership_csr(batch: torch.Tensor, N: int, G: int) -> Csr:
     if batch.dim() != 1 or batch.numel() != N:
         raise RuntimeError(f"batch must be a 1-D tensor with one entry per node ({N}), got shape {tuple(batch.shape)}")
     batch = batch.contiguous()
-    nodes = max(N, G, 1)
+    nodes = max(G, 1)                      # membership mode: rows = graphs, the node ids are the positions 0..N-1
     dev = batch.device
     layout = _lib.csr_layout(nodes, N)
     with torch.cuda.device(dev):

@@ -85,6 +85,8 @@ def edge_cases(kind, N, E, seed):
         ei = torch.randint(0, N, (2, E), generator=g)
         ei[1] = N // 2
         return ei
+    if kind == "low_ids":      # all edges among the first 100 nodes: one run of ~N absent keys at the end
+        return torch.randint(0, 100, (2, E), generator=g)
     if kind == "dup_self":
         ei = torch.randint(0, N, (2, E), generator=g)
         ei[1, ::3] = ei[0, ::3]          # self loops
@@ -102,6 +104,8 @@ def edge_cases(kind, N, E, seed):
     ("random", 50, 4096), ("random", 300, 8192), ("random", 300, 8193), ("random", 255, 20000), ("random", 256, 20000),
     ("random", 65536, 100000), ("random", 65537, 100000), ("random", (1 << 24) + 5, 60000),
     ("sorted_dst", 5000, 70000), ("sorted_both", 5000, 70000), ("one_dst", 1000, 50000),
+    # long runs of nodes without edges: cooperative gap fill of the row pointers (and its overflow path)
+    ("low_ids", 500000, 3000), ("random", 1000000, 2000),
 ])
 def test_csr_bit_exact(dev, kind, N, E):
     ei = edge_cases(kind, N, E, seed=N + E)
