@@ -27,7 +27,7 @@
 //                                registers; after the last chunk: + bias, LayerNorm (row statistics combined across
 //                                the four column quarters through smem), xhat out, (Leaky)ReLU, out -- through
 //                                swizzled full-row patches and cp.async.bulk.tensor stores
-// Tensor memory (512 columns): accumulators [0, 256), A slots [256, 448).
+// Tensor memory (512 columns): three accumulators [0, 384), two A slots [384, 512).
 // Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  Measured (profiles/r01c): 15.5k cycles per tile = 6.3k epilogue
 // tail (statistics 1.9k, two TMA pushes that queue behind the operand loads) + 9.2k drain paced by the MMA stream
 // (two accumulators of look-ahead); the HBM floor is 11.4k.  An SS-mode variant (A_hi/A_lo in shared memory, four
@@ -42,9 +42,10 @@ constexpr int kTcThreads = 768;   // 6 warpgroups: {TMA, MMA, alloc, idle} {conv
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
 constexpr int kTcStages = 3;
 constexpr int kTcBM = 128;
-constexpr int kTcAcc = 2;          // TMEM accumulator ring (one K chunk each), columns [0, 2*32*NT)
+constexpr int kTcAcc = 3;          // TMEM accumulator ring (one K chunk each), columns [0, 3*32*NT): look-ahead of the MMA stream
+constexpr int kTcASlots = 2;       // TMEM A slots (own ring, own "free" barriers: shorter than the smem stage ring)
 constexpr int kTcPatchBytes = 16 * 4 * 1024;   // TMA-store patches: 16 epilogue warps x 4 x [32 rows][8 cols]
-constexpr int kTcACol0 = 256;      // TMEM columns of the A ring: kTcStages x {A_hi[32] | A_lo[32]}
+constexpr int kTcACol0 = 384;      // TMEM columns of the A ring: kTcASlots x {A_hi[32] | A_lo[32]}
 constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
 
 // One work item = (128-row tile, output group).  Its K loop runs over nsrc A sources x Kc 32-wide chunks.
@@ -263,6 +264,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_full[kTcStages], bar_conv[kTcStages], bar_empty[kTcStages];
   __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
+  __shared__ uint64_t bar_afree[kTcASlots];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128], s_gamma[128], s_beta[128];
   __shared__ float s_sum[4][128], s_var[4][128];
@@ -272,8 +274,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   const uint32_t b_bytes = (uint32_t)Fout * 128;
   const uint32_t stage_bytes = a_bytes + 2 * b_bytes;   // raw A tile | B_hi | B_lo  (A_hi / A_lo live in tensor memory)
   constexpr int ACC_COLS = 32 * NT;
-  constexpr uint32_t TMEM_COLS = 512;                   // accumulators [0, 256) + A ring [256, 256 + 64*kTcStages)
-  static_assert(kTcAcc * 128 <= kTcACol0 && kTcACol0 + 64 * kTcStages <= 512, "TMEM budget");
+  constexpr uint32_t TMEM_COLS = 512;                   // accumulators [0, 384) + A slots [384, 512)
+  static_assert(kTcAcc * 128 <= kTcACol0 && kTcACol0 + 64 * kTcASlots <= 512, "TMEM budget");
 
   const int half = pb.Kc;
   const int nchunks = pb.nsrc * pb.Kc;
@@ -292,6 +294,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       mbar_init(&bar_conv[s], 4);
       mbar_init(&bar_empty[s], 1);
     }
+    for (int a = 0; a < kTcASlots; ++a) mbar_init(&bar_afree[a], 1);
     for (int a = 0; a < kTcAcc; ++a) {
       mbar_init(&bar_acc_full[a], 1);
       mbar_init(&bar_acc_empty[a], 16);
@@ -360,7 +363,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           // B descriptors differ only in the 14-bit start-address field (bytes >> 4); A comes from tensor memory
           const uint64_t d_b_hi = make_smem_desc_sw128(sa + a_bytes, 16, 1024);
           const uint64_t d_b_lo = d_b_hi + (b_bytes >> 4);
-          const uint32_t a_hi = tmem_base + kTcACol0 + s * 64;
+          const uint32_t asl = it % kTcASlots;
+          const uint32_t a_hi = tmem_base + kTcACol0 + asl * 64;
           const uint32_t a_lo = a_hi + 32;
           const uint32_t d = tmem_base + ab * ACC_COLS;
           // small products first: the accumulator rounds toward zero
@@ -370,7 +374,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_lo + 2 * ks, idesc, 1u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_hi + 2 * ks, idesc, 1u);
-          mma_commit(&bar_empty[s]);       // smem stage and TMEM A slot reusable once these MMAs have read them
+          mma_commit(&bar_empty[s]);       // smem stage reusable once these MMAs have read it
+          mma_commit(&bar_afree[asl]);     // ... and the TMEM A slot
           mma_commit(&bar_acc_full[ab]);   // chunk accumulator complete
           TC_TRACE(5, it);
         }
@@ -390,8 +395,10 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
         const uint32_t a_raw = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
         // this thread's row of the chunk: split every value into the part the tensor core keeps (hi) and the
         // rounded remainder (lo) and park both in the stage's tensor-memory slot (lane = row, column = k).
-        // The slot is free: TMA only refilled this stage after the MMAs that read the slot had committed.
-        const uint32_t t_hi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcACol0 + s * 64;
+        const uint32_t asl = it % kTcASlots, aslph = (it / kTcASlots) & 1;
+        mbar_wait(&bar_afree[asl], aslph ^ 1);     // the MMAs that read this slot two chunks ago have completed
+        tc_fence_after();
+        const uint32_t t_hi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcACol0 + asl * 64;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float4 v[4];
