@@ -120,8 +120,8 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
   const float* const bias = a.s_bias + c_lo;
   const float* const gam = a.s_gamma + c_lo;
   const float* const bet = a.s_beta + c_lo;
-  uint32_t it = 0;
-  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+  uint32_t it = 0, tcount = 0;
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
    for (int grp = 0; grp < a.ngroups; ++grp) {
     float z[HC];
     for (int c = 0; c < a.nchunks; ++c, ++it) {
@@ -155,8 +155,11 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
     float rs = 1.f;            // FWD: rstd of the row;  DGRAD: unused
     float cnt = 1.f;           // DGRAD group 0: max(deg,1)
     if constexpr (MODE == MODE_FWD) {
-      // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q:
-      //      they meet on a 128-thread named barrier, nobody else waits.  Sums run as four interleaved chains. ----
+      // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q.
+      //      Each quarter computes its own (sum, M2 about its own mean); ONE exchange through smem on a 128-thread
+      //      named barrier and Chan's merge give the row mean and variance:
+      //         M2 = sum_q M2_q + sum_q n_q (m_q - mean)^2        (two-pass accuracy, one barrier instead of two)
+      //      Sums run as four interleaved chains. ----
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j4 = 0; j4 < HC / 4; ++j4) {
@@ -169,21 +172,38 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
           ps[e] += (FULL || c_lo + j < Fout) ? z[j] : 0.f;
         }
       }
-      a.s_sum[cq * 128 + rloc] = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-      named_bar_sync(2 + q, 128);
-      const float mean = __fdiv_rn((a.s_sum[rloc] + a.s_sum[128 + rloc]) + (a.s_sum[256 + rloc] + a.s_sum[384 + rloc]), fF);
+      const int nq_i = FULL ? HC : max(0, min(HC, Fout - c_lo));     // valid columns of this quarter
+      const float nq = (float)nq_i;
+      const float sq = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      const float mq = nq_i > 0 ? __fdiv_rn(sq, nq) : 0.f;
       float pv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < HC; ++j) {
-        z[j] -= mean;
-        pv[j & 3] += (FULL || c_lo + j < Fout) ? z[j] * z[j] : 0.f;
+        const float d = z[j] - mq;
+        pv[j & 3] += (FULL || c_lo + j < Fout) ? d * d : 0.f;
       }
-      a.s_var[cq * 128 + rloc] = (pv[0] + pv[1]) + (pv[2] + pv[3]);
+      // buffers alternate per tile: a warp can only be one barrier ahead of its three partners, so the values of
+      // tile t are never overwritten (by tile t+2) before everybody has read them
+      float* const sS = a.s_sum + (tcount & 1) * 512;
+      float* const sV = a.s_var + (tcount & 1) * 512;
+      sS[cq * 128 + rloc] = sq;
+      sV[cq * 128 + rloc] = (pv[0] + pv[1]) + (pv[2] + pv[3]);
       named_bar_sync(2 + q, 128);
-      rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn((a.s_var[rloc] + a.s_var[128 + rloc]) + (a.s_var[256 + rloc] + a.s_var[384 + rloc]), fF) + a.eps));
-      if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
+      float s4[4], m2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < HC; ++j) z[j] *= rs;      // z now holds xhat
+      for (int k = 0; k < 4; ++k) s4[k] = sS[k * 128 + rloc];
+      const float mean = __fdiv_rn((s4[0] + s4[1]) + (s4[2] + s4[3]), fF);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int nk_i = FULL ? HC : max(0, min(HC, Fout - k * HC));
+        const float nk = (float)nk_i;
+        const float dm = (nk_i > 0 ? __fdiv_rn(s4[k], nk) : mean) - mean;
+        m2 += sV[k * 128 + rloc] + nk * dm * dm;
+      }
+      rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(m2, fF) + a.eps));
+#pragma unroll
+      for (int j = 0; j < HC; ++j) z[j] = (z[j] - mean) * rs;      // z now holds xhat
+      if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
       if (tid == 256) TC_TRACE(14, it - 1);
     } else {
       if (grp == 0 && row < a.N) {
@@ -267,7 +287,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   __shared__ uint64_t bar_afree[kTcASlots];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128], s_gamma[128], s_beta[128];
-  __shared__ float s_sum[4][128], s_var[4][128];
+  __shared__ float s_sum[2][4][128], s_var[2][4][128];   // double buffered by tile parity (one barrier per tile)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
@@ -428,7 +448,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     reg_inc<88>();
     // ---------------------------------------------------------------- epilogue --
     EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
-               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0], &s_var[0][0],
+               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0][0], &s_var[0][0][0],
                reinterpret_cast<float*>(smem + (size_t)kTcStages * stage_bytes), trace, &tm_o0, &tm_o1};
     const bool full = (Fout == 32 * NT);
     if (full) epilogue_role<NT, true, MODE>(ea); else epilogue_role<NT, false, MODE>(ea);
