@@ -16,8 +16,9 @@
 //
 // All of this is HBM-bound int32 work: 16E bytes read (int64 pairs), 8E written
 // per sorted column array, 8(N+1) for the row pointers.  Measured on B200
-// (profiles/r01d_csr_*.txt): 4.1 M edges 0.30 ms, 10 M unsorted edges 0.97 ms; the
-// passes are bound by the warp-vote (ADU) pipe of the stable ranking, not by HBM.
+// (profiles/r01g_csr_launches.txt): 4.1 M edges 0.29 ms, 10 M unsorted edges 0.81 ms; the
+// passes are bound by the stable ranking (warp votes on the ADU pipe, or shared-memory
+// atomics emulating match.any), not by HBM.
 #include "common.cuh"
 #include <algorithm>
 
@@ -182,6 +183,10 @@ constexpr int kOsWarps = kOsThreads / 32;
 constexpr int kOsKpt = 16;                       // keys per thread
 constexpr int kOsTile = kOsThreads * kOsKpt;     // 4096 keys per CTA
 constexpr int kMaxPass = 4;
+#ifndef SLDM_RANK_ATOMIC_OR
+#define SLDM_RANK_ATOMIC_OR 1
+#endif
+constexpr bool kRankAtomicOr = SLDM_RANK_ATOMIC_OR != 0;   // stable ranking: shared-memory atomicOr peer masks (1) or warp ballots (0)
 
 // ghist[p][d] += #keys whose p-th digit is d, for all passes at once.  High digits of clustered keys are uniform
 // across a warp: one shared-memory atomic per warp instead of 32.
@@ -288,6 +293,28 @@ k_onesweep_pass(const int32_t* __restrict__ keys_in, const int32_t* __restrict__
     k[r] = valid ? keys_in[tbase + i] : 0;
     v[r] = valid ? vals_in[tbase + i] : 0;
   }
+  if (kRankAtomicOr && nbits > 5) {   // narrow digits: a few ballots are cheaper
+    // peer mask through shared memory: every lane ORs its bit into the word of its digit, then reads the word back
+    // (an emulated match.any on the LSU pipe instead of eight votes on the ADU pipe)
+    unsigned* mk = reinterpret_cast<unsigned*>(skeys) + warp * 256;   // skeys is not used before the regroup step
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mk[lane + 32 * j] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kOsKpt; ++r) {
+      const bool valid = wbase + r * 32 < tile_n;
+      const int d = (k[r] >> shift) & 255;
+      if (valid) atomicOr(&mk[d], 1u << lane);
+      __syncwarp();
+      unsigned m = 0u;
+      int old = 0;
+      if (valid) { m = mk[d]; old = wh[warp][d]; }
+      __syncwarp();
+      if (valid && lane == __ffs(m) - 1) { wh[warp][d] = old + __popc(m); mk[d] = 0u; }
+      __syncwarp();
+      rl[r] = (unsigned short)(old + __popc(m & ((1u << lane) - 1u)));
+    }
+  } else {
 #pragma unroll
   for (int r = 0; r < kOsKpt; ++r) {
     const bool valid = wbase + r * 32 < tile_n;
@@ -302,6 +329,7 @@ k_onesweep_pass(const int32_t* __restrict__ keys_in, const int32_t* __restrict__
       rl[r] = (unsigned short)(old + __popc(m & ((1u << lane) - 1u)));
     }
     __syncwarp();
+  }
   }
   __syncthreads();
 
@@ -395,19 +423,21 @@ k_rowptr_from_sorted(const int32_t* __restrict__ keys_if_sorted, const int32_t* 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = ceil_div<int64_t>(n + 1, stride);
   for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = 0, hi = 0;
+    if (i <= n) {
+      lo = (i == 0) ? -1 : keys[i - 1];
+      hi = (i == n) ? N : keys[i];
+    }
+    const bool big = hi - lo > kInline;
+    if (!big) for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;
+    if (!__syncthreads_or(big)) continue;          // the common case: no long run in this CTA's slice
     if (threadIdx.x == 0) g_n = 0;
     __syncthreads();
-    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n) {
-      const int lo = (i == 0) ? -1 : keys[i - 1];
-      const int hi = (i == n) ? N : keys[i];
-      if (hi - lo <= kInline) {
-        for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;
-      } else {
-        const int slot = atomicAdd(&g_n, 1);
-        if (slot < kMaxGaps) { g_lo[slot] = lo; g_hi[slot] = hi; g_val[slot] = (int32_t)i; }
-        else for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;   // list full: fall back to the serial fill
-      }
+    if (big) {
+      const int slot = atomicAdd(&g_n, 1);
+      if (slot < kMaxGaps) { g_lo[slot] = lo; g_hi[slot] = hi; g_val[slot] = (int32_t)i; }
+      else for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;   // list full: fall back to the serial fill
     }
     __syncthreads();
     const int ng = min(g_n, kMaxGaps);
