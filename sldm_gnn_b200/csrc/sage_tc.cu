@@ -40,7 +40,8 @@ using namespace tc;
 
 constexpr int kTcThreads = 768;   // 6 warpgroups: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 4
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 5;        // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
+constexpr int kTcBStages = 2;       // B ring: weight chunks B_hi | B_lo (L2 resident, short latency)
 constexpr int kTcBM = 128;
 constexpr int kTcAcc = 3;          // TMEM accumulator ring (one K chunk each), columns [0, 3*32*NT): look-ahead of the MMA stream
 constexpr int kTcASlots = 2;       // TMEM A slots (own ring, own "free" barriers: shorter than the smem stage ring)
@@ -282,9 +283,10 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   const int Fout = pb.Nout;   // MMA N / output width of this problem
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_full[kTcStages], bar_conv[kTcStages], bar_empty[kTcStages];
+  __shared__ uint64_t bar_full[kTcStages], bar_empty[kTcStages];       // A ring: TMA -> converter -> TMA
+  __shared__ uint64_t bar_bfull[kTcBStages], bar_bempty[kTcBStages];   // B ring: TMA -> MMA -> TMA
+  __shared__ uint64_t bar_conv[kTcASlots], bar_afree[kTcASlots];       // TMEM A slots: converter -> MMA -> converter
   __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
-  __shared__ uint64_t bar_afree[kTcASlots];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128], s_gamma[128], s_beta[128];
   __shared__ float s_sum[2][4][128], s_var[2][4][128];   // double buffered by tile parity (one barrier per tile)
@@ -292,7 +294,9 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
   const uint32_t b_bytes = (uint32_t)Fout * 128;
-  const uint32_t stage_bytes = a_bytes + 2 * b_bytes;   // raw A tile | B_hi | B_lo  (A_hi / A_lo live in tensor memory)
+  // shared memory: A ring (kTcStages raw tiles) | B ring (kTcBStages x {B_hi, B_lo}) | epilogue patches
+  uint8_t* const smem_b = smem + (size_t)kTcStages * a_bytes;
+  uint8_t* const smem_patch = smem_b + (size_t)kTcBStages * 2 * b_bytes;
   constexpr int ACC_COLS = 32 * NT;
   constexpr uint32_t TMEM_COLS = 512;                   // accumulators [0, 384) + A slots [384, 512)
   static_assert(kTcAcc * 128 <= kTcACol0 && kTcACol0 + 64 * kTcASlots <= 512, "TMEM budget");
@@ -311,9 +315,13 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_conv[s], 4);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], 4);       // released by the four converter warps once the raw tile is in registers
     }
+    for (int s = 0; s < kTcBStages; ++s) {
+      mbar_init(&bar_bfull[s], 1);
+      mbar_init(&bar_bempty[s], 1);      // released by tcgen05.commit
+    }
+    for (int a = 0; a < kTcASlots; ++a) mbar_init(&bar_conv[a], 4);
     for (int a = 0; a < kTcASlots; ++a) mbar_init(&bar_afree[a], 1);
     for (int a = 0; a < kTcAcc; ++a) {
       mbar_init(&bar_acc_full[a], 1);
@@ -334,7 +342,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   if (warp < 4) {
    reg_dec<40>();
    if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer --
+    // ---------------------------------------------------------- TMA producer: A --
+    // raw activation chunks, kTcStages deep: this is the HBM stream, it keeps running while the epilogue finishes a tile
     if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -345,16 +354,32 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
             TC_TRACE(0, it);
             mbar_wait(&bar_empty[s], ph ^ 1);
             TC_TRACE(1, it);
-            uint8_t* st = smem + (size_t)s * stage_bytes;
-            mbar_expect_tx(&bar_full[s], a_bytes + 2 * b_bytes);
+            mbar_expect_tx(&bar_full[s], a_bytes);
+            const int src = c / half;
+            const int k0 = (c - src * half) * 32;
+            tma_load_2d(smem + (size_t)s * a_bytes, src == 0 ? &tm_agg : &tm_x, k0, row0, &bar_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------------------------------------------------- TMA producer: B --
+    // pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk (L2 resident; re-streaming them is not a limiter:
+    // skipping these loads changed the kernel time by < 5% on B200)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int g = 0; g < ngroups; ++g) {
+          for (int c = 0; c < nchunks; ++c, ++it) {
+            const uint32_t s = it % kTcBStages, ph = (it / kTcBStages) & 1;
+            mbar_wait(&bar_bempty[s], ph ^ 1);
+            uint8_t* st = smem_b + (size_t)s * 2 * b_bytes;
+            mbar_expect_tx(&bar_bfull[s], 2 * b_bytes);
             const int src = c / half;
             const int k0 = (c - src * half) * 32;
             const int wrow = 2 * (g * pb.nsrc + src) * Fout;
-            tma_load_2d(st, src == 0 ? &tm_agg : &tm_x, k0, row0, &bar_full[s]);
-            // (re-streaming the weight tiles from L2 for every chunk is NOT the limiter: skipping these two loads
-            //  changed the kernel time by < 5% on B200)
-            tma_load_2d(st + a_bytes, &tm_w, k0, wrow, &bar_full[s]);
-            tma_load_2d(st + a_bytes + b_bytes, &tm_w, k0, wrow + Fout, &bar_full[s]);
+            tma_load_2d(st, &tm_w, k0, wrow, &bar_bfull[s]);
+            tma_load_2d(st + b_bytes, &tm_w, k0, wrow + Fout, &bar_bfull[s]);
           }
         }
       }
@@ -370,20 +395,21 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < ngroups * nchunks; ++c, ++it) {
-          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+          const uint32_t sb = it % kTcBStages, bph = (it / kTcBStages) & 1;
+          const uint32_t asl = it % kTcASlots, aslph = (it / kTcASlots) & 1;
           const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
           if ((it & 1u) != my_parity) continue;
           TC_TRACE(2, it);
-          mbar_wait(&bar_acc_empty[ab], aph ^ 1);   // epilogue drained this accumulator (two chunks ago)
+          mbar_wait(&bar_acc_empty[ab], aph ^ 1);   // epilogue drained this accumulator (three chunks ago)
           TC_TRACE(3, it);
-          mbar_wait(&bar_conv[s], ph);              // converter done => TMA data landed too (it waited on bar_full)
+          mbar_wait(&bar_conv[asl], aslph);         // a_hi | a_lo of this chunk are in the TMEM slot
+          mbar_wait(&bar_bfull[sb], bph);           // weight tiles of this chunk have landed
           TC_TRACE(4, it);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sa = smem_u32(smem_b + (size_t)sb * 2 * b_bytes);
           // B descriptors differ only in the 14-bit start-address field (bytes >> 4); A comes from tensor memory
-          const uint64_t d_b_hi = make_smem_desc_sw128(sa + a_bytes, 16, 1024);
+          const uint64_t d_b_hi = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t d_b_lo = d_b_hi + (b_bytes >> 4);
-          const uint32_t asl = it % kTcASlots;
           const uint32_t a_hi = tmem_base + kTcACol0 + asl * 64;
           const uint32_t a_lo = a_hi + 32;
           const uint32_t d = tmem_base + ab * ACC_COLS;
@@ -394,7 +420,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_lo + 2 * ks, idesc, 1u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_hi + 2 * ks, idesc, 1u);
-          mma_commit(&bar_empty[s]);       // smem stage reusable once these MMAs have read it
+          mma_commit(&bar_bempty[sb]);     // weight stage reusable once these MMAs have read it
           mma_commit(&bar_afree[asl]);     // ... and the TMEM A slot
           mma_commit(&bar_acc_full[ab]);   // chunk accumulator complete
           TC_TRACE(5, it);
@@ -412,9 +438,9 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
         const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
         mbar_wait(&bar_full[s], ph);
         if (tid == 128) TC_TRACE(6, it);
-        const uint32_t a_raw = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
+        const uint32_t a_raw = smem_u32(smem + (size_t)s * a_bytes) + (uint32_t)r * 128;
         // this thread's row of the chunk: split every value into the part the tensor core keeps (hi) and the
-        // rounded remainder (lo) and park both in the stage's tensor-memory slot (lane = row, column = k).
+        // rounded remainder (lo) and park both in a tensor-memory slot (lane = row, column = k).
         const uint32_t asl = it % kTcASlots, aslph = (it / kTcASlots) & 1;
         mbar_wait(&bar_afree[asl], aslph ^ 1);     // the MMAs that read this slot two chunks ago have completed
         tc_fence_after();
@@ -424,6 +450,13 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           float4 v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = lds128(a_raw + (uint32_t)(((4 * h + j) ^ (r & 7)) << 4));
+          if (h == 1) {                            // the whole row is in registers: hand the raw stage back to TMA
+            // (the loads must have RETURNED before the stage is released: make the release depend on their values)
+            float guard = v[0].x + v[1].x + v[2].x + v[3].x;
+            asm volatile("" ::"f"(guard) : "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[s]);
+          }
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -440,7 +473,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_conv[s]);
+        if (lane == 0) mbar_arrive(&bar_conv[asl]);
         if (tid == 128) TC_TRACE(7, it);
       }
     }
@@ -449,7 +482,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     // ---------------------------------------------------------------- epilogue --
     EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
                bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0][0], &s_var[0][0][0],
-               reinterpret_cast<float*>(smem + (size_t)kTcStages * stage_bytes), trace, &tm_o0, &tm_o1};
+               reinterpret_cast<float*>(smem_patch), trace, &tm_o0, &tm_o1};
     const bool full = (Fout == 32 * NT);
     if (full) epilogue_role<NT, true, MODE>(ea); else epilogue_role<NT, false, MODE>(ea);
   }
@@ -656,11 +689,11 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
                      const CUtensorMap& mo1, const TcProblem& pb,
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
-  const size_t smem = (size_t)kTcStages * (kTcBM * 128 + 2 * (size_t)pb.Nout * 128) + kTcPatchBytes + 1024;
+  const size_t smem = (size_t)kTcStages * kTcBM * 128 + (size_t)kTcBStages * 2 * pb.Nout * 128 + kTcPatchBytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     SLDM_CUDA(cudaFuncSetAttribute(k_sage_tc<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kTcStages * (kTcBM * 128 + 2 * 128 * 128) + kTcPatchBytes + 1024));
+                                   kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcPatchBytes + 1024));
     attr_done = true;
   }
   const int64_t ntiles = ceil_div<int64_t>(pb.N, kTcBM);
