@@ -14,24 +14,26 @@
 // sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
 //
 // Pipeline (one persistent CTA per SM, 768 threads, 128 rows x Fout per tile; setmaxnreg 40 / 72 / 88 of the 80 x 768 pool):
-//   warp 0        TMA producer : per K chunk (32 floats) loads A raw [128 x 32] (agg, then x) and the pre-split
-//                                weight tiles B_hi, B_lo [Fout x 32] into a 3-stage shared-memory ring
+//   warp 0        TMA producer A: raw activation chunks [128 x 32] (agg, then x) into a 5-deep ring -- the HBM stream;
+//                                a stage is handed back by the CONVERTER as soon as the tile is in registers
+//   warp 2        TMA producer B: pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk into a 2-deep ring (L2 hits)
 //   warps 4-7     converter    : reads its row of the raw tile, splits every value into a_hi (what the tensor core
 //                                keeps) and a_lo = rna_tf32(a - a_hi) and parks both in TENSOR MEMORY with tcgen05.st
-//                                (lane = row, column = k; one 64-column slot per stage) -- the MMAs take A from TMEM,
-//                                so shared memory only carries the raw tile once and the weights
+//                                (lane = row, column = k; two 64-column slots with their own free barriers) -- the MMAs
+//                                take A from TMEM, so shared memory only carries the raw tile once and the weights
 //   warps 1, 3    MMA issuers  : alternate K chunks; 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8), A from TMEM, B
-//                                from smem descriptors, into one of two TMEM accumulators; tcgen05.commit frees the
-//                                smem stage + TMEM slot and signals the epilogue
+//                                from smem descriptors, into one of three TMEM accumulators; tcgen05.commit frees the
+//                                weight stage and the TMEM A slot and signals the epilogue
 //   warps 8-23    epilogue     : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add into
-//                                registers; after the last chunk: + bias, LayerNorm (row statistics combined across
-//                                the four column quarters through smem), xhat out, (Leaky)ReLU, out -- through
+//                                registers; after the last chunk: + bias, LayerNorm (one exchange of per-quarter
+//                                (sum, M2) through smem, Chan's merge), xhat out, (Leaky)ReLU, out -- through
 //                                swizzled full-row patches and cp.async.bulk.tensor stores
 // Tensor memory (512 columns): three accumulators [0, 384), two A slots [384, 512).
-// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  Measured (profiles/r01c): 15.5k cycles per tile = 6.3k epilogue
-// tail (statistics 1.9k, two TMA pushes that queue behind the operand loads) + 9.2k drain paced by the MMA stream
-// (two accumulators of look-ahead); the HBM floor is 11.4k.  An SS-mode variant (A_hi/A_lo in shared memory, four
-// accumulators, 8 epilogue warps) measured the same 0.40 ms; this one uses 48 KB less shared memory.
+// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  Measured (profiles/r01c traces): 14.7k cycles per
+// 128-row tile against an HBM floor of 11.4k: 6.8k epilogue tail (statistics 1.9k, two TMA pushes that queue behind the
+// operand loads) during which the MMA stream can only run three accumulators ahead, then a drain paced by the
+// MMA -> free TMEM slot -> converter -> MMA chain (~1.25k cycles per chunk).  Tensor memory is the binding resource:
+// 2 accumulators + 4 slots, 3 + 2 (this), and an SS-mode variant with 4 accumulators all land within 4% of 0.40 ms.
 #include "common.cuh"
 #include "tc_common.cuh"
 
