@@ -64,10 +64,6 @@ inline int64_t hub_capacity(int64_t E) {
 }
 
 // ---- internal launchers shared between translation units --------------------
-// exclusive scan of n int32 (in place allowed); spine must hold scan_spine_elems(n) ints
-int64_t scan_spine_elems(int64_t n);
-int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* spine, cudaStream_t s);
-
 int segment_reduce_launch(const float* src, int64_t N, int32_t F,
                           const int32_t* rowptr, const int32_t* col,
                           const int32_t* hub_list, const int32_t* hub_count, int64_t hub_cap,

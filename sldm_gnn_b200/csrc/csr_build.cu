@@ -42,12 +42,6 @@ CsrLayout csr_layout(int64_t N, int64_t E) {
 }
 
 // -------------------------------------------------------------------- scan --
-constexpr int kScanThreads = 512;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
-
-int64_t scan_spine_elems(int64_t n) { return ceil_div<int64_t>(n, kScanTile) + 2; }
-
 // exclusive scan of one value per thread across the block; returns the prefix
 // of this thread and (to every thread) the block total.
 template <int THREADS>
@@ -78,70 +72,6 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total, int* smem
   total = smem[NW];
   __syncthreads();
   return prefix;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_reduce(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ spine) {
-  __shared__ int sm[kScanThreads / 32 + 1];
-  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    int64_t idx = base + i;
-    if (idx < n) s += in[idx];
-  }
-  int total;
-  block_exclusive_scan<kScanThreads>(s, total, sm);
-  if (threadIdx.x == 0) spine[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of spine[0..nb) in place
-__global__ void __launch_bounds__(1024)
-k_scan_spine(int32_t* __restrict__ spine, int64_t nb) {
-  __shared__ int sm[1024 / 32 + 1];
-  int carry = 0;
-  for (int64_t c = 0; c < nb; c += 1024) {
-    int64_t idx = c + threadIdx.x;
-    int v = (idx < nb) ? spine[idx] : 0;
-    int total;
-    int p = block_exclusive_scan<1024>(v, total, sm);
-    if (idx < nb) spine[idx] = carry + p;
-    carry += total;
-  }
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_apply(const int32_t* in, int32_t* out, int64_t n, const int32_t* __restrict__ spine) {
-  __shared__ int sm[kScanThreads / 32 + 1];
-  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  int v[kScanItems];
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    int64_t idx = base + i;
-    v[i] = (idx < n) ? in[idx] : 0;
-    s += v[i];
-  }
-  int total;
-  int p = block_exclusive_scan<kScanThreads>(s, total, sm) + spine[blockIdx.x];
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    int64_t idx = base + i;
-    if (idx < n) out[idx] = p;
-    p += v[i];
-  }
-}
-
-int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* spine, cudaStream_t s) {
-  if (n <= 0) return SLDM_OK;
-  int64_t nb = ceil_div<int64_t>(n, kScanTile);
-  k_scan_reduce<<<(unsigned)nb, kScanThreads, 0, s>>>(in, n, spine);
-  SLDM_LAUNCH_CHECK("k_scan_reduce");
-  k_scan_spine<<<1, 1024, 0, s>>>(spine, nb);
-  SLDM_LAUNCH_CHECK("k_scan_spine");
-  k_scan_apply<<<(unsigned)nb, kScanThreads, 0, s>>>(in, out, n, spine);
-  SLDM_LAUNCH_CHECK("k_scan_apply");
-  return SLDM_OK;
 }
 
 // ---------------------------------------------------------------- convert --
