@@ -497,13 +497,16 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
 // dW_l = dz^T agg, dW_r = dz^T x as one GEMM  D[m][n] = sum_r dz[r][m] * [agg | x][r][n]   (M = Fout <= 128 lanes,
 // N = 2*32*NB columns, K = node rows).  Both operands have the reduction index as their slow dimension, i.e. they are
 // "MN-major": the tiles are TMA-loaded as [32 rows][32 floats] boxes with the 128B_ATOM_32B swizzle and described with
-// layout SWIZZLE_128B_BASE32B (lbo = 4096 between 32-column blocks, sbo = 512, 1024 bytes per K=8 step) -- found with
+// layout SWIZZLE_128B_BASE32B (lbo = bytes of one [rows x 32] block between 32-column blocks, sbo = 512, 1024 bytes per
+// K=8 step) -- found with
 // tools/tc_probe.cu.  Split precision as in the forward: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, small terms first.
 // Every CTA owns a contiguous slab of rows; the TMEM accumulator is flushed into fp32 registers every kWgFlush chunks
 // (the tensor core accumulates with round-toward-zero) and the per-CTA partial is written once at the end;
 // k_reduce_parts sums the partials in CTA order (deterministic).
-constexpr int kWgStages = 2;
-constexpr int kWgFlush = 4;      // 32-row chunks per TMEM accumulator (128 rows)
+constexpr int kWgRows = 16;                 // node rows per pipeline chunk (the K extent of one stage)
+constexpr int kWgStages = 4;                // 4 x 48 KB: the fixed TMA latency is spread over more, smaller stages
+constexpr int kWgFlush = 128 / kWgRows;     // chunks per TMEM accumulator (128 rows)
+constexpr uint32_t kWgBlk = kWgRows * 128;  // bytes of one [kWgRows x 32 floats] operand block
 
 template <int NB>   // NB = ceil(Fin / 32) in 1..4
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -516,14 +519,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
   __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t A_BYTES = 4 * 4096;              // dz chunk: 32 rows x 128 columns
-  constexpr uint32_t B_BYTES = 2 * NB * 4096;         // [agg | x] chunk: 32 rows x 2*32*NB columns
+  constexpr uint32_t A_BYTES = 4 * kWgBlk;            // dz chunk: kWgRows rows x 128 columns
+  constexpr uint32_t B_BYTES = 2 * NB * kWgBlk;       // [agg | x] chunk: kWgRows rows x 2*32*NB columns
   constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t STAGE_BYTES = 2 * RAW_BYTES;     // raw (= hi) followed by lo, same layout
   constexpr int NCOLS = 64 * NB;                      // accumulator columns
   constexpr uint32_t TMEM_COLS = (2 * NCOLS <= 128) ? 128 : ((2 * NCOLS <= 256) ? 256 : 512);
 
-  const int64_t total_chunks = (N + 31) / 32;
+  const int64_t total_chunks = (N + kWgRows - 1) / kWgRows;
   const int64_t c_beg = (int64_t)blockIdx.x * chunks_per_cta;
   int64_t c_end = c_beg + chunks_per_cta;
   if (c_end > total_chunks) c_end = total_chunks;
@@ -550,13 +553,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
         mbar_wait(&bar_empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
         mbar_expect_tx(&bar_full[s], RAW_BYTES);
-        const int r0 = (int)((c_beg + it) * 32);
+        const int r0 = (int)((c_beg + it) * kWgRows);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &tm_dz, b * 32, r0, &bar_full[s]);
+        for (int b = 0; b < 4; ++b) tma_load_2d(st + b * kWgBlk, &tm_dz, b * 32, r0, &bar_full[s]);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + b * 4096, &tm_agg, b * 32, r0, &bar_full[s]);
+        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + b * kWgBlk, &tm_agg, b * 32, r0, &bar_full[s]);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + (NB + b) * 4096, &tm_x, b * 32, r0, &bar_full[s]);
+        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + (NB + b) * kWgBlk, &tm_x, b * 32, r0, &bar_full[s]);
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------------------------ MMA issuer --
@@ -569,17 +572,17 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
         mbar_wait(&bar_conv[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint64_t d_a_hi = make_smem_desc(sa, 4096, 512, 1);
+        const uint64_t d_a_hi = make_smem_desc(sa, kWgBlk, 512, 1);
         const uint64_t d_b_hi = d_a_hi + (A_BYTES >> 4);
         const uint64_t d_a_lo = d_a_hi + (RAW_BYTES >> 4);
         const uint64_t d_b_lo = d_b_hi + (RAW_BYTES >> 4);
         const uint32_t d = tmem_base + ab * NCOLS;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_lo + 64 * ks, d_b_hi + 64 * ks, idesc, (first && ks == 0) ? 0u : 1u);
+        for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_lo + 64 * ks, d_b_hi + 64 * ks, idesc, (first && ks == 0) ? 0u : 1u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
+        for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_hi + 64 * ks, idesc, 1u);
+        for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_hi + 64 * ks, idesc, 1u);
         mma_commit(&bar_empty[s]);
         if ((it % kWgFlush) == kWgFlush - 1 || it == nch - 1) mma_commit(&bar_acc_full[ab]);
       }
@@ -800,7 +803,7 @@ int64_t wgrad_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64
 template <int NB>
 static int launch_wgrad(const CUtensorMap& mz, const CUtensorMap& ma, const CUtensorMap& mx, int64_t N, int Fin,
                         int Fout, int cpc, int grid, float* part, cudaStream_t s) {
-  const size_t smem = (size_t)kWgStages * 2 * (4 + 2 * NB) * 4096 + 1024;
+  const size_t smem = (size_t)kWgStages * 2 * (4 + 2 * NB) * kWgBlk + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     SLDM_CUDA(cudaFuncSetAttribute(k_wgrad_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -816,10 +819,10 @@ int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N
                     float* part, int* nparts, cudaStream_t s) {
   CUtensorMap mz, ma, mx;
   int rc;
-  if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, 32, 32, 1))) return rc;
-  if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, 32, 32, 1))) return rc;
-  if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, 32, 32, 1))) return rc;
-  const int64_t total_chunks = ceil_div<int64_t>(N, 32);
+  if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kWgRows, 32, 1))) return rc;
+  if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, kWgRows, 32, 1))) return rc;
+  if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kWgRows, 32, 1))) return rc;
+  const int64_t total_chunks = ceil_div<int64_t>(N, kWgRows);
   int grid = wgrad_tc_grid();
   if (grid > total_chunks) grid = (int)total_chunks;
   // whole flush groups per CTA keep the slab boundaries independent of the grid rounding
