@@ -465,18 +465,29 @@ k_wgrad(const float* __restrict__ dz, const float* __restrict__ agg, const float
   }
 }
 
-// out[i] = sum_{s < S} part[s*stride + i]   (s ascending: deterministic)
+// out[i] = sum_{s < S} part[s*stride + i], deterministic: a CTA owns 32 consecutive outputs, its 8 warps each add the
+// slices s = w, w+8, ... in ascending order, the 8 partial sums are combined in warp order.  (One thread per output
+// walking all S slices was latency bound: 592 dependent loads for the 384 column sums took 52 us -- profiles/r01i.)
 __global__ void __launch_bounds__(256)
 k_reduce_parts(const float* __restrict__ part, int S, int64_t stride, int64_t count,
                float* __restrict__ out0, int64_t split, float* __restrict__ out1,
                int64_t split2, float* __restrict__ out2) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int k = 0; k < S; ++k) s += __ldg(part + (int64_t)k * stride + i);
-  if (i < split) out0[i] = s;
-  else if (i < split2) out1[i - split] = s;
-  else out2[i - split2] = s;
+  if (i < count)
+    for (int k = w; k < S; k += 8) s += __ldg(part + (int64_t)k * stride + i);
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < count) {
+    float t = sm[0][lane];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += sm[q][lane];
+    if (i < split) out0[i] = t;
+    else if (i < split2) out1[i - split] = t;
+    else out2[i - split2] = t;
+  }
 }
 
 // ------------------------------------------------------------------ launch --
@@ -609,11 +620,11 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
   }
   {
     const int64_t count = 2 * wcount;
-    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(count, 256), 256, 0, s>>>(part, nparts, 2 * wcount, count,
+    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(count, 32), 256, 0, s>>>(part, nparts, 2 * wcount, count,
                                                                          dW_l, wcount, dW_r, count, nullptr);
     SLDM_LAUNCH_CHECK("k_reduce_parts(dW)");
     const int64_t c3 = 3 * (int64_t)Fout;
-    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(c3, 256), 256, 0, s>>>(colpart, ncolparts, c3, c3,
+    k_reduce_parts<<<(unsigned)ceil_div<int64_t>(c3, 32), 256, 0, s>>>(colpart, ncolparts, c3, c3,
                                                                       dln_w, Fout, dln_b, 2 * (int64_t)Fout, db_l);
     SLDM_LAUNCH_CHECK("k_reduce_parts(cols)");
   }
