@@ -46,9 +46,11 @@ WORKLOADS = {
     "batch": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=256),
     "c1": dict(kind="graphs", graphs=32, hdims=[64, 64, 64], cpu_sample_graphs=32),
     "c4": dict(kind="skewed", nodes=1_000_000, edges=10_000_000, hdims=[128, 128], cpu_sample_graphs=None),
+    # BASELINE configs[2]: batched inference, hidden 128 -- one mega-batch of 4096 graphs, forward only (inference_mode)
+    "infer": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=256, forward_only=True),
 }
 SLOPE = 0.1
-METRIC = "sageblock_fwd_bwd_edges_per_sec"
+METRIC = "sageblock_fwd_bwd_edges_per_sec"     # --workload infer reports forward-only traversals under the same name, flagged in config.step
 
 
 def env_rank():
@@ -182,7 +184,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU legs --
-def cpu_reference_step(block, x, ei):
+def cpu_reference_step(block, x, ei, forward_only=False):
+    if forward_only:
+        with torch.inference_mode():
+            block(x, ei)
+        return
     xr = x.clone().requires_grad_(True)
     y = block(xr, ei)
     y.square().mean().backward()
@@ -215,11 +221,12 @@ def run_cpu(wl, steps, warmup):
     torch.manual_seed(0)
     blk = SageBlockOracle(wl["hdims"], dropout=None, negative_slope=SLOPE)
     x, ei, N, graphs, desc = cpu_sample(wl)
+    fo = bool(wl.get("forward_only"))
     for _ in range(warmup):
-        cpu_reference_step(blk, x, ei)
+        cpu_reference_step(blk, x, ei, fo)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(blk, x, ei)
+        cpu_reference_step(blk, x, ei, fo)
     dt = (time.perf_counter() - t0) / steps
     L = len(wl["hdims"]) - 1
     return dict(edges_per_s=ei.size(1) * L / dt, graphs_per_s=graphs / dt, ms=dt * 1e3, cores=cores, sample=desc)
@@ -245,7 +252,8 @@ def main_reference(args, wl):
 
 def workload_config(name, wl, N, E, graphs):
     c = {"workload": name, "hdims": wl["hdims"], "negative_slope": SLOPE, "dropout": None,
-         "step": "csr_build + forward + backward from a fixed upstream gradient dL/dout (+ grad all-reduce at N>1)",
+         "step": ("csr_build + forward under inference_mode (no backward)" if wl.get("forward_only") else
+                  "csr_build + forward + backward from a fixed upstream gradient dL/dout (+ grad all-reduce at N>1)"),
          "l2": "inputs and saved tensors exceed the 126 MB L2 (x alone is N*F*4 B); two input batches alternate"}
     if N is not None:
         c.update(nodes_per_gpu=N, edges_per_gpu=E, graphs_per_gpu=graphs)
@@ -335,10 +343,15 @@ def main_ours(args, wl):
         b["w"] = torch.randn(b["N"], hdims[-1], generator=torch.Generator().manual_seed(7 + b["N"])).to(dev)
     N, E, graphs = batches[0]["N"], batches[0]["E"], batches[0]["graphs"]
 
+    fwd_only = bool(wl.get("forward_only"))
+
     def step(b, x=None, ei=None):
         x = b["x"] if x is None else x
         ei = b["ei"] if ei is None else ei
-        blk.clear_cache()                      # every training batch is a new graph: CSR build is part of the step
+        blk.clear_cache()                      # every batch is a new graph: CSR build is part of the step
+        if fwd_only:                           # inference (test.py:136): no autograd graph, nothing saved
+            with torch.inference_mode():
+                return blk(x.detach(), ei)
         ddp.zero_grad()
         x.grad = None
         y = ddp(x, ei)
@@ -400,7 +413,7 @@ def main_ours(args, wl):
         b, xd, eid, ev = item
         main_stream.wait_event(ev)
         xd.record_stream(main_stream); eid.record_stream(main_stream)
-        return step(b, xd.requires_grad_(True), eid).sum().item()   # .item(): the D2H read of the step's metric
+        return step(b, xd if fwd_only else xd.requires_grad_(True), eid).sum().item()   # .item(): the D2H read of the step's metric
 
     nxt = prefetch(0)
     for i in range(2):
@@ -431,7 +444,10 @@ def main_ours(args, wl):
         ms_step = ms_total / args.steps
         value = E_all * L / (ms_step * 1e-3)
         e2e_ms = e2e_ms_total / e2e_steps
-        step_bytes = sum(layer_bytes_fwd_bwd(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+        if fwd_only:   # SURVEY 8d FWD_inf per layer: E(Fin s + 4) + 4(N+1) + N s (Fin + Fout)
+            step_bytes = sum(E * (hdims[l] * 4 + 4) + 4 * (N + 1) + N * 4 * (hdims[l] + hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+        else:
+            step_bytes = sum(layer_bytes_fwd_bwd(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
         if kern is None:
             kern, top = {}, None
         else:
@@ -461,7 +477,8 @@ def main_ours(args, wl):
                 "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None},
             "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / ms_step / 1e6,
                               "peak": peak_gbs, "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / peak_gbs,
-                              "model": "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)"},
+                              "model": ("SURVEY 8d FWD_inf: sum_l [E(Fin*4+4) + 4(N+1) + 4N(Fin+Fout)] + 24E + 8(N+1)" if fwd_only else
+                                        "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)")},
             "kernels": kern,
         }
         if world == 1 and not args.no_cpu:
