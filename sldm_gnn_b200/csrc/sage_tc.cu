@@ -444,8 +444,6 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
         // this thread's row of the chunk: split every value into the part the tensor core keeps (hi) and the
         // rounded remainder (lo) and park both in a tensor-memory slot (lane = row, column = k).
         const uint32_t asl = it % kTcASlots, aslph = (it / kTcASlots) & 1;
-        mbar_wait(&bar_afree[asl], aslph ^ 1);     // the MMAs that read this slot two chunks ago have completed
-        tc_fence_after();
         const uint32_t t_hi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcACol0 + asl * 64;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -468,6 +466,12 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
               hi[4 * j + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
               lo[4 * j + e] = __float_as_uint(tf32_lo(f[e]));
             }
+          }
+          if (h == 0) {
+            // the first half is converted while the MMAs that still read this slot (two chunks ago) finish; only
+            // the tensor-memory stores wait for them
+            mbar_wait(&bar_afree[asl], aslph ^ 1);
+            tc_fence_after();
           }
           tmem_st_32x16(t_hi + 16 * h, hi);
           tmem_st_32x16(t_hi + 32 + 16 * h, lo);
