@@ -84,7 +84,8 @@ KERNEL_NAMES = {"segment_mean_fwd": "k_segment_rows_lean", "project_ln_act_fwd":
                 "segment_sum_bwd": "k_segment_rows_lean (transpose CSR)", "ln_bwd": "k_ln_bwd_rows",
                 "csr_build": "k_convert + k_digit_hist + k_onesweep_pass x3 + k_rowptr_from_sorted",
                 "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean",
-                "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_ties + k_readout_bwd"}
+                "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_coef + k_readout_bwd",
+                "collate_32_graphs": "k_concat_chunks x5 + k_collate_edge_index + k_batch_from_ptr (+ host table upload)"}
 KERNEL_LAUNCHES_PER_LAYER = {"segment_mean_fwd": 1, "project_ln_act_fwd": 1, "segment_sum_bwd": 1}
 
 
@@ -304,6 +305,18 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
         dro = torch.randn_like(ro)
         groups["readout_mean_max_fwd"] = (lambda: sg.global_mean_max_pool(out, bv, G), N * Fo * s + G * 2 * Fo * s + 8 * N)
         groups["readout_bwd"] = (lambda: torch.autograd.grad(ro, xo, dro, retain_graph=True), 2 * N * Fo * s + N * Fo * s + 8 * N)
+    if batch_vec is not None:
+        # mini-batch assembly at the reference's DataLoader batch size: 32 device-resident unit graphs with the
+        # fields of a pack (x [n,T,6], edge_index, xsttype, xdims, pos_raw, y); timed end to end (host tables + kernels)
+        from sldm_gnn_b200.synth import unit_map_graphs
+        items, nb = [], 0
+        for gidx in range(32):
+            eg, _, ng = unit_map_graphs(1, seed=100 + gidx)
+            d = dict(x=torch.randn(ng, 16, 6), edge_index=eg, xsttype=torch.randint(0, 5, (ng,)), xdims=torch.randn(ng, 2),
+                     pos_raw=torch.randn(ng, 16, 2), y=torch.zeros(1, 4))
+            nb += 2 * sum(v.numel() * v.element_size() for v in d.values()) + 8 * ng
+            items.append(sg.GraphData(**{k: v.to(x.device) for k, v in d.items()}))
+        groups["collate_32_graphs"] = (lambda: sg.collate(items), nb)
     res = {}
     for k, (fn, nbytes) in groups.items():
         fn(); torch.cuda.synchronize()

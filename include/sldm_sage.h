@@ -187,6 +187,21 @@ int     sldm_readout_backward(const float* x, int64_t N, int32_t F, const int64_
                               const float* dmean, const float* dmax, int64_t ld_d,
                               float* dx, void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
 
+/* ---- mini-batch assembly (the producer of the SageBlock input) -------------
+ * Replaces torch_geometric.data.Batch.from_data_list / collate (PyG 2.7.0) as used by the reference's DataLoader
+ * (main.py:166-167, src/utils.py:218-223) for graphs that already live on the device (src/dataset.py:75-89):
+ *   sldm_concat_chunks       out[dst_off_g .. +bytes_g) = src_g[0 .. bytes_g): torch.cat along dim 0 of G tensors.
+ *                            table_dev: G rows of four int64 {src device pointer, dst byte offset, byte count, 0}.
+ *   sldm_collate_graph_index edge_index_out[:, eoff_g + k] = edge_index_g[:, k] + node_ptr[g]  (int64 [2, Etot]) and
+ *                            batch_out[i] = g for node_ptr[g] <= i < node_ptr[g+1] (may be NULL).
+ *                            table_dev: G rows {edge_index_g device pointer, eoff_g, e_g, row stride in elements}.
+ * At most 65535 graphs per call; max_* size the grids (largest chunk).  Bit-exact by construction.
+ */
+int sldm_concat_chunks(const void* table_dev, int64_t G, int64_t max_chunk_bytes, void* out, sldm_stream_t stream);
+int sldm_collate_graph_index(const void* table_dev, const int64_t* node_ptr_dev, int64_t G, int64_t Etot,
+                             int64_t max_edges, int64_t max_nodes, int64_t* edge_index_out,
+                             int64_t* batch_out, sldm_stream_t stream);
+
 /* ---- whole block, host buffers in / host buffers out -----------------------
  * For hosts that own no device memory (the reference-side stub in
  * INTEGRATION.md).  All pointers are HOST pointers.  Parameters of layer l are

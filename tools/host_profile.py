@@ -29,3 +29,24 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(200): step()
 pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+
+# ---- collate: ours vs a torch.cat restatement on the device (what PyG's collate launches) -------------------------
+from sldm_gnn_b200.synth import unit_map_graphs as _umg
+items = []
+for g in range(32):
+    eg, _, ng = _umg(1, seed=100 + g)
+    items.append(sg.GraphData(x=torch.randn(ng, 16, 6, device=dev), edge_index=eg.to(dev), xsttype=torch.randint(0, 5, (ng,), device=dev),
+                              xdims=torch.randn(ng, 2, device=dev), pos_raw=torch.randn(ng, 16, 2, device=dev), y=torch.zeros(1, 4, device=dev)))
+def torch_collate():
+    nodes = [int(d.x.size(0)) for d in items]
+    ptr = torch.zeros(len(items) + 1, dtype=torch.long); ptr[1:] = torch.cumsum(torch.tensor(nodes), 0)
+    out = {k: torch.cat([getattr(d, k) for d in items], 0) for k in ("x", "xsttype", "xdims", "pos_raw", "y")}
+    out["edge_index"] = torch.cat([d.edge_index + int(ptr[g]) for g, d in enumerate(items)], -1)
+    out["batch"] = torch.repeat_interleave(torch.arange(len(items), device=dev), torch.tensor(nodes, device=dev))
+    return out
+for name, fn in (("sg.collate", lambda: sg.collate(items)), ("torch.cat restatement", torch_collate)):
+    for _ in range(10): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(100): fn()
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    print("collate of 32 graphs, %-22s %.1f us per batch" % (name + ":", (t1 - t0) / 100 * 1e6))
