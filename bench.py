@@ -85,6 +85,7 @@ KERNEL_NAMES = {"segment_mean_fwd": "k_segment_rows_lean", "project_ln_act_fwd":
                 "csr_build": "k_convert + k_digit_hist + k_onesweep_pass x3 + k_rowptr_from_sorted",
                 "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean",
                 "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_coef + k_readout_bwd",
+                "map_attention_fwd": "k_map_attention_fwd", "map_attention_bwd": "k_map_attention_bwd + membership CSR + k_map_attention_demb",
                 "collate_32_graphs": "k_concat_chunks x5 + k_collate_edge_index + k_batch_from_ptr (+ host table upload)"}
 KERNEL_LAUNCHES_PER_LAYER = {"segment_mean_fwd": 1, "project_ln_act_fwd": 1, "segment_sum_bwd": 1}
 
@@ -317,6 +318,18 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
             nb += 2 * sum(v.numel() * v.element_size() for v in d.values()) + 8 * ng
             items.append(sg.GraphData(**{k: v.to(x.device) for k, v in d.items()}))
         groups["collate_32_graphs"] = (lambda: sg.collate(items), nb)
+    if batch_vec is not None:
+        # map attention: one position per node of the batch, a 2048-segment map, 32-d map embeddings, K = 5
+        Sm, Dm = 2048, 32
+        gm = torch.Generator().manual_seed(11)
+        att = sg.MapSpatialAttention(torch.rand(Sm, 2, generator=gm) * 2000.0, 5).to(x.device)
+        posm = (torch.rand(N, 2, generator=gm) * 2000.0).to(x.device)
+        embm = torch.randn(Sm, Dm, generator=gm).to(x.device).requires_grad_(True)
+        ctxm = att(posm, embm)
+        dctxm = torch.randn_like(ctxm)
+        groups["map_attention_fwd"] = (lambda: att(posm, embm.detach()), N * (8 + 5 * Dm * s + Dm * s + 5 * 16) + Sm * (8 + Dm * s))
+        groups["map_attention_bwd"] = (lambda: torch.autograd.grad(ctxm, [embm] + list(att.parameters()), dctxm, retain_graph=True),
+                                       N * (Dm * s + 5 * Dm * s + 5 * 16) + 2 * 5 * N * Dm * s // 2 + Sm * Dm * s)
     res = {}
     for k, (fn, nbytes) in groups.items():
         fn(); torch.cuda.synchronize()

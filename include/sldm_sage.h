@@ -202,6 +202,29 @@ int sldm_collate_graph_index(const void* table_dev, const int64_t* node_ptr_dev,
                              int64_t max_edges, int64_t max_nodes, int64_t* edge_index_out,
                              int64_t* batch_out, sldm_stream_t stream);
 
+/* ---- map attention (between the map-graph block and the vehicle-graph block) --
+ * Replaces MapSpatialAttention.forward, src/models/map/mapattention.py:21-56 (called at src/models/grusage.py:175-178):
+ *   dist[b,s] = ||pos_b - centroid_s||_2 ; the K nearest segments (ties: lower index first) ;
+ *   score_k = W2 . relu(W1 * dist_k + b1) + b2   (attn_mlp = Linear(1,H) -> ReLU -> Linear(H,1); W1, b1, W2 are [H]) ;
+ *   w = softmax_k(score) ; ctx[b,:] = sum_k w_k emb[idx_k,:].
+ * forward also returns idx [B,K] int64 (ascending distance), dist [B,K], w [B,K] (the saved tensors of backward).
+ * backward: gradients for emb (demb [S,D], may be NULL) and the four MLP tensors; positions and centroids are data.
+ * csr = membership CSR of idx: sldm_csr_build_pairs(NULL, idx, B*K, csr_nodes >= S, ...) (only needed for demb).
+ * K <= 8, H <= 64, S >= K (else SLDM_ESHAPE, like torch.topk).
+ */
+int64_t sldm_map_attention_workspace_bytes(int64_t B, int32_t H);
+int     sldm_map_attention_forward(const float* pos, int64_t B, const float* centroids, int64_t S,
+                                   const float* emb, int32_t D, int32_t K,
+                                   const float* W1, const float* b1, const float* W2, const float* b2, int32_t H,
+                                   float* ctx, int64_t* idx_out, float* dist_out, float* w_out,
+                                   sldm_stream_t stream);
+int     sldm_map_attention_backward(const float* dctx, int64_t B, const float* emb, int64_t S, int32_t D, int32_t K,
+                                    const int64_t* idx, const float* dist, const float* w,
+                                    const float* W1, const float* b1, const float* W2, int32_t H,
+                                    const int32_t* csr, int64_t csr_nodes,
+                                    float* demb, float* dW1, float* db1, float* dW2, float* db2,
+                                    void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
+
 /* ---- whole block, host buffers in / host buffers out -----------------------
  * For hosts that own no device memory (the reference-side stub in
  * INTEGRATION.md).  All pointers are HOST pointers.  Parameters of layer l are

@@ -55,6 +55,10 @@ _PROTOS = {
     "sldm_readout_backward": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _p, _p, _i64, _p]),
     "sldm_concat_chunks": (C.c_int, [_p, _i64, _i64, _p, _p]),
     "sldm_collate_graph_index": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "sldm_map_attention_workspace_bytes": (_i64, [_i64, _i32]),
+    "sldm_map_attention_forward": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "sldm_map_attention_backward": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64,
+                                              _p, _p, _p, _p, _p, _p, _i64, _p]),
     "sldm_sage_block_forward_host": (C.c_int, [_p, _p, _i64, _i64, C.POINTER(_i32), _i32, C.POINTER(_p), _f, _f, _p]),
     "sldm_sage_block_train_host": (C.c_int, [_p, _p, _i64, _i64, C.POINTER(_i32), _i32, C.POINTER(_p), _f, _f,
                                              _p, _p, _p, C.POINTER(_p)]),

@@ -1,0 +1,313 @@
+// map_attention.cu -- MapSpatialAttention (src/models/map/mapattention.py:21-56), the step between the map-graph
+// SageBlock and the vehicle-graph SageBlock (src/models/grusage.py:171-179).  SURVEY 8f rank 3.
+//
+// Reference (plain torch, 7 launches, materialises [B,S,2] and [B,S]):
+//   diff = pos[:,None,:] - centroids[None,:,:] ; dists = norm(diff, dim=2)            # [B,S]
+//   neg, idx = topk(-dists, k) ; kd = -neg                                            # K nearest segments
+//   score = attn_mlp(kd[...,None]) = W2 . relu(W1*kd + b1) + b2                       # Linear(1,H) -> ReLU -> Linear(H,1)
+//   w = softmax(score, dim=1) ; ctx = sum_k w_k * emb[idx_k]                          # [B,D]
+// Here: one warp per vehicle scans the centroids (staged in shared memory, coalesced), keeps a per-lane sorted list
+// of the K nearest, the warp merges the 32 lists with K rounds of a 64-bit (distance, index) min-reduction, then the
+// MLP, softmax and the weighted sum of K embedding rows run in registers.  Nothing of size B*S ever touches memory.
+// Ties in distance are broken towards the LOWER segment index (torch.topk leaves that unspecified).
+// Backward: per-vehicle kernel for the softmax / MLP chain (parameter gradients as per-CTA partials, reduced in fixed
+// order), and a deterministic gather for d_emb over a membership CSR keyed by the selected segment (no atomics).
+// Bound: the scan is FP32-issue bound (B*S distance evaluations), everything else HBM: B*(8 + K*D*4 + D*4) bytes.
+#include "common.cuh"
+#include <algorithm>
+#include <math.h>
+
+namespace sldm {
+
+constexpr int kMaK = 8;          // K <= 8
+constexpr int kMaH = 64;         // hidden width of the score MLP <= 64 (reference: 16)
+constexpr int kMaTile = 4096;    // centroids per shared-memory tile (32 KB); a map that fits is loaded once per CTA
+
+__device__ __forceinline__ unsigned long long pack_key(float d, int idx) {
+  // d >= 0: its bit pattern orders like the value; NaN sorts last
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_map_attention_fwd(const float* __restrict__ pos, int64_t B, const float2* __restrict__ cent, int S,
+                    const float* __restrict__ emb, int D, const float* __restrict__ W1, const float* __restrict__ b1,
+                    const float* __restrict__ W2, const float* __restrict__ b2, int H,
+                    float* __restrict__ ctx, int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
+                    float* __restrict__ w_out) {
+  __shared__ float2 s_c[kMaTile];
+  __shared__ float s_w1[kMaH], s_b1[kMaH], s_w2[kMaH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int h = threadIdx.x; h < H; h += 256) { s_w1[h] = W1[h]; s_b1[h] = b1[h]; s_w2[h] = W2[h]; }
+  // persistent over groups of 8 vehicles (one per warp).  A map of at most kMaTile segments is staged ONCE per CTA -- with
+  // one group per CTA the kernel spent its time filling shared memory (16 KB per 8 vehicles) rather than scanning.
+  const bool single = S <= kMaTile;
+  if (single) {
+    for (int i = threadIdx.x; i < S; i += 256) s_c[i] = __ldg(cent + i);
+  }
+  __syncthreads();
+  for (int64_t vb = blockIdx.x; vb * 8 < B; vb += gridDim.x) {
+  const int64_t b = vb * 8 + warp;
+  const bool live = b < B;
+  const float px = live ? __ldg(pos + 2 * b) : 0.f, py = live ? __ldg(pos + 2 * b + 1) : 0.f;
+  // The K best (distance, index) keys of the WARP live in lanes 0..K-1 (ascending).  A round looks at 32 segments, one
+  // per lane; a ballot on the squared distance against the warp's current K-th best finds the few that can enter, and each
+  // of those is inserted with a warp-uniform shift (no per-lane lists, no divergence: per-lane sorted lists cost 5.4k warp
+  // instructions per vehicle at 15/32 active lanes -- ncu, profiles/r01j).
+  unsigned long long L = ~0ull;
+  float thr2 = INFINITY;                           // squared distance a candidate must not exceed
+  for (int t0 = 0; t0 < S; t0 += kMaTile) {
+    const int tn = min(kMaTile, S - t0);
+    if (!single) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < tn; i += 256) s_c[i] = __ldg(cent + t0 + i);
+      __syncthreads();
+    }
+    if (live) {
+      for (int i0 = 0; i0 < tn; i0 += 32) {
+        const int i = i0 + lane;
+        float d2 = INFINITY;
+        if (i < tn) {
+          const float dx = __fsub_rn(px, s_c[i].x), dy = __fsub_rn(py, s_c[i].y);
+          // dx*dx + dy*dy without FMA contraction: the same operations torch.norm performs
+          d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        }
+        unsigned pass = __ballot_sync(0xffffffffu, i < tn && d2 <= thr2);
+        while (pass) {
+          const int srcl = __ffs(pass) - 1;
+          pass &= pass - 1;
+          const float c2 = __shfl_sync(0xffffffffu, d2, srcl);
+          if (c2 <= thr2) {                        // the threshold may have tightened inside this round (uniform)
+            const unsigned long long key = pack_key(__fsqrt_rn(c2), t0 + i0 + srcl);
+            const bool lt = L < key;
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, L, 1);
+            const int prevlt = __shfl_up_sync(0xffffffffu, (int)lt, 1);
+            if (lane < K) L = lt ? L : ((lane == 0 || prevlt) ? key : prev);
+            const unsigned long long worst = __shfl_sync(0xffffffffu, L, K - 1);
+            if (worst != ~0ull) {                  // list full: tighten the filter (inflated by a few ulp so that a
+              const float wd = __uint_as_float((unsigned)(worst >> 32));          // candidate that would TIE after the
+              thr2 = __fmul_rn(__fmul_rn(wd, wd), 1.000001f);                      // rounding of sqrt still gets in)
+            }
+          }
+        }
+      }
+    }
+  }
+  if (live) {
+  const float kd = __uint_as_float((unsigned)(L >> 32));          // lane k (< K): the k-th nearest
+  const int kidx = (int)(unsigned)(L & 0xffffffffu);
+  // score MLP + softmax on lanes 0..K-1
+  float score = -INFINITY;
+  if (lane < K) {
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) {
+      const float pre = fmaf(s_w1[h], kd, s_b1[h]);
+      acc = fmaf(s_w2[h], pre > 0.f ? pre : 0.f, acc);
+    }
+    score = acc + __ldg(b2);
+  }
+  float mx = score;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float ex = lane < K ? expf(score - mx) : 0.f;
+  float den = ex;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const float w = __fdiv_rn(ex, den);
+  if (lane < K) {
+    idx_out[b * K + lane] = kidx;
+    dist_out[b * K + lane] = kd;
+    w_out[b * K + lane] = w;
+  }
+  // ctx = sum_k w_k emb[idx_k]   (k ascending); the broadcasts happen before the column loop (not every lane enters it)
+  float wk[K]; int ik[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { wk[k] = __shfl_sync(0xffffffffu, w, k); ik[k] = __shfl_sync(0xffffffffu, kidx, k); }
+  for (int c = lane; c < D; c += 32) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc = fmaf(wk[k], __ldg(emb + (int64_t)ik[k] * D + c), acc);
+    ctx[b * D + c] = acc;
+  }
+  }   // live
+  }   // vehicle groups
+}
+
+// per vehicle: gw_k = <emb[idx_k], dctx_b>; ds = softmax backward; MLP parameter gradients as per-CTA partials
+//   part[cta][0:H] = dW1, [H:2H] = db1, [2H:3H] = dW2, [3H] = db2
+template <int K>
+__global__ void __launch_bounds__(256)
+k_map_attention_bwd(const float* __restrict__ dctx, int64_t B, const float* __restrict__ emb, int D,
+                    const int64_t* __restrict__ idx, const float* __restrict__ dist, const float* __restrict__ wgt,
+                    const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2, int H,
+                    float* __restrict__ part) {
+  __shared__ float s_w1[kMaH], s_b1[kMaH], s_w2[kMaH];
+  __shared__ float s_p[8][3 * kMaH + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int h = threadIdx.x; h < H; h += 256) { s_w1[h] = W1[h]; s_b1[h] = b1[h]; s_w2[h] = W2[h]; }
+  __syncthreads();
+  float a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f}, a3[2] = {0.f, 0.f}, a4 = 0.f;   // lane h (and h+32): dW1, db1, dW2; db2
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += nw) {
+    float gw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) gw[k] = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float g = __ldg(dctx + b * D + c);
+#pragma unroll
+      for (int k = 0; k < K; ++k) gw[k] = fmaf(__ldg(emb + __ldg(idx + b * K + k) * D + c), g, gw[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gw[k] += __shfl_xor_sync(0xffffffffu, gw[k], o);
+    float dot = 0.f, wk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { wk[k] = __ldg(wgt + b * K + k); dot = fmaf(wk[k], gw[k], dot); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float ds = wk[k] * (gw[k] - dot);      // d loss / d score_k
+      const float d = __ldg(dist + b * K + k);
+      a4 += ds;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int h = lane + 32 * q;
+        if (h < H) {
+          const float pre = fmaf(s_w1[h], d, s_b1[h]);
+          const float act = pre > 0.f ? pre : 0.f;
+          a3[q] = fmaf(ds, act, a3[q]);
+          const float da = pre > 0.f ? ds * s_w2[h] : 0.f;
+          a1[q] = fmaf(da, d, a1[q]);
+          a2[q] += da;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int h = lane + 32 * q;
+    if (h < H) { s_p[warp][h] = a1[q]; s_p[warp][H + h] = a2[q]; s_p[warp][2 * H + h] = a3[q]; }
+  }
+  if (lane == 0) s_p[warp][3 * H] = a4;            // every lane accumulated the same db2
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * H + 1; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_p[w][i];
+    part[(int64_t)blockIdx.x * (3 * H + 1) + i] = s;
+  }
+}
+
+// d_emb[s,:] = sum over the (vehicle, k) pairs that selected segment s of w * dctx[vehicle,:]; one CTA per segment,
+// members from the membership CSR in ascending position order, 8 warps combined in warp order (deterministic)
+__global__ void __launch_bounds__(256)
+k_map_attention_demb(const float* __restrict__ dctx, int D, int K, const float* __restrict__ wgt,
+                     const int32_t* __restrict__ ptr, const int32_t* __restrict__ members, float* __restrict__ demb) {
+  extern __shared__ float sm[];                    // [8][D]
+  const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int beg = __ldg(ptr + s), end = __ldg(ptr + s + 1);
+  for (int c = lane; c < D; c += 32) {
+    float acc = 0.f;
+    for (int i = beg + warp; i < end; i += 8) {
+      const int p = __ldg(members + i);
+      acc = fmaf(__ldg(wgt + p), __ldg(dctx + (int64_t)(p / K) * D + c), acc);
+    }
+    sm[warp * D + c] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w * D + c];
+    demb[(int64_t)s * D + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_map_attention_reduce(const float* __restrict__ part, int nparts, int H, float* __restrict__ dW1,
+                       float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * H + 1) return;
+  float s = 0.f;
+  for (int k = 0; k < nparts; ++k) s += part[(int64_t)k * (3 * H + 1) + i];
+  if (i < H) dW1[i] = s; else if (i < 2 * H) db1[i - H] = s; else if (i < 3 * H) dW2[i - 2 * H] = s; else db2[0] = s;
+}
+
+static int bwd_grid(int64_t B) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(B, 8), (int64_t)num_sms() * 4)); }
+
+}  // namespace sldm
+
+using namespace sldm;
+
+extern "C" int64_t sldm_map_attention_workspace_bytes(int64_t B, int32_t H) {
+  if (B < 0 || H < 0) return -1;
+  return align_bytes((int64_t)bwd_grid(B) * (3 * H + 1) * 4);
+}
+
+extern "C" int sldm_map_attention_forward(const float* pos, int64_t B, const float* centroids, int64_t S,
+                                          const float* emb, int32_t D, int32_t K,
+                                          const float* W1, const float* b1, const float* W2, const float* b2, int32_t H,
+                                          float* ctx, int64_t* idx_out, float* dist_out, float* w_out,
+                                          sldm_stream_t stream) {
+  SLDM_REQUIRE(B >= 0 && S >= 0 && D >= 1, SLDM_EINVAL, "sldm_map_attention_forward: bad sizes");
+  SLDM_REQUIRE(K >= 1 && K <= kMaK, SLDM_EUNSUPPORTED, "sldm_map_attention_forward: k_neighbors=%d outside 1..%d", K, kMaK);
+  SLDM_REQUIRE(H >= 1 && H <= kMaH, SLDM_EUNSUPPORTED, "sldm_map_attention_forward: MLP width %d outside 1..%d", H, kMaH);
+  SLDM_REQUIRE(S >= K, SLDM_ESHAPE, "selected index k out of range");   // torch.topk's message
+  SLDM_REQUIRE(S < ((int64_t)1 << 31), SLDM_EUNSUPPORTED, "sldm_map_attention_forward: S too large");
+  if (B == 0) return SLDM_OK;
+  SLDM_REQUIRE(pos && centroids && emb && W1 && b1 && W2 && b2 && ctx && idx_out && dist_out && w_out, SLDM_EINVAL,
+               "sldm_map_attention_forward: NULL pointer");
+  SLDM_REQUIRE((reinterpret_cast<uintptr_t>(centroids) & 7u) == 0, SLDM_EINVAL, "sldm_map_attention_forward: centroids must be 8-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(B, 8), (int64_t)num_sms() * 8);
+  const float2* c2 = reinterpret_cast<const float2*>(centroids);
+#define SLDM_MA(KK) k_map_attention_fwd<KK><<<grid, 256, 0, s>>>(pos, B, c2, (int)S, emb, D, W1, b1, W2, b2, H, ctx, idx_out, dist_out, w_out)
+  switch (K) {
+    case 1: SLDM_MA(1); break; case 2: SLDM_MA(2); break; case 3: SLDM_MA(3); break; case 4: SLDM_MA(4); break;
+    case 5: SLDM_MA(5); break; case 6: SLDM_MA(6); break; case 7: SLDM_MA(7); break; default: SLDM_MA(8); break;
+  }
+#undef SLDM_MA
+  SLDM_LAUNCH_CHECK("k_map_attention_fwd");
+  return SLDM_OK;
+}
+
+// csr: membership CSR of the selected segments: sldm_csr_build_pairs(NULL, idx (as [B*K] int64), B*K, csr_nodes >= S, ...)
+extern "C" int sldm_map_attention_backward(const float* dctx, int64_t B, const float* emb, int64_t S, int32_t D, int32_t K,
+                                           const int64_t* idx, const float* dist, const float* w,
+                                           const float* W1, const float* b1, const float* W2, int32_t H,
+                                           const int32_t* csr, int64_t csr_nodes,
+                                           float* demb, float* dW1, float* db1, float* dW2, float* db2,
+                                           void* workspace, int64_t workspace_bytes, sldm_stream_t stream) {
+  SLDM_REQUIRE(B >= 0 && S >= 0 && D >= 1 && D <= 1024, SLDM_EINVAL, "sldm_map_attention_backward: bad sizes");
+  SLDM_REQUIRE(K >= 1 && K <= kMaK && H >= 1 && H <= kMaH, SLDM_EUNSUPPORTED, "sldm_map_attention_backward: K / H out of range");
+  SLDM_REQUIRE(dW1 && db1 && dW2 && db2, SLDM_EINVAL, "sldm_map_attention_backward: NULL gradient output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    SLDM_CUDA(cudaMemsetAsync(dW1, 0, H * 4, s)); SLDM_CUDA(cudaMemsetAsync(db1, 0, H * 4, s));
+    SLDM_CUDA(cudaMemsetAsync(dW2, 0, H * 4, s)); SLDM_CUDA(cudaMemsetAsync(db2, 0, 4, s));
+    if (demb && S > 0) SLDM_CUDA(cudaMemsetAsync(demb, 0, (size_t)S * D * 4, s));
+    return SLDM_OK;
+  }
+  SLDM_REQUIRE(dctx && emb && idx && dist && w && W1 && b1 && W2, SLDM_EINVAL, "sldm_map_attention_backward: NULL pointer");
+  SLDM_REQUIRE(workspace != nullptr && workspace_bytes >= sldm_map_attention_workspace_bytes(B, H), SLDM_EWORKSPACE,
+               "sldm_map_attention_backward: workspace too small");
+  float* part = static_cast<float*>(workspace);
+  const int grid = bwd_grid(B);
+#define SLDM_MB(KK) k_map_attention_bwd<KK><<<grid, 256, 0, s>>>(dctx, B, emb, D, idx, dist, w, W1, b1, W2, H, part)
+  switch (K) {
+    case 1: SLDM_MB(1); break; case 2: SLDM_MB(2); break; case 3: SLDM_MB(3); break; case 4: SLDM_MB(4); break;
+    case 5: SLDM_MB(5); break; case 6: SLDM_MB(6); break; case 7: SLDM_MB(7); break; default: SLDM_MB(8); break;
+  }
+#undef SLDM_MB
+  SLDM_LAUNCH_CHECK("k_map_attention_bwd");
+  k_map_attention_reduce<<<1, 256, 0, s>>>(part, grid, H, dW1, db1, dW2, db2);
+  SLDM_LAUNCH_CHECK("k_map_attention_reduce");
+  if (demb != nullptr && S > 0) {
+    SLDM_REQUIRE(csr != nullptr && csr_nodes >= S, SLDM_EINVAL, "sldm_map_attention_backward: membership CSR missing / too small");
+    CsrLayout L = csr_layout(csr_nodes, B * K);
+    k_map_attention_demb<<<(unsigned)S, 256, (size_t)8 * D * sizeof(float), s>>>(
+        dctx, D, K, w, csr + L.off[SLDM_CSR_ROWPTR_DST], csr + L.off[SLDM_CSR_COL_SRC], demb);
+    SLDM_LAUNCH_CHECK("k_map_attention_demb");
+  }
+  return SLDM_OK;
+}

@@ -1,0 +1,178 @@
+"""MapSpatialAttention (src/models/map/mapattention.py:5-56).
+
+Parity is PINNED here: the reference class is plain torch, so the golden vectors under tests/golden/map_attention were
+produced by the reference itself, and the oracle restatement is checked against the imported reference when
+/root/reference is present.  Tolerance: rtol 1e-5 / atol 1e-6 on the context vectors and the gradients (the MLP,
+softmax and the weighted sum are fp32 with a different association than ATen's), adjudicated against an fp64 run of
+the oracle where the fp32 reference itself is no more accurate than that; neighbour indices and distances exact
+except for vehicles whose K-th and (K+1)-th distances are closer than 1e-6 relative (the order of near ties is
+unspecified in torch.topk), which are skipped."""
+import glob
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle.map_attention_oracle import MapSpatialAttentionOracle
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "map_attention", "*.pt")))
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _close(a, b, what, scale=False, scale_ref=None):
+    """scale_ref: parameter gradients are sums of the same B*K terms; d(bias of the last layer) = sum_k ds_k is exactly 0
+    in exact arithmetic (softmax backward), so its rounding noise is measured against the magnitude of its sibling
+    gradients, not against its own (zero) value."""
+    a, b = a.detach().cpu(), b.detach().cpu()
+    ref_mag = float(b.abs().max()) if scale_ref is None else scale_ref
+    atol = ATOL * (max(1.0, ref_mag) if (scale or scale_ref is not None) else 1.0)
+    err = (a - b).abs()
+    assert bool((err <= atol + RTOL * b.abs()).all()), f"{what}: max err {float(err.max()):.3e}"
+
+
+# ------------------------------------------------------------------------------ CPU --
+def test_golden_files_exist():
+    assert len(GOLDEN) == 4
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_reproduces_reference_golden(path):
+    d = torch.load(path)
+    m = MapSpatialAttentionOracle(d["centroids"], d["k"])
+    m.load_state_dict(d["state_dict"], strict=True)
+    emb = d["emb"].clone().requires_grad_(True)
+    out = m(d["pos"], emb)
+    (out * d["upstream"]).sum().backward()
+    assert torch.equal(out.detach(), d["out"])                      # same torch ops, same machine class: bit equal
+    assert torch.allclose(emb.grad, d["demb"], rtol=1e-6, atol=1e-7)
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, d["dparams"][k], rtol=1e-6, atol=1e-7), k
+
+
+def test_oracle_equals_imported_reference_if_present():
+    if not os.path.isdir("/root/reference/src/models/map"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.map.mapattention import MapSpatialAttention as Ref
+    finally:
+        sys.path.pop(0)
+    g = torch.Generator().manual_seed(3)
+    cent, pos, emb = torch.randn(50, 2, generator=g) * 30, torch.randn(21, 2, generator=g) * 30, torch.randn(50, 12, generator=g)
+    torch.manual_seed(1)
+    ref = Ref(cent, k_neighbors=4)
+    orc = MapSpatialAttentionOracle(cent, 4)
+    orc.load_state_dict(ref.state_dict(), strict=True)
+    assert torch.equal(ref(pos, emb), orc(pos, emb))
+
+
+def test_module_contract_matches_reference_fixture():
+    import sldm_gnn_b200 as sg
+    d = torch.load(GOLDEN[0])
+    m = sg.MapSpatialAttention(d["centroids"], d["k"])
+    m.load_state_dict(d["state_dict"], strict=True)                 # same keys, same shapes
+    assert "map_centroids" not in m.state_dict()                    # non-persistent buffer, like the reference
+    with pytest.raises(RuntimeError):
+        m(d["pos"], d["emb"])                                       # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------ GPU --
+def _mask_clear(orc, pos):
+    """vehicles whose K-th and (K+1)-th nearest distances are clearly separated"""
+    d, _ = orc.neighbours(pos)
+    if d.size(1) <= orc.k:
+        return torch.ones(pos.size(0), dtype=torch.bool)
+    a, b = d[:, orc.k - 1], d[:, orc.k]
+    return (b - a) > 1e-6 * b.abs().clamp(min=1e-30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cuda_matches_reference_golden(path):
+    import sldm_gnn_b200 as sg
+    dev = torch.device("cuda:0")
+    d = torch.load(path)
+    m = sg.MapSpatialAttention(d["centroids"], d["k"]).to(dev)
+    m.load_state_dict(d["state_dict"], strict=True)
+    emb = d["emb"].to(dev).requires_grad_(True)
+    out = m(d["pos"].to(dev), emb)
+    (out * d["upstream"].to(dev)).sum().backward()
+    orc = MapSpatialAttentionOracle(d["centroids"], d["k"])
+    ok = _mask_clear(orc, d["pos"])
+    assert float(ok.float().mean()) > 0.95
+    _close(out[ok.to(dev)], d["out"][ok], "ctx")
+    if bool(ok.all()):
+        _close(emb.grad, d["demb"], "demb", scale=True)
+        mag = 10.0 * max(float(v.abs().max()) for v in d["dparams"].values())
+        for k, p in m.named_parameters():
+            _close(p.grad, d["dparams"][k], "grad " + k, scale_ref=mag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S,D,K", [(1, 5, 4, 5), (257, 33, 32, 5), (1000, 3000, 32, 5), (64, 2049, 128, 8), (9, 40, 7, 2)])
+def test_cuda_matches_oracle_random(B, S, D, K):
+    import sldm_gnn_b200 as sg
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B + S)
+    cent = torch.rand(S, 2, generator=g) * 500 - 250
+    pos = torch.rand(B, 2, generator=g) * 500 - 250
+    emb = torch.randn(S, D, generator=g)
+    up = torch.randn(B, D, generator=g)
+    torch.manual_seed(5)
+    orc = MapSpatialAttentionOracle(cent, K)
+    m = sg.MapSpatialAttention(cent, K).to(dev)
+    m.load_state_dict(orc.state_dict(), strict=True)
+    ok = _mask_clear(orc, pos)
+    e_r = emb.clone().requires_grad_(True)
+    o_r = orc(pos, e_r)
+    (o_r * up * ok[:, None]).sum().backward()
+    # fp64 adjudicator: the softmax backward (w * (g - <w,g>)) cancels, so the fp32 reference itself is only accurate
+    # to a few 1e-5 relative on the MLP gradients of small batches; our error against the exact answer must stay within
+    # the bar or within 2x the fp32 reference's own error
+    o64 = MapSpatialAttentionOracle(cent.double(), K).double()
+    o64.load_state_dict({k: v.double() for k, v in orc.state_dict().items()})
+    e_d = emb.double().requires_grad_(True)
+    o_d = o64(pos.double(), e_d)
+    (o_d * (up * ok[:, None]).double()).sum().backward()
+    e_g = emb.to(dev).requires_grad_(True)
+    o_g = m(pos.to(dev), e_g)
+    (o_g * (up * ok[:, None]).to(dev)).sum().backward()
+
+    def adjudicated(got, ref32, ref64, what, mag):
+        got, ref32, ref64 = got.detach().cpu().double(), ref32.detach().double(), ref64.detach()
+        atol = ATOL * max(1.0, mag)
+        e_g64, e_r64 = (got - ref64).abs(), (ref32 - ref64).abs()
+        fine = (e_g64 <= atol + RTOL * ref64.abs()) | (e_g64 <= 2.0 * float(e_r64.max()))
+        assert bool(fine.all()), f"{what}: ours vs fp64 {float(e_g64.max()):.3e}, fp32 reference vs fp64 {float(e_r64.max()):.3e}"
+
+    # the scores are MLP(distance) with distances of a few hundred: an fp32 rounding of the score (1e-5 absolute) moves the
+    # softmax weights by 1e-5 relative in the fp32 reference as well, so the context vectors are adjudicated too
+    adjudicated(o_g[ok.to(dev)], o_r[ok], o_d[ok], "ctx", 1.0)
+    adjudicated(e_g.grad, e_r.grad, e_d.grad, "demb", float(e_d.grad.abs().max()))
+    rp, dp = dict(orc.named_parameters()), dict(o64.named_parameters())
+    mag = max(float(v.grad.abs().max()) for v in dp.values())
+    for k, p in m.named_parameters():
+        adjudicated(p.grad, rp[k].grad, dp[k].grad, "grad " + k, mag)
+    # determinism
+    assert torch.equal(m(pos.to(dev), emb.to(dev)), m(pos.to(dev), emb.to(dev)))
+
+
+@pytest.mark.gpu
+def test_cuda_edge_cases_and_modes():
+    import sldm_gnn_b200 as sg
+    dev = torch.device("cuda:0")
+    cent = torch.randn(10, 2)
+    m = sg.MapSpatialAttention(cent, 5).to(dev)
+    out = m(torch.empty(0, 2, device=dev), torch.randn(10, 8, device=dev))
+    assert out.shape == (0, 8)
+    with torch.inference_mode():
+        assert m(torch.randn(3, 2, device=dev), torch.randn(10, 8, device=dev)).shape == (3, 8)
+    with pytest.raises(RuntimeError):
+        sg.MapSpatialAttention(torch.randn(3, 2), 5).to(dev)(torch.randn(2, 2, device=dev), torch.randn(3, 8, device=dev))
+    # duplicate centroids: ties go to the lower index, the result is still a valid convex combination
+    cent2 = torch.zeros(6, 2)
+    m2 = sg.MapSpatialAttention(cent2, 3).to(dev)
+    emb = torch.arange(6.).view(6, 1).to(dev)
+    o = m2(torch.ones(4, 2, device=dev), emb)
+    assert torch.allclose(o, torch.full((4, 1), 1.0, device=dev))     # equal distances -> equal weights over segments 0,1,2

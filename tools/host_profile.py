@@ -50,3 +50,22 @@ for name, fn in (("sg.collate", lambda: sg.collate(items)), ("torch.cat restatem
     for _ in range(100): fn()
     torch.cuda.synchronize(); t1 = time.perf_counter()
     print("collate of 32 graphs, %-22s %.1f us per batch" % (name + ":", (t1 - t0) / 100 * 1e6))
+
+# ---- map attention: fused kernel vs the reference's torch ops on the device ---------------------------------------
+import torch.nn.functional as F
+B, S, D, K = 200_000, 2048, 32, 5
+g = torch.Generator().manual_seed(0)
+cent = (torch.rand(S, 2, generator=g) * 2000).to(dev); pos = (torch.rand(B, 2, generator=g) * 2000).to(dev)
+emb = torch.randn(S, D, generator=g).to(dev)
+att = sg.MapSpatialAttention(cent, K).to(dev)
+def ref_ops():
+    dists = torch.norm(pos.unsqueeze(1) - cent.unsqueeze(0), dim=2)
+    nd, idx = torch.topk(-dists, k=K, dim=1)
+    w = F.softmax(att.attn_mlp((-nd).unsqueeze(2)).squeeze(2), dim=1).unsqueeze(2)
+    return torch.sum(emb[idx, :] * w, dim=1)
+for name, fn in (("fused kernel", lambda: att(pos, emb)), ("reference torch ops on the GPU", ref_ops)):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10): fn()
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    print("map attention forward B=%d S=%d, %-32s %.3f ms" % (B, S, name + ":", (t1 - t0) / 10 * 1e3))
