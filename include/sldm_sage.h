@@ -225,6 +225,20 @@ int     sldm_map_attention_backward(const float* dctx, int64_t B, const float* e
                                     float* demb, float* dW1, float* db1, float* dW2, float* db2,
                                     void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
 
+/* ---- proximity edges between trajectories (the producer of edge_index) -----
+ * Replaces the O(V^2 T) Python double loop of src/gbuilder.py:88-112 / :244-268 (GraphOnlineCreator, rcv.py:77):
+ * x is [V, T, F] fp32 (feature 0 = X, 1 = Y, 4 = presence flag); for every ordered pair i != j the distances over the
+ * frames where both are present give an edge iff their minimum is <= m_radius, with attributes
+ * [min, max, mean, mean of squares]; edges come out in (i, j) lexicographic order like the reference's lists.
+ *   count: counts[V], offsets[V+1]; the caller reads E = offsets[V] (device -> host) to size the outputs,
+ *   fill : edge_index int64 [2,E], edge_attr fp32 [E,4].      T <= 128.
+ */
+int sldm_edge_build_count(const float* x, int64_t V, int32_t T, int32_t F, float m_radius,
+                          int32_t* counts, int32_t* offsets, sldm_stream_t stream);
+int sldm_edge_build_fill(const float* x, int64_t V, int32_t T, int32_t F, float m_radius,
+                         const int32_t* offsets, int64_t E, int64_t* edge_index, float* edge_attr,
+                         sldm_stream_t stream);
+
 /* ---- whole block, host buffers in / host buffers out -----------------------
  * For hosts that own no device memory (the reference-side stub in
  * INTEGRATION.md).  All pointers are HOST pointers.  Parameters of layer l are

@@ -109,6 +109,36 @@ int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N
                     float* part, int* nparts, cudaStream_t s);
 
 // ---- device helpers -----------------------------------------------------------
+// exclusive scan of one int per thread across a 256-thread CTA; returns this thread's prefix, `total` to every thread.
+// smem: 256/32 + 1 ints.  (csr_build.cu has the general-width version.)
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int& total, int* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < 8 ? smem[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < 8) smem[lane] = winc - w;
+    if (lane == 7) smem[8] = winc;
+  }
+  __syncthreads();
+  const int prefix = smem[warp] + inc - v;
+  total = smem[8];
+  __syncthreads();
+  return prefix;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }

@@ -1,0 +1,66 @@
+"""Proximity edges between trajectories (src/gbuilder.py:88-112, :244-268, rcv.py:77).
+edge_index must be identical to the reference loop's (same pairs, same (i, j) order); min / max distances bit exact;
+mean and mean-square within 1 ulp-level tolerance (rtol 1e-6) of numpy's float32 pairwise sums."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.edges_oracle import proximity_edges_oracle
+
+
+def _traj(V, T, seed, spread=60.0, p_present=0.8):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.zeros(V, T, 6)
+    start = (torch.rand(V, 1, 2, generator=g) - 0.5) * spread
+    vel = (torch.rand(V, 1, 2, generator=g) - 0.5) * 4.0
+    x[:, :, :2] = start + vel * torch.arange(T).view(1, T, 1)
+    x[:, :, 2] = torch.rand(V, T, generator=g) * 30
+    x[:, :, 3] = torch.rand(V, T, generator=g) * 6.28
+    x[:, :, 4] = (torch.rand(V, T, generator=g) < p_present).float()
+    x[:, :, 5] = torch.rand(V, T, generator=g)
+    return x
+
+
+def test_kat_edges_oracle():
+    x = torch.zeros(3, 2, 5)
+    x[0, :, :2] = torch.tensor([[0., 0.], [0., 0.]]); x[1, :, :2] = torch.tensor([[3., 4.], [0., 1.]]); x[2, :, :2] = 100.
+    x[:, :, 4] = 1.0
+    x[1, 0, 4] = 0.0                                          # vehicle 1 absent in frame 0
+    ei, ea = proximity_edges_oracle(x, 2.0)
+    assert torch.equal(ei, torch.tensor([[0, 1], [1, 0]]))   # only frame 1 counts: distance 1 <= 2
+    assert torch.equal(ea, torch.tensor([[1., 1., 1., 1.], [1., 1., 1., 1.]]))
+    ei2, _ = proximity_edges_oracle(x, 0.5)
+    assert ei2.shape == (2, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,T,radius,pp", [(40, 16, 15.0, 0.8), (1, 16, 5.0, 1.0), (7, 5, 1000.0, 1.0), (120, 16, 8.0, 0.5),
+                                           (300, 20, 12.0, 0.9), (33, 9, 0.0, 1.0), (25, 16, 20.0, 0.0), (64, 128, 10.0, 0.7)])
+def test_edges_match_reference_loop(V, T, radius, pp):
+    import sldm_gnn_b200 as sg
+    dev = torch.device("cuda:0")
+    x = _traj(V, T, seed=V + T, p_present=pp)
+    ei_r, ea_r = proximity_edges_oracle(x, radius)
+    ei_g, ea_g = sg.build_proximity_edges(x.to(dev), radius)
+    assert ei_g.dtype == torch.long and ea_g.dtype == torch.float32
+    assert torch.equal(ei_g.cpu(), ei_r), f"edge lists differ: {ei_g.shape} vs {ei_r.shape}"
+    assert torch.equal(ea_g[:, :2].cpu(), ea_r[:, :2]), "min / max distances must be exact"
+    assert torch.allclose(ea_g[:, 2:].cpu(), ea_r[:, 2:], rtol=1e-6, atol=0.0), "mean / mean-square"
+    exact = float((ea_g[:, 2:].cpu() == ea_r[:, 2:]).float().mean()) if ea_r.numel() else 1.0
+    assert exact > 0.99, f"only {exact:.3f} of the means are bit-identical to numpy's pairwise sums"
+
+
+@pytest.mark.gpu
+def test_edges_feed_the_block():
+    import sldm_gnn_b200 as sg
+    dev = torch.device("cuda:0")
+    x = _traj(50, 16, seed=1).to(dev)
+    ei, ea = sg.build_proximity_edges(x, 15.0)
+    assert bool((ei[0] != ei[1]).all()) and ea.shape == (ei.size(1), 4)
+    # symmetric by construction: (i, j) present <=> (j, i) present
+    key = ei[0] * 50 + ei[1]
+    assert torch.equal(torch.sort(key).values, torch.sort(ei[1] * 50 + ei[0]).values)
+    blk = sg.SageBlock([6, 8], negative_slope=0.1).to(dev)
+    assert blk(x[:, -1, :].contiguous(), ei).shape == (50, 8)
+    with pytest.raises(RuntimeError):
+        sg.build_proximity_edges(x.cpu(), 15.0)

@@ -69,3 +69,19 @@ for name, fn in (("fused kernel", lambda: att(pos, emb)), ("reference torch ops 
     for _ in range(10): fn()
     torch.cuda.synchronize(); t1 = time.perf_counter()
     print("map attention forward B=%d S=%d, %-32s %.3f ms" % (B, S, name + ":", (t1 - t0) / 10 * 1e3))
+
+# ---- proximity edges: device build vs the reference's Python double loop (restated in oracle/edges_oracle.py) --------
+from oracle.edges_oracle import proximity_edges_oracle   # tools/ may use the oracle: it is not product code
+V, T = 300, 16
+gx = torch.Generator().manual_seed(0)
+xt = torch.zeros(V, T, 6)
+xt[:, :, :2] = (torch.rand(V, 1, 2, generator=gx) - 0.5) * 400 + (torch.rand(V, 1, 2, generator=gx) - 0.5) * 4 * torch.arange(T).view(1, T, 1)
+xt[:, :, 4] = (torch.rand(V, T, generator=gx) < 0.9).float()
+xd = xt.to(dev)
+for _ in range(3): sg.build_proximity_edges(xd, 30.0)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(50): ei_g, _ = sg.build_proximity_edges(xd, 30.0)
+torch.cuda.synchronize(); t1 = time.perf_counter()
+t2 = time.perf_counter(); ei_r, _ = proximity_edges_oracle(xt, 30.0); t3 = time.perf_counter()
+print("proximity edges V=%d T=%d E=%d: device build %.3f ms (incl. the host read of E), reference Python loop %.1f ms, identical=%s"
+      % (V, T, ei_r.size(1), (t1 - t0) / 50 * 1e3, (t3 - t2) * 1e3, bool(torch.equal(ei_g.cpu(), ei_r))))
