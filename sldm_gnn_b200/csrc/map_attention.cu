@@ -64,29 +64,65 @@ k_map_attention_fwd(const float* __restrict__ pos, int64_t B, const float2* __re
       __syncthreads();
     }
     if (live) {
-      for (int i0 = 0; i0 < tn; i0 += 32) {
-        const int i = i0 + lane;
-        float d2 = INFINITY;
-        if (i < tn) {
-          const float dx = __fsub_rn(px, s_c[i].x), dy = __fsub_rn(py, s_c[i].y);
-          // dx*dx + dy*dy without FMA contraction: the same operations torch.norm performs
-          d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      int i0 = 0;
+      if (t0 == 0) {
+        // bootstrap: the first 32 segments are sorted with a warp bitonic network (15 compare-exchange steps) instead of
+        // 32 serial insertions; lanes 0..K-1 then hold the K best so far
+        unsigned long long key = ~0ull;
+        if (lane < tn) {
+          const float dx = __fsub_rn(px, s_c[lane].x), dy = __fsub_rn(py, s_c[lane].y);
+          key = pack_key(__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), lane);
         }
-        unsigned pass = __ballot_sync(0xffffffffu, i < tn && d2 <= thr2);
-        while (pass) {
-          const int srcl = __ffs(pass) - 1;
-          pass &= pass - 1;
-          const float c2 = __shfl_sync(0xffffffffu, d2, srcl);
-          if (c2 <= thr2) {                        // the threshold may have tightened inside this round (uniform)
-            const unsigned long long key = pack_key(__fsqrt_rn(c2), t0 + i0 + srcl);
-            const bool lt = L < key;
-            const unsigned long long prev = __shfl_up_sync(0xffffffffu, L, 1);
-            const int prevlt = __shfl_up_sync(0xffffffffu, (int)lt, 1);
-            if (lane < K) L = lt ? L : ((lane == 0 || prevlt) ? key : prev);
-            const unsigned long long worst = __shfl_sync(0xffffffffu, L, K - 1);
-            if (worst != ~0ull) {                  // list full: tighten the filter (inflated by a few ulp so that a
-              const float wd = __uint_as_float((unsigned)(worst >> 32));          // candidate that would TIE after the
-              thr2 = __fmul_rn(__fmul_rn(wd, wd), 1.000001f);                      // rounding of sqrt still gets in)
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+            key = (take_min == (other < key)) ? other : key;
+          }
+        }
+        L = lane < K ? key : ~0ull;
+        const unsigned long long worst = __shfl_sync(0xffffffffu, L, K - 1);
+        if (worst != ~0ull) {
+          const float wd = __uint_as_float((unsigned)(worst >> 32));
+          thr2 = __fmul_rn(__fmul_rn(wd, wd), 1.000001f);
+        }
+        i0 = 32;
+      }
+      // afterwards: 64 segments per round (two per lane): one ballot per 32, the filter rarely fires
+      for (; i0 < tn; i0 += 64) {
+        float d2[2];
+        unsigned pass[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = i0 + 32 * h + lane;
+          d2[h] = INFINITY;
+          if (i < tn) {
+            const float dx = __fsub_rn(px, s_c[i].x), dy = __fsub_rn(py, s_c[i].y);
+            // dx*dx + dy*dy without FMA contraction: the same operations torch.norm performs
+            d2[h] = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          }
+          pass[h] = __ballot_sync(0xffffffffu, i < tn && d2[h] <= thr2);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned m = pass[h];
+          while (m) {
+            const int srcl = __ffs(m) - 1;
+            m &= m - 1;
+            const float c2 = __shfl_sync(0xffffffffu, d2[h], srcl);
+            if (c2 <= thr2) {                      // the threshold may have tightened inside this round (uniform)
+              const unsigned long long key = pack_key(__fsqrt_rn(c2), t0 + i0 + 32 * h + srcl);
+              const bool lt = L < key;
+              const unsigned long long prev = __shfl_up_sync(0xffffffffu, L, 1);
+              const int prevlt = __shfl_up_sync(0xffffffffu, (int)lt, 1);
+              if (lane < K) L = lt ? L : ((lane == 0 || prevlt) ? key : prev);
+              const unsigned long long worst = __shfl_sync(0xffffffffu, L, K - 1);
+              if (worst != ~0ull) {                // list full: tighten the filter (inflated by a few ulp so that a
+                const float wd = __uint_as_float((unsigned)(worst >> 32));        // candidate that would TIE after the
+                thr2 = __fmul_rn(__fmul_rn(wd, wd), 1.000001f);                    // rounding of sqrt still gets in)
+              }
             }
           }
         }
