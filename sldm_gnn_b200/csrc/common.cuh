@@ -44,6 +44,20 @@ inline int64_t align_bytes(int64_t n) { return round_up<int64_t>(n, 256); }
 
 int num_sms();  // cached per process (current device at first call)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember it per (call site, device)
+// so that a process driving several GPUs sets it on each of them, and the driver call is not repeated per launch.
+#define SLDM_OPT_IN_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                    \
+    static unsigned long long _done_mask = 0ull;   /* benign race: setting the attribute twice is fine */ \
+    int _dev = 0;                                                                                         \
+    SLDM_CUDA(cudaGetDevice(&_dev));                                                                      \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                                  \
+    if (!(_done_mask & _bit)) {                                                                           \
+      SLDM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _done_mask |= _bit;                                                                                 \
+    }                                                                                                     \
+  } while (0)
+
 // bump allocator over a caller-provided workspace
 struct Arena {
   char* base; int64_t size; int64_t off;

@@ -196,12 +196,10 @@ extern "C" int sldm_readout_forward(const float* x, int64_t N, int32_t F, const 
   const size_t smem = (size_t)kRoWarps * 2 * F * sizeof(float);
   const bool vec = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
   if (vec) {
-    static bool attr = false;
-    if (!attr) { SLDM_CUDA(cudaFuncSetAttribute(k_readout_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    SLDM_OPT_IN_SMEM(k_readout_fwd<true>, 160 * 1024);
     k_readout_fwd<true><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_mean, out_max, ld);
   } else {
-    static bool attr = false;
-    if (!attr) { SLDM_CUDA(cudaFuncSetAttribute(k_readout_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    SLDM_OPT_IN_SMEM(k_readout_fwd<false>, 160 * 1024);
     k_readout_fwd<false><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_mean, out_max, ld);
   }
   SLDM_LAUNCH_CHECK("k_readout_fwd");

@@ -527,11 +527,7 @@ static int launch_b1(int grid, size_t smem, cudaStream_t s,
                      const float* beta, float slope, int64_t N, int Fin, int Fout, int KP,
                      const float* W_l, const float* W_r, const int32_t* rowptr_dst,
                      float* dz, float* dagg, float* dxroot, float* colpart, int need_dx, int vec_w, int vec_o) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLDM_CUDA(cudaFuncSetAttribute(k_ln_bwd_dgrad<TX, TN, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_done = true;
-  }
+  SLDM_OPT_IN_SMEM((k_ln_bwd_dgrad<TX, TN, TM>), 160 * 1024);
   k_ln_bwd_dgrad<TX, TN, TM><<<grid, 256, smem, s>>>(dout, xhat, rstd, gamma, beta, slope, N, Fin, Fout, KP,
                                                      W_l, W_r, rowptr_dst, dz, dagg, dxroot, colpart,
                                                      need_dx, vec_w, vec_o);

@@ -699,12 +699,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   const size_t smem = (size_t)kTcStages * kTcBM * 128 + (size_t)kTcBStages * 2 * pb.Nout * 128 + kTcPatchBytes + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLDM_CUDA(cudaFuncSetAttribute(k_sage_tc<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcPatchBytes + 1024));
-    attr_done = true;
-  }
+  SLDM_OPT_IN_SMEM((k_sage_tc<NT, MODE>), kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcPatchBytes + 1024);
   const int64_t ntiles = ceil_div<int64_t>(pb.N, kTcBM);
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
   long long* trace = nullptr;
@@ -808,11 +803,7 @@ template <int NB>
 static int launch_wgrad(const CUtensorMap& mz, const CUtensorMap& ma, const CUtensorMap& mx, int64_t N, int Fin,
                         int Fout, int cpc, int grid, float* part, cudaStream_t s) {
   const size_t smem = (size_t)kWgStages * 2 * (4 + 2 * NB) * kWgBlk + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLDM_CUDA(cudaFuncSetAttribute(k_wgrad_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  SLDM_OPT_IN_SMEM(k_wgrad_tc<NB>, smem);
   k_wgrad_tc<NB><<<grid, kWgThreads, smem, s>>>(mz, ma, mx, N, Fin, Fout, cpc, part);
   SLDM_LAUNCH_CHECK("k_wgrad_tc");
   return SLDM_OK;
