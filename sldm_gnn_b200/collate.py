@@ -67,7 +67,7 @@ def collate(data_list) -> GraphBatch:
     # pass 1 (host only): one table for ALL attributes -- [ptr (G+1, padded to a multiple of 4) | G rows of 4 per attribute]
     # so that a single pinned upload feeds every launch
     flat = list(ptr_h) + [0] * ((-(G + 1)) % 4)
-    plan, keep = [], []
+    plan = []
     with torch.cuda.device(dev):
         for k in keys:
             vals = [getattr(d, k) for d in data_list]
@@ -105,7 +105,6 @@ def collate(data_list) -> GraphBatch:
                     off += nb
                     mx = max(mx, nb)
                 plan.append(("cat", k, res, row0, off, mx))
-            keep += vals                                    # sources stay alive until the kernels are enqueued
         table = torch.tensor(flat, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
         # pass 2: one launch per attribute
         stream = _stream(dev)
@@ -125,5 +124,6 @@ def collate(data_list) -> GraphBatch:
         out.batch = batch
         out.ptr = table[:G + 1]
         out.num_graphs = G
-        out._keep = keep + [table]                          # released with the batch (kernels are long done by then)
+        # nothing else needs to be kept: the kernels are enqueued on the stream that owns every source tensor, so the
+        # caching allocator cannot hand their memory out before the copies have run
     return out
