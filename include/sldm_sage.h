@@ -211,8 +211,22 @@ int sldm_collate_graph_index(const void* table_dev, const int64_t* node_ptr_dev,
  * backward: gradients for emb (demb [S,D], may be NULL) and the four MLP tensors; positions and centroids are data.
  * csr = membership CSR of idx: sldm_csr_build_pairs(NULL, idx, B*K, csr_nodes >= S, ...) (only needed for demb).
  * K <= 8, H <= 64, S >= K (else SLDM_ESHAPE, like torch.topk).
+ * Two forward entry points with identical results (bit for bit):
+ *   sldm_map_attention_forward       exhaustive scan of the S centroids per position (no preparation);
+ *   sldm_map_attention_forward_grid  ring search over a uniform grid of the centroids.  The centroids are a constant
+ *                                    of the reference module (register_buffer, mapattention.py:9), so the grid is built
+ *                                    once per map: sldm_map_grid_build(centroids, S, grid, sldm_map_grid_bytes(S), ..)
+ *                                    and reused by every forward; rebuild it when the centroids change.
+ * Non-finite positions or centroids: memory-safe, selection unspecified.
  */
 int64_t sldm_map_attention_workspace_bytes(int64_t B, int32_t H);
+int64_t sldm_map_grid_bytes(int64_t S);
+int     sldm_map_grid_build(const float* centroids, int64_t S, void* grid, int64_t grid_bytes, sldm_stream_t stream);
+int     sldm_map_attention_forward_grid(const float* pos, int64_t B, const void* grid, int64_t grid_bytes, int64_t S,
+                                        const float* emb, int32_t D, int32_t K,
+                                        const float* W1, const float* b1, const float* W2, const float* b2, int32_t H,
+                                        float* ctx, int64_t* idx_out, float* dist_out, float* w_out,
+                                        sldm_stream_t stream);
 int     sldm_map_attention_forward(const float* pos, int64_t B, const float* centroids, int64_t S,
                                    const float* emb, int32_t D, int32_t K,
                                    const float* W1, const float* b1, const float* W2, const float* b2, int32_t H,

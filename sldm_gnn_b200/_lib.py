@@ -57,6 +57,9 @@ _PROTOS = {
     "sldm_collate_graph_index": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "sldm_map_attention_workspace_bytes": (_i64, [_i64, _i32]),
     "sldm_map_attention_forward": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "sldm_map_grid_bytes": (_i64, [_i64]),
+    "sldm_map_grid_build": (C.c_int, [_p, _i64, _p, _i64, _p]),
+    "sldm_map_attention_forward_grid": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "sldm_map_attention_backward": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64,
                                               _p, _p, _p, _p, _p, _p, _i64, _p]),
     "sldm_edge_build_count": (C.c_int, [_p, _i64, _i32, _i32, _f, _p, _p, _p]),

@@ -169,6 +169,252 @@ k_map_attention_fwd(const float* __restrict__ pos, int64_t B, const float2* __re
   }   // vehicle groups
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Grid path.  The map is fixed for the life of the module (a registered buffer of the reference class), the positions
+// change every call: the centroids are binned ONCE into a uniform G x G grid over their bounding box (about two per
+// cell), and a query walks square rings of cells around its own cell until the K-th best distance is provably smaller
+// than the distance to anything not yet visited.  ~40 candidates per vehicle instead of S, the same (distance, index)
+// keys as the exhaustive scan above, hence bit-identical idx / dist / w / ctx (tests/test_map_attention.py).
+//   grid buffer: [MapGridHeader 64 B][cell_start int32 G*G+1][cursor int32 G*G][entries float4 S = {x, y, index, -}]
+// Cell of a point: clamp(floor((v - min) / w), 0, G-1) per axis; cell ids are row-major, so a run of cells of one grid
+// row is one contiguous run of entries.  `slack` (4e-6 x the largest coordinate magnitude, ~30x the rounding error of
+// the cell arithmetic) is taken off every geometric bound: a larger slack only costs an extra ring, never an answer.
+struct MapGridHeader { float minx, miny, wx, wy, inv_wx, inv_wy, slack; int32_t G; int32_t pad[8]; };
+static_assert(sizeof(MapGridHeader) == 64, "grid header layout");
+constexpr int kMaGridMax = 512;
+
+struct MapGridLayout { int G; int64_t off_start, off_cursor, off_entries, total; };
+static MapGridLayout map_grid_layout(int64_t S) {
+  MapGridLayout L;
+  int64_t g = (int64_t)ceil(sqrt((double)std::max<int64_t>(S, 1) / 2.0));
+  L.G = (int)std::max<int64_t>(1, std::min<int64_t>(g, kMaGridMax));
+  const int64_t cells = (int64_t)L.G * L.G;
+  L.off_start = 64;
+  L.off_cursor = L.off_start + align_bytes((cells + 1) * 4);
+  L.off_entries = L.off_cursor + align_bytes(cells * 4);
+  L.total = L.off_entries + align_bytes(std::max<int64_t>(S, 1) * 16);
+  return L;
+}
+
+__device__ __forceinline__ int grid_coord(float v, float mn, float inv_w, int G) {
+  const float f = floorf((v - mn) * inv_w);
+  return (int)fminf(fmaxf(f, 0.f), (float)(G - 1));      // NaN -> 0
+}
+
+// one CTA: bounding box, counts, exclusive scan, fill.  Runs once per map.
+__global__ void __launch_bounds__(1024)
+k_map_grid_build(const float2* __restrict__ cent, int S, int G, MapGridHeader* __restrict__ hdr,
+                 int* __restrict__ cell_start, int* __restrict__ cursor, float4* __restrict__ entries) {
+  __shared__ float s_red[4][32];
+  __shared__ int s_warp[33];
+  __shared__ MapGridHeader s_h;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cells = G * G;
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = tid; i < S; i += 1024) {
+    const float2 c = cent[i];
+    if (isfinite(c.x) && isfinite(c.y)) {
+      mnx = fminf(mnx, c.x); mxx = fmaxf(mxx, c.x);
+      mny = fminf(mny, c.y); mxy = fmaxf(mxy, c.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mxx; s_red[2][warp] = mny; s_red[3][warp] = mxy; }
+  for (int i = tid; i < cells; i += 1024) cursor[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 32; ++w) {
+      mnx = fminf(mnx, s_red[0][w]); mxx = fmaxf(mxx, s_red[1][w]);
+      mny = fminf(mny, s_red[2][w]); mxy = fmaxf(mxy, s_red[3][w]);
+    }
+    if (!(mnx <= mxx)) { mnx = mxx = 0.f; mny = mxy = 0.f; }       // no finite centroid at all
+    float wx = (mxx - mnx) / (float)G, wy = (mxy - mny) / (float)G;
+    if (!(wx > 0.f) || !isfinite(wx)) wx = 1.f;                    // degenerate extent: everything in column 0
+    if (!(wy > 0.f) || !isfinite(wy)) wy = 1.f;
+    MapGridHeader h;
+    h.minx = mnx; h.miny = mny; h.wx = wx; h.wy = wy; h.inv_wx = 1.f / wx; h.inv_wy = 1.f / wy;
+    h.slack = 4e-6f * fmaxf(fmaxf(fabsf(mnx), fabsf(mxx)), fmaxf(fabsf(mny), fabsf(mxy)));
+    h.G = G;
+    for (int i = 0; i < 8; ++i) h.pad[i] = 0;
+    s_h = h;
+    *hdr = h;
+  }
+  __syncthreads();
+  const MapGridHeader h = s_h;
+  auto cell_of = [&](const float2 c) {
+    if (!(isfinite(c.x) && isfinite(c.y))) return 0;
+    return grid_coord(c.y, h.miny, h.inv_wy, G) * G + grid_coord(c.x, h.minx, h.inv_wx, G);
+  };
+  for (int i = tid; i < S; i += 1024) atomicAdd(&cursor[cell_of(cent[i])], 1);
+  __syncthreads();
+  // exclusive scan of the cell counts: a contiguous slice per thread, the 1024 slice totals scanned by warps
+  const int per = (cells + 1023) / 1024;
+  const int lo = min(tid * per, cells), hi = min(lo + per, cells);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += cursor[i];
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_warp[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;
+  }
+  __syncthreads();
+  int run = s_warp[warp] + inc - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int c = cursor[i];
+    cell_start[i] = run;
+    cursor[i] = run;
+    run += c;
+  }
+  if (tid == 0) cell_start[cells] = S;
+  __syncthreads();
+  // fill.  The order inside a cell is whatever the atomics give: the search keys are (distance, index), a total order,
+  // so the selected set does not depend on the order of the visits.
+  for (int i = tid; i < S; i += 1024) {
+    const float2 c = cent[i];
+    const int at = atomicAdd(&cursor[cell_of(c)], 1);
+    entries[at] = make_float4(c.x, c.y, __int_as_float(i), 0.f);
+  }
+}
+
+// thread = vehicle for the search and the score MLP; the context rows are then written warp-cooperatively (lane = column)
+template <int K>
+__global__ void __launch_bounds__(256)
+k_map_attention_grid_fwd(const float* __restrict__ pos, int64_t B, const MapGridHeader* __restrict__ hdr,
+                         const int* __restrict__ cell_start, const float4* __restrict__ entries,
+                         const float* __restrict__ emb, int D, const float* __restrict__ W1, const float* __restrict__ b1,
+                         const float* __restrict__ W2, const float* __restrict__ b2, int H,
+                         float* __restrict__ ctx, int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
+                         float* __restrict__ w_out) {
+  __shared__ float s_w1[kMaH], s_b1[kMaH], s_w2[kMaH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int h = threadIdx.x; h < H; h += 256) { s_w1[h] = W1[h]; s_b1[h] = b1[h]; s_w2[h] = W2[h]; }
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool live = b < B;
+  unsigned long long L[K];                         // the K best (distance, index) keys so far, ascending
+#pragma unroll
+  for (int k = 0; k < K; ++k) L[k] = ~0ull;
+  if (live) {
+    const float px = __ldg(pos + 2 * b), py = __ldg(pos + 2 * b + 1);
+    const float minx = __ldg(&hdr->minx), miny = __ldg(&hdr->miny), wx = __ldg(&hdr->wx), wy = __ldg(&hdr->wy);
+    const float slack = __ldg(&hdr->slack);
+    const int G = __ldg(&hdr->G);
+    const int cx = grid_coord(px, minx, __ldg(&hdr->inv_wx), G), cy = grid_coord(py, miny, __ldg(&hdr->inv_wy), G);
+    float thr2 = INFINITY;                         // squared distance a candidate must not exceed
+    auto scan = [&](int beg, int end) {
+      for (int e = beg; e < end; ++e) {
+        const float4 c = __ldg(entries + e);
+        const float dx = __fsub_rn(px, c.x), dy = __fsub_rn(py, c.y);
+        // dx*dx + dy*dy without FMA contraction: the same operations torch.norm performs
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (!(d2 > thr2)) {                        // (NaN passes: the exact key comparison below decides)
+          const unsigned long long key = pack_key(__fsqrt_rn(d2), __float_as_int(c.z));
+          if (key < L[K - 1]) {
+            L[K - 1] = key;
+#pragma unroll
+            for (int k = K - 1; k > 0; --k) {
+              const unsigned long long a = L[k - 1], bk = L[k];
+              const bool sw = bk < a;
+              L[k - 1] = sw ? bk : a;
+              L[k] = sw ? a : bk;
+            }
+            if (L[K - 1] != ~0ull) {               // list full: tighten the filter (inflated by a few ulp so that a
+              const float wd = __uint_as_float((unsigned)(L[K - 1] >> 32));   // candidate that would TIE after the
+              thr2 = __fmul_rn(__fmul_rn(wd, wd), 1.000001f);                  // rounding of sqrt still gets in)
+            }
+          }
+        }
+      }
+    };
+    for (int r = 0;; ++r) {
+      const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r;
+      const int xa = max(x0, 0), xb = min(x1, G - 1);
+      if (y0 >= 0) scan(__ldg(cell_start + y0 * G + xa), __ldg(cell_start + y0 * G + xb + 1));
+      if (r > 0 && y1 <= G - 1) scan(__ldg(cell_start + y1 * G + xa), __ldg(cell_start + y1 * G + xb + 1));
+      for (int y = max(y0 + 1, 0); y <= min(y1 - 1, G - 1); ++y) {
+        if (x0 >= 0) scan(__ldg(cell_start + y * G + x0), __ldg(cell_start + y * G + x0 + 1));
+        if (x1 <= G - 1) scan(__ldg(cell_start + y * G + x1), __ldg(cell_start + y * G + x1 + 1));
+      }
+      // everything within Chebyshev ring r (clipped to the grid) has been seen.  A centroid not seen yet lies beyond one
+      // of the block's four edges that are still inside the grid; its distance is at least the distance to that edge.
+      float bound = INFINITY;
+      bool more = false;
+      if (x0 > 0) { more = true; bound = fminf(bound, px - (minx + (float)x0 * wx)); }
+      if (x1 < G - 1) { more = true; bound = fminf(bound, (minx + (float)(x1 + 1) * wx) - px); }
+      if (y0 > 0) { more = true; bound = fminf(bound, py - (miny + (float)y0 * wy)); }
+      if (y1 < G - 1) { more = true; bound = fminf(bound, (miny + (float)(y1 + 1) * wy) - py); }
+      if (!more) break;                            // the whole grid has been visited
+      if (L[K - 1] != ~0ull && __uint_as_float((unsigned)(L[K - 1] >> 32)) < bound - slack) break;
+    }
+  }
+  // score MLP + softmax per thread (same operation order as the exhaustive kernel: its warp butterfly adds pairs 4, 2, 1 apart)
+  float w[K];
+  int ki[K];
+  {
+    float kd[K], sc[K], ex8[8];
+    const float bias2 = __ldg(b2);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      kd[k] = __uint_as_float((unsigned)(L[k] >> 32));
+      ki[k] = (int)(unsigned)(L[k] & 0xffffffffu);
+      float acc = 0.f;
+      for (int h = 0; h < H; ++h) {
+        const float pre = fmaf(s_w1[h], kd[k], s_b1[h]);
+        acc = fmaf(s_w2[h], pre > 0.f ? pre : 0.f, acc);
+      }
+      sc[k] = acc + bias2;
+      mx = fmaxf(mx, sc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ex8[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) ex8[k] = expf(sc[k] - mx);
+    const float den = ((ex8[0] + ex8[4]) + (ex8[2] + ex8[6])) + ((ex8[1] + ex8[5]) + (ex8[3] + ex8[7]));
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[k] = __fdiv_rn(ex8[k], den);
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        idx_out[b * K + k] = ki[k];
+        dist_out[b * K + k] = kd[k];
+        w_out[b * K + k] = w[k];
+      }
+    }
+  }
+  // ctx = sum_k w_k emb[idx_k]   (k ascending): the warp walks its 32 vehicles, lane = column
+  const int64_t b0 = (int64_t)blockIdx.x * 256 + warp * 32;
+  for (int v = 0; v < 32 && b0 + v < B; ++v) {
+    float wv[K];
+    int iv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { wv[k] = __shfl_sync(0xffffffffu, w[k], v); iv[k] = __shfl_sync(0xffffffffu, ki[k], v); }
+    for (int c = lane; c < D; c += 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc = fmaf(wv[k], __ldg(emb + (int64_t)iv[k] * D + c), acc);
+      ctx[(b0 + v) * D + c] = acc;
+    }
+  }
+}
+
 // per vehicle: gw_k = <emb[idx_k], dctx_b>; ds = softmax backward; MLP parameter gradients as per-CTA partials
 //   part[cta][0:H] = dW1, [H:2H] = db1, [2H:3H] = dW2, [3H] = db2
 template <int K>
@@ -304,6 +550,56 @@ extern "C" int sldm_map_attention_forward(const float* pos, int64_t B, const flo
   }
 #undef SLDM_MA
   SLDM_LAUNCH_CHECK("k_map_attention_fwd");
+  return SLDM_OK;
+}
+
+extern "C" int64_t sldm_map_grid_bytes(int64_t S) {
+  if (S < 0 || S >= ((int64_t)1 << 31)) return -1;
+  return map_grid_layout(S).total;
+}
+
+extern "C" int sldm_map_grid_build(const float* centroids, int64_t S, void* grid, int64_t grid_bytes, sldm_stream_t stream) {
+  SLDM_REQUIRE(S >= 0 && S < ((int64_t)1 << 31), SLDM_EINVAL, "sldm_map_grid_build: bad S");
+  const MapGridLayout L = map_grid_layout(S);
+  SLDM_REQUIRE(grid != nullptr && grid_bytes >= L.total, SLDM_EWORKSPACE, "sldm_map_grid_build: grid buffer too small");
+  SLDM_REQUIRE(S == 0 || centroids != nullptr, SLDM_EINVAL, "sldm_map_grid_build: NULL centroids");
+  SLDM_REQUIRE((reinterpret_cast<uintptr_t>(centroids) & 7u) == 0 && (reinterpret_cast<uintptr_t>(grid) & 15u) == 0, SLDM_EINVAL,
+               "sldm_map_grid_build: centroids must be 8-byte, the grid buffer 16-byte aligned");
+  uint8_t* g = static_cast<uint8_t*>(grid);
+  k_map_grid_build<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(centroids), (int)S, L.G, reinterpret_cast<MapGridHeader*>(g),
+      reinterpret_cast<int*>(g + L.off_start), reinterpret_cast<int*>(g + L.off_cursor), reinterpret_cast<float4*>(g + L.off_entries));
+  SLDM_LAUNCH_CHECK("k_map_grid_build");
+  return SLDM_OK;
+}
+
+extern "C" int sldm_map_attention_forward_grid(const float* pos, int64_t B, const void* grid, int64_t grid_bytes, int64_t S,
+                                               const float* emb, int32_t D, int32_t K,
+                                               const float* W1, const float* b1, const float* W2, const float* b2, int32_t H,
+                                               float* ctx, int64_t* idx_out, float* dist_out, float* w_out,
+                                               sldm_stream_t stream) {
+  SLDM_REQUIRE(B >= 0 && S >= 0 && D >= 1, SLDM_EINVAL, "sldm_map_attention_forward_grid: bad sizes");
+  SLDM_REQUIRE(K >= 1 && K <= kMaK, SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: k_neighbors=%d outside 1..%d", K, kMaK);
+  SLDM_REQUIRE(H >= 1 && H <= kMaH, SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: MLP width %d outside 1..%d", H, kMaH);
+  SLDM_REQUIRE(S >= K, SLDM_ESHAPE, "selected index k out of range");   // torch.topk's message
+  SLDM_REQUIRE(S < ((int64_t)1 << 31), SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: S too large");
+  if (B == 0) return SLDM_OK;
+  const MapGridLayout L = map_grid_layout(S);
+  SLDM_REQUIRE(grid != nullptr && grid_bytes >= L.total, SLDM_EWORKSPACE, "sldm_map_attention_forward_grid: grid buffer too small");
+  SLDM_REQUIRE(pos && emb && W1 && b1 && W2 && b2 && ctx && idx_out && dist_out && w_out, SLDM_EINVAL,
+               "sldm_map_attention_forward_grid: NULL pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint8_t* g = static_cast<const uint8_t*>(grid);
+  const unsigned nblk = (unsigned)ceil_div<int64_t>(B, 256);
+#define SLDM_MG(KK) k_map_attention_grid_fwd<KK><<<nblk, 256, 0, s>>>(pos, B, reinterpret_cast<const MapGridHeader*>(g), \
+      reinterpret_cast<const int*>(g + L.off_start), reinterpret_cast<const float4*>(g + L.off_entries), emb, D, W1, b1, W2, b2, H, \
+      ctx, idx_out, dist_out, w_out)
+  switch (K) {
+    case 1: SLDM_MG(1); break; case 2: SLDM_MG(2); break; case 3: SLDM_MG(3); break; case 4: SLDM_MG(4); break;
+    case 5: SLDM_MG(5); break; case 6: SLDM_MG(6); break; case 7: SLDM_MG(7); break; default: SLDM_MG(8); break;
+  }
+#undef SLDM_MG
+  SLDM_LAUNCH_CHECK("k_map_attention_grid_fwd");
   return SLDM_OK;
 }
 

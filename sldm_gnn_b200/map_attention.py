@@ -5,8 +5,14 @@ tree (`attn_mlp` = Sequential(Linear(1,16), ReLU, Linear(16,1)); `map_centroids`
 reference's state dicts load strictly.  The arithmetic is one fused kernel of libsldm_sage.so (no [B,S] intermediates)
 with a hand-written backward for the embeddings and the MLP; positions and centroids are data and get no gradient.
 Distance ties are broken towards the lower segment index.  CUDA only.
+
+The centroids are a constant of the module, so they are binned once into a uniform grid (sldm_map_grid_build) and every
+forward is a ring search over ~40 candidates per position instead of a scan of all S; the grid is rebuilt when the
+buffer is replaced, moved or written in place.  SLDM_MAP_ATTENTION_SCAN=1 selects the exhaustive kernel (same bits).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn as nn
@@ -18,7 +24,7 @@ from .ops import Csr, _ptr, _require_cuda, _stream
 
 class _MapAttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, centroids, emb, W1, b1, W2, b2, K):
+    def forward(ctx, pos, centroids, emb, W1, b1, W2, b2, K, grid=None):
         B, S, D, H = pos.size(0), centroids.size(0), emb.size(1), W1.numel()
         dev = pos.device
         with torch.cuda.device(dev):
@@ -26,8 +32,13 @@ class _MapAttentionFn(torch.autograd.Function):
             idx = torch.empty((B, K), dtype=torch.long, device=dev)
             dist = torch.empty((B, K), dtype=torch.float32, device=dev)
             w = torch.empty((B, K), dtype=torch.float32, device=dev)
-            check(lib.sldm_map_attention_forward(_ptr(pos), B, _ptr(centroids), S, _ptr(emb), D, K, _ptr(W1), _ptr(b1),
-                                                 _ptr(W2), _ptr(b2), H, _ptr(out), _ptr(idx), _ptr(dist), _ptr(w), _stream(dev)))
+            if grid is not None:
+                check(lib.sldm_map_attention_forward_grid(_ptr(pos), B, grid.data_ptr(), grid.numel(), S, _ptr(emb), D, K,
+                                                          _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), H, _ptr(out), _ptr(idx),
+                                                          _ptr(dist), _ptr(w), _stream(dev)))
+            else:
+                check(lib.sldm_map_attention_forward(_ptr(pos), B, _ptr(centroids), S, _ptr(emb), D, K, _ptr(W1), _ptr(b1),
+                                                     _ptr(W2), _ptr(b2), H, _ptr(out), _ptr(idx), _ptr(dist), _ptr(w), _stream(dev)))
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(emb, idx, dist, w, W1, b1, W2)
             ctx.S, ctx.K = S, K
@@ -59,7 +70,7 @@ class _MapAttentionFn(torch.autograd.Function):
                                                   ws2.data_ptr(), wsb2, _stream(dev)))
             if need_emb and B == 0:
                 demb.zero_()
-        return None, None, demb, dW1, db1, dW2, db2, None
+        return None, None, demb, dW1, db1, dW2, db2, None, None
 
 
 class MapSpatialAttention(nn.Module):
@@ -68,6 +79,20 @@ class MapSpatialAttention(nn.Module):
         self.register_buffer("map_centroids", map_centroids, persistent=False)
         self.k = k_neighbors
         self.attn_mlp = nn.Sequential(nn.Linear(1, 16), nn.ReLU(), nn.Linear(16, 1))
+        self._grid, self._grid_key = None, None
+
+    def _centroid_grid(self, cent):
+        """Uniform grid over the centroids, built on first use and whenever the buffer changes (new tensor, new device,
+        in-place write)."""
+        key = (cent.data_ptr(), cent._version, cent.size(0), cent.device)
+        if self._grid is None or self._grid_key != key:
+            S, dev = cent.size(0), cent.device
+            nbytes = int(lib.sldm_map_grid_bytes(S))
+            with torch.cuda.device(dev):
+                grid = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                check(lib.sldm_map_grid_build(_ptr(cent), S, grid.data_ptr(), nbytes, _stream(dev)))
+            self._grid, self._grid_key, self._grid_src = grid, key, cent     # keep `cent` alive: the key holds its address
+        return self._grid
 
     def forward(self, vehicle_last_positions, map_embeddings):
         pos, emb, cent = vehicle_last_positions, map_embeddings, self.map_centroids
@@ -81,5 +106,7 @@ class MapSpatialAttention(nn.Module):
         if cent.size(0) < self.k:
             raise RuntimeError("selected index k out of range")      # torch.topk's error
         l1, l2 = self.attn_mlp[0], self.attn_mlp[2]
-        return _MapAttentionFn.apply(pos.float().contiguous(), cent.float().contiguous(), emb.float().contiguous(),
-                                     l1.weight.reshape(-1), l1.bias, l2.weight.reshape(-1), l2.bias, int(self.k))
+        cent = cent.float().contiguous()
+        grid = None if os.environ.get("SLDM_MAP_ATTENTION_SCAN") == "1" else self._centroid_grid(cent)
+        return _MapAttentionFn.apply(pos.float().contiguous(), cent, emb.float().contiguous(),
+                                     l1.weight.reshape(-1), l1.bias, l2.weight.reshape(-1), l2.bias, int(self.k), grid)

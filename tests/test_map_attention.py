@@ -178,3 +178,99 @@ def test_cuda_edge_cases_and_modes():
     emb = torch.arange(6.).view(6, 1).to(dev)
     o = m2(torch.ones(4, 2, device=dev), emb)
     assert torch.allclose(o, torch.full((4, 1), 1.0, device=dev))     # equal distances -> equal weights over segments 0,1,2
+
+
+# ------------------------------------------------------------------ grid search vs exhaustive scan --
+def _forward_raw(kind, pos, cent, emb, params, K):
+    """idx / dist / w / ctx of one forward straight through the C-ABI; kind = 'scan' | 'grid'."""
+    from sldm_gnn_b200._lib import lib, check
+    dev = pos.device
+    B, S, D, H = pos.size(0), cent.size(0), emb.size(1), params[0].numel()
+    ctx = torch.empty(B, D, device=dev)
+    idx = torch.empty(B, K, dtype=torch.long, device=dev)
+    dist, w = torch.empty(B, K, device=dev), torch.empty(B, K, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    W1, b1, W2, b2 = params
+    if kind == "scan":
+        check(lib.sldm_map_attention_forward(pos.data_ptr(), B, cent.data_ptr(), S, emb.data_ptr(), D, K, W1.data_ptr(), b1.data_ptr(),
+                                             W2.data_ptr(), b2.data_ptr(), H, ctx.data_ptr(), idx.data_ptr(), dist.data_ptr(), w.data_ptr(), st))
+    else:
+        nb = int(lib.sldm_map_grid_bytes(S))
+        grid = torch.empty(nb, dtype=torch.uint8, device=dev)
+        check(lib.sldm_map_grid_build(cent.data_ptr(), S, grid.data_ptr(), nb, st))
+        check(lib.sldm_map_attention_forward_grid(pos.data_ptr(), B, grid.data_ptr(), nb, S, emb.data_ptr(), D, K, W1.data_ptr(),
+                                                  b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), H, ctx.data_ptr(), idx.data_ptr(),
+                                                  dist.data_ptr(), w.data_ptr(), st))
+    torch.cuda.synchronize()
+    return idx, dist, w, ctx
+
+
+def _geometries():
+    g = torch.Generator().manual_seed(77)
+    r = lambda *s: torch.rand(*s, generator=g)
+    lattice = torch.stack(torch.meshgrid(torch.arange(40.), torch.arange(30.), indexing="ij"), -1).reshape(-1, 2)
+    clusters = (torch.randint(0, 6, (3000, 1), generator=g).float() * 400.0) + torch.randn(3000, 2, generator=g) * 0.5
+    cases = {
+        "uniform": (r(2048, 2) * 2000, r(5000, 2) * 2000, 5),
+        "outside": (r(1500, 2) * 100, torch.cat([r(2000, 2) * 3000 - 1500, torch.tensor([[0., 0.], [100., 100.], [-1e6, 50.], [50., 1e7]])]), 5),
+        "clustered": (clusters, torch.cat([clusters[:500] + 0.1, r(1500, 2) * 2400 - 200]), 8),
+        "collinear_x": (torch.stack([r(700) * 50, torch.full((700,), 3.25)], 1), r(900, 2) * 60 - 5, 4),
+        "collinear_y": (torch.stack([torch.full((700,), -7.5), r(700) * 50], 1), r(900, 2) * 60 - 5, 4),
+        "identical": (torch.full((300, 2), 12.5), r(100, 2) * 30, 6),
+        "lattice_ties": (lattice, torch.cat([lattice[::7], lattice[::5] + 0.5, lattice[::3] + torch.tensor([0.5, 0.0])]), 5),
+        "on_centroids": (r(999, 2) * 10, (r(999, 2) * 10)[:0].new_zeros(0, 2), 3),      # positions filled in below
+        "S_equals_K": (r(5, 2), r(64, 2) * 3 - 1, 5),
+        "single": (r(1, 2), r(33, 2), 1),
+        "far_offset": (r(4000, 2) * 300 + 1.0e6, r(3000, 2) * 320 + 1.0e6 - 10, 5),     # ulp of the coordinates = 0.06
+        "tiny_extent": (r(2000, 2) * 1e-3, r(1000, 2) * 1.2e-3, 5),
+        "large_map": (r(20000, 2) * 5000, r(4000, 2) * 5000, 5),
+        "grid_side_cap": (r(600000, 2) * 9000, r(600, 2) * 9000, 5),                     # G capped at 512
+    }
+    c, _, k = cases["on_centroids"]
+    cases["on_centroids"] = (c, c.clone(), k)
+    return cases
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(_geometries().keys()))
+def test_grid_search_equals_exhaustive_scan(name):
+    """Same (distance, index) keys, same arithmetic after the selection: every output is bit-identical."""
+    dev = torch.device("cuda:0")
+    cent, pos, K = _geometries()[name]
+    S, D = cent.size(0), 16
+    g = torch.Generator().manual_seed(S)
+    emb = torch.randn(S, D, generator=g).to(dev)
+    params = [t.to(dev) for t in (torch.randn(16, generator=g), torch.randn(16, generator=g), torch.randn(16, generator=g),
+                                  torch.randn(1, generator=g))]
+    cent, pos = cent.to(dev).contiguous(), pos.to(dev).contiguous()
+    a = _forward_raw("scan", pos, cent, emb, params, K)
+    b = _forward_raw("grid", pos, cent, emb, params, K)
+    for x, y, what in zip(a, b, ("idx", "dist", "w", "ctx")):
+        assert torch.equal(x, y), f"{name}: {what} differs in {int((x != y).sum())} places"
+    # and the selection is the true K nearest: distances ascending, ties by index, nothing closer left out
+    idx, dist = b[0], b[1]
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())
+    same = dist[:, 1:] == dist[:, :-1]
+    assert bool((idx[:, 1:][same] > idx[:, :-1][same]).all())
+    if S <= 20000:
+        full = torch.cdist(pos.double(), cent.double())
+        kth = full.gather(1, idx[:, -1:])
+        assert int(((full < kth * (1 - 1e-6)).sum(1) > K - 1).sum()) == 0
+
+
+@pytest.mark.gpu
+def test_grid_follows_the_centroid_buffer(monkeypatch):
+    import sldm_gnn_b200 as sg
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    cent = torch.rand(500, 2, generator=g) * 100
+    m = sg.MapSpatialAttention(cent, 5).to(dev)
+    pos, emb = (torch.rand(300, 2, generator=g) * 100).to(dev), torch.randn(500, 8, generator=g).to(dev)
+    o1 = m(pos, emb)
+    grid1 = m._grid
+    assert m(pos, emb) is not None and m._grid is grid1                      # cached
+    m.map_centroids.copy_(torch.rand(500, 2, generator=g).to(dev) * 100)     # in-place write -> rebuilt
+    o2 = m(pos, emb)
+    assert m._grid is not grid1 and not torch.equal(o1, o2)
+    monkeypatch.setenv("SLDM_MAP_ATTENTION_SCAN", "1")
+    assert torch.equal(m(pos, emb), o2)
