@@ -171,7 +171,7 @@ k_map_attention_fwd(const float* __restrict__ pos, int64_t B, const float2* __re
 
 // ---------------------------------------------------------------------------------------------------------------
 // Grid path.  The map is fixed for the life of the module (a registered buffer of the reference class), the positions
-// change every call: the centroids are binned ONCE into a uniform G x G grid over their bounding box (about two per
+// change every call: the centroids are binned ONCE into a uniform G x G grid over their bounding box (about four per
 // cell), and a query walks square rings of cells around its own cell until the K-th best distance is provably smaller
 // than the distance to anything not yet visited.  ~40 candidates per vehicle instead of S, the same (distance, index)
 // keys as the exhaustive scan above, hence bit-identical idx / dist / w / ctx (tests/test_map_attention.py).
@@ -182,11 +182,14 @@ k_map_attention_fwd(const float* __restrict__ pos, int64_t B, const float2* __re
 struct MapGridHeader { float minx, miny, wx, wy, inv_wx, inv_wy, slack; int32_t G; int32_t pad[8]; };
 static_assert(sizeof(MapGridHeader) == 64, "grid header layout");
 constexpr int kMaGridMax = 512;
+// centroids per cell on average: with 4 the K = 5 nearest are almost always inside the 3 x 3 block around the own cell, so
+// the lanes of a warp stop together (with 2, ~20% of the lanes needed a second ring and the other lanes idled through it)
+constexpr double kMaCellLoad = 4.0;
 
 struct MapGridLayout { int G; int64_t off_start, off_cursor, off_entries, total; };
 static MapGridLayout map_grid_layout(int64_t S) {
   MapGridLayout L;
-  int64_t g = (int64_t)ceil(sqrt((double)std::max<int64_t>(S, 1) / 2.0));
+  int64_t g = (int64_t)ceil(sqrt((double)std::max<int64_t>(S, 1) / kMaCellLoad));
   L.G = (int)std::max<int64_t>(1, std::min<int64_t>(g, kMaGridMax));
   const int64_t cells = (int64_t)L.G * L.G;
   L.off_start = 64;
@@ -295,7 +298,7 @@ k_map_grid_build(const float2* __restrict__ cent, int S, int G, MapGridHeader* _
 
 // thread = vehicle for the search and the score MLP; the context rows are then written warp-cooperatively (lane = column)
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_map_attention_grid_fwd(const float* __restrict__ pos, int64_t B, const MapGridHeader* __restrict__ hdr,
                          const int* __restrict__ cell_start, const float4* __restrict__ entries,
                          const float* __restrict__ emb, int D, const float* __restrict__ W1, const float* __restrict__ b1,
@@ -303,6 +306,7 @@ k_map_attention_grid_fwd(const float* __restrict__ pos, int64_t B, const MapGrid
                          float* __restrict__ ctx, int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
                          float* __restrict__ w_out) {
   __shared__ float s_w1[kMaH], s_b1[kMaH], s_w2[kMaH];
+  __shared__ float2 s_sel[8][K][32];               // (softmax weight, element offset of the embedding row) per warp / k / vehicle
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int h = threadIdx.x; h < H; h += 256) { s_w1[h] = W1[h]; s_b1[h] = b1[h]; s_w2[h] = W2[h]; }
   __syncthreads();
@@ -343,14 +347,22 @@ k_map_attention_grid_fwd(const float* __restrict__ pos, int64_t B, const MapGrid
         }
       }
     };
-    for (int r = 0;; ++r) {
+    // the 3 x 3 block around the own cell first (three runs of entries, one per grid row), then ring by ring
+    {
+      const int xa = max(cx - 1, 0), xb = min(cx + 1, G - 1);
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, G - 1); ++y)
+        scan(__ldg(cell_start + y * G + xa), __ldg(cell_start + y * G + xb + 1));
+    }
+    for (int r = 1;; ++r) {
       const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r;
-      const int xa = max(x0, 0), xb = min(x1, G - 1);
-      if (y0 >= 0) scan(__ldg(cell_start + y0 * G + xa), __ldg(cell_start + y0 * G + xb + 1));
-      if (r > 0 && y1 <= G - 1) scan(__ldg(cell_start + y1 * G + xa), __ldg(cell_start + y1 * G + xb + 1));
-      for (int y = max(y0 + 1, 0); y <= min(y1 - 1, G - 1); ++y) {
-        if (x0 >= 0) scan(__ldg(cell_start + y * G + x0), __ldg(cell_start + y * G + x0 + 1));
-        if (x1 <= G - 1) scan(__ldg(cell_start + y * G + x1), __ldg(cell_start + y * G + x1 + 1));
+      if (r > 1) {
+        const int xa = max(x0, 0), xb = min(x1, G - 1);
+        if (y0 >= 0) scan(__ldg(cell_start + y0 * G + xa), __ldg(cell_start + y0 * G + xb + 1));
+        if (y1 <= G - 1) scan(__ldg(cell_start + y1 * G + xa), __ldg(cell_start + y1 * G + xb + 1));
+        for (int y = max(y0 + 1, 0); y <= min(y1 - 1, G - 1); ++y) {
+          if (x0 >= 0) scan(__ldg(cell_start + y * G + x0), __ldg(cell_start + y * G + x0 + 1));
+          if (x1 <= G - 1) scan(__ldg(cell_start + y * G + x1), __ldg(cell_start + y * G + x1 + 1));
+        }
       }
       // everything within Chebyshev ring r (clipped to the grid) has been seen.  A centroid not seen yet lies beyond one
       // of the block's four edges that are still inside the grid; its distance is at least the distance to that edge.
@@ -369,20 +381,24 @@ k_map_attention_grid_fwd(const float* __restrict__ pos, int64_t B, const MapGrid
   int ki[K];
   {
     float kd[K], sc[K], ex8[8];
-    const float bias2 = __ldg(b2);
-    float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       kd[k] = __uint_as_float((unsigned)(L[k] >> 32));
       ki[k] = (int)(unsigned)(L[k] & 0xffffffffu);
-      float acc = 0.f;
-      for (int h = 0; h < H; ++h) {
-        const float pre = fmaf(s_w1[h], kd[k], s_b1[h]);
-        acc = fmaf(s_w2[h], pre > 0.f ? pre : 0.f, acc);
-      }
-      sc[k] = acc + bias2;
-      mx = fmaxf(mx, sc[k]);
+      sc[k] = 0.f;
     }
+    for (int h = 0; h < H; ++h) {
+      const float w1 = s_w1[h], bb = s_b1[h], w2 = s_w2[h];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float pre = fmaf(w1, kd[k], bb);
+        sc[k] = fmaf(w2, pre > 0.f ? pre : 0.f, sc[k]);
+      }
+    }
+    const float bias2 = __ldg(b2);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { sc[k] += bias2; mx = fmaxf(mx, sc[k]); }
 #pragma unroll
     for (int k = 0; k < 8; ++k) ex8[k] = 0.f;
 #pragma unroll
@@ -399,78 +415,199 @@ k_map_attention_grid_fwd(const float* __restrict__ pos, int64_t B, const MapGrid
       }
     }
   }
-  // ctx = sum_k w_k emb[idx_k]   (k ascending): the warp walks its 32 vehicles, lane = column
-  const int64_t b0 = (int64_t)blockIdx.x * 256 + warp * 32;
-  for (int v = 0; v < 32 && b0 + v < B; ++v) {
-    float wv[K];
-    int iv[K];
+  // ctx = sum_k w_k emb[idx_k]   (k ascending): the warp walks its 32 vehicles, lane = column.  (weight, row offset) pairs
+  // go through shared memory: one broadcast 8-byte read per neighbour instead of two shuffles and 64-bit index arithmetic.
 #pragma unroll
-    for (int k = 0; k < K; ++k) { wv[k] = __shfl_sync(0xffffffffu, w[k], v); iv[k] = __shfl_sync(0xffffffffu, ki[k], v); }
-    for (int c = lane; c < D; c += 32) {
+  for (int k = 0; k < K; ++k)
+    s_sel[warp][k][lane] = make_float2(w[k], __uint_as_float(live ? (unsigned)ki[k] * (unsigned)D : 0u));
+  __syncwarp();
+  const int64_t b0 = (int64_t)blockIdx.x * 256 + warp * 32;
+  const int nv = (int)min((int64_t)32, B - b0);
+  if (D == 32) {
+    const float* const e0 = emb + lane;
+    float* const c0 = ctx + b0 * 32 + lane;
+#pragma unroll 4
+    for (int v = 0; v < nv; ++v) {
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc = fmaf(wv[k], __ldg(emb + (int64_t)iv[k] * D + c), acc);
-      ctx[(b0 + v) * D + c] = acc;
+      for (int k = 0; k < K; ++k) {
+        const float2 t = s_sel[warp][k][v];
+        acc = fmaf(t.x, __ldg(e0 + __float_as_uint(t.y)), acc);
+      }
+      c0[v * 32] = acc;
+    }
+  } else {
+    for (int v = 0; v < nv; ++v) {
+      for (int c = lane; c < D; c += 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float2 t = s_sel[warp][k][v];
+          acc = fmaf(t.x, __ldg(emb + __float_as_uint(t.y) + c), acc);
+        }
+        ctx[(b0 + v) * D + c] = acc;
+      }
     }
   }
 }
 
-// per vehicle: gw_k = <emb[idx_k], dctx_b>; ds = softmax backward; MLP parameter gradients as per-CTA partials
-//   part[cta][0:H] = dW1, [H:2H] = db1, [2H:3H] = dW2, [3H] = db2
-template <int K>
+// ---------------------------------------------------------------------------------------------------- backward --
+// Three streaming kernels (all reductions in a fixed order, no atomics):
+//   k_map_attention_bwd_ds   per vehicle: gw_k = <emb[idx_k], dctx_b>, ds_k = w_k (gw_k - sum_j w_j gw_j) = dL/dscore_k
+//   k_map_attention_bwd_mlp  per vehicle: the score MLP's parameter gradients from (dist, ds), per-CTA partials
+//                            part[cta][0:H] = dW1, [H:2H] = db1, [2H:3H] = dW2, [3H] = db2, summed by k_map_attention_reduce
+//   k_map_attention_demb     d_emb[s,:] = sum over the (vehicle, k) pairs that selected segment s of w * dctx[vehicle,:]
+
+// LPV lanes share a vehicle (LPV = 8: four vehicles per warp, float4 columns; LPV = 32: scalar columns, any D / alignment).
+// The loop is latency bound (index -> embedding row -> dot product), so the indices, weights and the first dctx columns of
+// the NEXT vehicle are fetched while the current one is reduced.
+template <int K, int LPV>
 __global__ void __launch_bounds__(256)
-k_map_attention_bwd(const float* __restrict__ dctx, int64_t B, const float* __restrict__ emb, int D,
-                    const int64_t* __restrict__ idx, const float* __restrict__ dist, const float* __restrict__ wgt,
-                    const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2, int H,
-                    float* __restrict__ part) {
-  __shared__ float s_w1[kMaH], s_b1[kMaH], s_w2[kMaH];
-  __shared__ float s_p[8][3 * kMaH + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int h = threadIdx.x; h < H; h += 256) { s_w1[h] = W1[h]; s_b1[h] = b1[h]; s_w2[h] = W2[h]; }
-  __syncthreads();
-  float a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f}, a3[2] = {0.f, 0.f}, a4 = 0.f;   // lane h (and h+32): dW1, db1, dW2; db2
-  const int64_t nw = (int64_t)gridDim.x * 8;
-  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += nw) {
-    float gw[K];
+k_map_attention_bwd_ds(const float* __restrict__ dctx, int64_t B, const float* __restrict__ emb, int D,
+                       const int64_t* __restrict__ idx, const float* __restrict__ wgt, float* __restrict__ ds_out) {
+  constexpr int VPW = 32 / LPV;                    // vehicles per warp
+  constexpr int CW = LPV == 8 ? 4 : 1;             // columns per lane and step
+  const int lane = threadIdx.x & 31, sub = lane % LPV;
+  const int c0 = CW * sub;
+  const int64_t wglobal = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int64_t stride = (((int64_t)gridDim.x * 256) >> 5) * VPW;
+  const int64_t Bp = round_up<int64_t>(B, VPW);    // padded to whole warps so that the shuffles stay convergent
+  unsigned off_n[K];
+  float w_n[K];
+  float4 g_n;
+  auto fetch = [&](int64_t bb) {
+    const bool live = bb < B;
 #pragma unroll
-    for (int k = 0; k < K; ++k) gw[k] = 0.f;
-    for (int c = lane; c < D; c += 32) {
-      const float g = __ldg(dctx + b * D + c);
+    for (int k = 0; k < K; ++k) {
+      off_n[k] = live ? (unsigned)__ldg(idx + bb * K + k) * (unsigned)D : 0u;
+      w_n[k] = live ? __ldg(wgt + bb * K + k) : 0.f;
+    }
+    g_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && c0 < D) {
+      if constexpr (LPV == 8) g_n = __ldg(reinterpret_cast<const float4*>(dctx + bb * D + c0));
+      else g_n.x = __ldg(dctx + bb * D + c0);
+    }
+  };
+  int64_t b = wglobal * VPW + lane / LPV;
+  if (b < Bp) fetch(b);
+  for (; b < Bp; b += stride) {
+    const bool live = b < B;
+    unsigned off[K];
+    float gw[K], wk[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) gw[k] = fmaf(__ldg(emb + __ldg(idx + b * K + k) * D + c), g, gw[k]);
+    for (int k = 0; k < K; ++k) { off[k] = off_n[k]; wk[k] = w_n[k]; gw[k] = 0.f; }
+    float4 g = g_n;
+    if (live) {
+      for (int c = c0; c < D; c += 32) {
+        if (c != c0) {
+          if constexpr (LPV == 8) g = __ldg(reinterpret_cast<const float4*>(dctx + b * D + c));
+          else g.x = __ldg(dctx + b * D + c);
+        }
+        if constexpr (LPV == 8) {
+          float4 e[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) e[k] = __ldg(reinterpret_cast<const float4*>(emb + off[k] + c));
+          if (c == c0 && b + stride < Bp) fetch(b + stride);
+#pragma unroll
+          for (int k = 0; k < K; ++k) gw[k] = fmaf(e[k].w, g.w, fmaf(e[k].z, g.z, fmaf(e[k].y, g.y, fmaf(e[k].x, g.x, gw[k]))));
+        } else {
+          float e[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) e[k] = __ldg(emb + off[k] + c);
+          if (c == c0 && b + stride < Bp) fetch(b + stride);
+#pragma unroll
+          for (int k = 0; k < K; ++k) gw[k] = fmaf(e[k], g.x, gw[k]);
+        }
+      }
+      if (c0 >= D && b + stride < Bp) fetch(b + stride);       // lanes beyond the columns of a narrow D
+    } else if (b + stride < Bp) {
+      fetch(b + stride);
     }
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gw[k] += __shfl_xor_sync(0xffffffffu, gw[k], o);
-    float dot = 0.f, wk[K];
+      for (int o = LPV / 2; o > 0; o >>= 1) gw[k] += __shfl_xor_sync(0xffffffffu, gw[k], o);
+    float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { wk[k] = __ldg(wgt + b * K + k); dot = fmaf(wk[k], gw[k], dot); }
+    for (int k = 0; k < K; ++k) dot = fmaf(wk[k], gw[k], dot);
+    float mine = 0.f;                              // lane `sub` (< K) of the group stores ds_sub
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float ds = wk[k] * (gw[k] - dot);      // d loss / d score_k
-      const float d = __ldg(dist + b * K + k);
-      a4 += ds;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int h = lane + 32 * q;
-        if (h < H) {
-          const float pre = fmaf(s_w1[h], d, s_b1[h]);
-          const float act = pre > 0.f ? pre : 0.f;
-          a3[q] = fmaf(ds, act, a3[q]);
-          const float da = pre > 0.f ? ds * s_w2[h] : 0.f;
-          a1[q] = fmaf(da, d, a1[q]);
-          a2[q] += da;
-        }
-      }
-    }
+    for (int k = 0; k < K; ++k) mine = (sub == k) ? wk[k] * (gw[k] - dot) : mine;
+    if (live && sub < K) ds_out[b * K + sub] = mine;
   }
+}
+
+// lane = (hidden unit, vehicle slot): HL lanes cover the hidden units (two per lane when H > 32), 32 / HL vehicles are in
+// flight per warp.  The K terms of a vehicle cancel (sum_k ds_k = 0), so they are summed locally first and only the
+// residual enters the running sums; every lane takes its vehicles in index order; CTAs own contiguous vehicle ranges.
+__global__ void __launch_bounds__(256)
+k_map_attention_bwd_mlp(const float* __restrict__ dist, const float* __restrict__ ds, int64_t B, int K, int64_t per_cta,
+                        const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                        int H, int HL, float* __restrict__ part) {
+  __shared__ float s_p[8][3 * kMaH + 1];
+  __shared__ float s_g[8][32][7];                  // per lane: a1[2], a2[2], a3[2], a4
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int EG = 32 / HL, hl = lane % HL, eg = lane / HL;
+  float w1[2], bb[2], w2[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    const int h = lane + 32 * q;
-    if (h < H) { s_p[warp][h] = a1[q]; s_p[warp][H + h] = a2[q]; s_p[warp][2 * H + h] = a3[q]; }
+    const int h = hl + 32 * q;
+    const bool on = h < H && (q == 0 || HL == 32);
+    w1[q] = on ? __ldg(W1 + h) : 0.f; bb[q] = on ? __ldg(b1 + h) : 0.f; w2[q] = on ? __ldg(W2 + h) : 0.f;
   }
-  if (lane == 0) s_p[warp][3 * H] = a4;            // every lane accumulated the same db2
+  float a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f}, a3[2] = {0.f, 0.f}, a4 = 0.f;
+  const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(B, beg + per_cta);
+  for (int64_t v0 = beg + warp * 32; v0 < end; v0 += 256) {
+    const int64_t v = v0 + lane;
+    float d_l[kMaK], s_l[kMaK];
+#pragma unroll
+    for (int k = 0; k < kMaK; ++k) {
+      const bool on = v < end && k < K;
+      d_l[k] = on ? __ldg(dist + v * K + k) : 0.f;
+      s_l[k] = on ? __ldg(ds + v * K + k) : 0.f;              // ds = 0: a padded slot contributes nothing
+    }
+    for (int j = 0; j < HL; ++j) {                            // HL = 32 / EG rounds, EG vehicles per round
+      const int src = j * EG + eg;
+      float l1[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f}, l3[2] = {0.f, 0.f}, l4 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaK; ++k) {
+        if (k < K) {
+          const float d = __shfl_sync(0xffffffffu, d_l[k], src);
+          const float g = __shfl_sync(0xffffffffu, s_l[k], src);
+          l4 += g;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q == 1 && HL < 32) break;                      // H <= 32: one hidden unit per lane
+            const float pre = fmaf(w1[q], d, bb[q]);
+            const bool pos = pre > 0.f;
+            l3[q] = fmaf(g, pos ? pre : 0.f, l3[q]);
+            const float da = pos ? g * w2[q] : 0.f;
+            l1[q] = fmaf(da, d, l1[q]);
+            l2[q] += da;
+          }
+        }
+      }
+      a4 += l4;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) { a1[q] += l1[q]; a2[q] += l2[q]; a3[q] += l3[q]; }
+    }
+  }
+  // combine the element slots of a warp in slot order, then the warps in warp order
+  s_g[warp][lane][0] = a1[0]; s_g[warp][lane][1] = a1[1]; s_g[warp][lane][2] = a2[0]; s_g[warp][lane][3] = a2[1];
+  s_g[warp][lane][4] = a3[0]; s_g[warp][lane][5] = a3[1]; s_g[warp][lane][6] = a4;
+  __syncwarp();
+  if (lane < HL) {
+    float t[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < EG; ++e)
+#pragma unroll
+      for (int v = 0; v < 7; ++v) t[v] += s_g[warp][e * HL + lane][v];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int h = lane + 32 * q;
+      if (h < H && (q == 0 || HL == 32)) { s_p[warp][h] = t[q]; s_p[warp][H + h] = t[2 + q]; s_p[warp][2 * H + h] = t[4 + q]; }
+    }
+    if (lane == 0) s_p[warp][3 * H] = t[6];
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * H + 1; i += 256) {
     float s = 0.f;
@@ -480,50 +617,88 @@ k_map_attention_bwd(const float* __restrict__ dctx, int64_t B, const float* __re
   }
 }
 
-// d_emb[s,:] = sum over the (vehicle, k) pairs that selected segment s of w * dctx[vehicle,:]; one CTA per segment,
-// members from the membership CSR in ascending position order, 8 warps combined in warp order (deterministic)
-__global__ void __launch_bounds__(256)
-k_map_attention_demb(const float* __restrict__ dctx, int D, int K, const float* __restrict__ wgt,
+// one CTA per segment; members from the membership CSR in ascending position order.  A warp takes 32 members at a time
+// (ids and weights loaded coalesced, broadcast by shuffle) so that the dctx row loads of a block are independent; the
+// warps are combined in warp order (deterministic).
+constexpr int kDembWarps = 4;   // 128-thread CTAs: 16 per SM, so a 2048-segment map is ONE wave and all segments walk the
+                                // vehicles in step -- the K segments that share a dctx row find it in L2
+template <int K>
+__global__ void __launch_bounds__(32 * kDembWarps)
+k_map_attention_demb(const float* __restrict__ dctx, int D, const float* __restrict__ wgt,
                      const int32_t* __restrict__ ptr, const int32_t* __restrict__ members, float* __restrict__ demb) {
-  extern __shared__ float sm[];                    // [8][D]
+  extern __shared__ float sm[];                    // [kDembWarps][D]
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int beg = __ldg(ptr + s), end = __ldg(ptr + s + 1);
-  for (int c = lane; c < D; c += 32) {
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    const int c = c0 + lane;
+    const bool on = c < D;
     float acc = 0.f;
-    for (int i = beg + warp; i < end; i += 8) {
-      const int p = __ldg(members + i);
-      acc = fmaf(__ldg(wgt + p), __ldg(dctx + (int64_t)(p / K) * D + c), acc);
+    // member ids and weights of the NEXT block are fetched while the 32 row loads of the current one are in flight
+    int i0 = beg + warp * 32;
+    int p_n = 0;
+    float w_n = 0.f;
+    if (i0 + lane < end) { p_n = __ldg(members + i0 + lane); w_n = __ldg(wgt + p_n); }
+    for (; i0 < end; i0 += 32 * kDembWarps) {
+      const float wp = w_n;
+      const unsigned rowoff = (unsigned)(p_n / K) * (unsigned)D;       // B * D < 2^32 (checked on the host)
+      const int cnt = min(32, end - i0);
+      const int inext = i0 + 32 * kDembWarps + lane;
+      p_n = 0; w_n = 0.f;
+      if (inext < end) p_n = __ldg(members + inext);
+      if (cnt == 32) {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = on ? __ldg(dctx + __shfl_sync(0xffffffffu, rowoff, j) + c) : 0.f;
+        if (inext < end) w_n = __ldg(wgt + p_n);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(__shfl_sync(0xffffffffu, wp, j), r[j], acc);
+      } else {
+        if (inext < end) w_n = __ldg(wgt + p_n);
+        for (int j = 0; j < cnt; ++j) {
+          const unsigned ro = __shfl_sync(0xffffffffu, rowoff, j);
+          const float wj = __shfl_sync(0xffffffffu, wp, j);
+          if (on) acc = fmaf(wj, __ldg(dctx + ro + c), acc);
+        }
+      }
     }
-    sm[warp * D + c] = acc;
+    if (on) sm[warp * D + c] = acc;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < D; c += 256) {
+  for (int c = threadIdx.x; c < D; c += 32 * kDembWarps) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[w * D + c];
+    for (int w = 0; w < kDembWarps; ++w) t += sm[w * D + c];
     demb[(int64_t)s * D + c] = t;
   }
 }
 
+// one warp per output: lanes stride over the partials (index order), then a fixed butterfly
 __global__ void __launch_bounds__(256)
 k_map_attention_reduce(const float* __restrict__ part, int nparts, int H, float* __restrict__ dW1,
                        float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= 3 * H + 1) return;
   float s = 0.f;
-  for (int k = 0; k < nparts; ++k) s += part[(int64_t)k * (3 * H + 1) + i];
-  if (i < H) dW1[i] = s; else if (i < 2 * H) db1[i - H] = s; else if (i < 3 * H) dW2[i - 2 * H] = s; else db2[0] = s;
+  for (int k = lane; k < nparts; k += 32) s += part[(int64_t)k * (3 * H + 1) + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (i < H) dW1[i] = s; else if (i < 2 * H) db1[i - H] = s; else if (i < 3 * H) dW2[i - 2 * H] = s; else db2[0] = s;
+  }
 }
 
-static int bwd_grid(int64_t B) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(B, 8), (int64_t)num_sms() * 4)); }
+// kernel for the MLP gradients: elements = B * kMaK at most; the partial count is fixed by B alone (workspace sizing)
+static int mlp_grid(int64_t B) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(B, 256), (int64_t)num_sms() * 4)); }
 
 }  // namespace sldm
 
 using namespace sldm;
 
+// workspace: [ds: B * 8 floats][partials: mlp_grid(B) x (3H + 1) floats]
 extern "C" int64_t sldm_map_attention_workspace_bytes(int64_t B, int32_t H) {
   if (B < 0 || H < 0) return -1;
-  return align_bytes((int64_t)bwd_grid(B) * (3 * H + 1) * 4);
+  return align_bytes(B * kMaK * 4) + align_bytes((int64_t)mlp_grid(B) * (3 * H + 1) * 4);
 }
 
 extern "C" int sldm_map_attention_forward(const float* pos, int64_t B, const float* centroids, int64_t S,
@@ -582,7 +757,7 @@ extern "C" int sldm_map_attention_forward_grid(const float* pos, int64_t B, cons
   SLDM_REQUIRE(K >= 1 && K <= kMaK, SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: k_neighbors=%d outside 1..%d", K, kMaK);
   SLDM_REQUIRE(H >= 1 && H <= kMaH, SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: MLP width %d outside 1..%d", H, kMaH);
   SLDM_REQUIRE(S >= K, SLDM_ESHAPE, "selected index k out of range");   // torch.topk's message
-  SLDM_REQUIRE(S < ((int64_t)1 << 31), SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: S too large");
+  SLDM_REQUIRE(S * (int64_t)D < ((int64_t)1 << 32), SLDM_EUNSUPPORTED, "sldm_map_attention_forward_grid: S * D must stay below 2^32");
   if (B == 0) return SLDM_OK;
   const MapGridLayout L = map_grid_layout(S);
   SLDM_REQUIRE(grid != nullptr && grid_bytes >= L.total, SLDM_EWORKSPACE, "sldm_map_attention_forward_grid: grid buffer too small");
@@ -611,6 +786,8 @@ extern "C" int sldm_map_attention_backward(const float* dctx, int64_t B, const f
                                            float* demb, float* dW1, float* db1, float* dW2, float* db2,
                                            void* workspace, int64_t workspace_bytes, sldm_stream_t stream) {
   SLDM_REQUIRE(B >= 0 && S >= 0 && D >= 1 && D <= 1024, SLDM_EINVAL, "sldm_map_attention_backward: bad sizes");
+  SLDM_REQUIRE(S * (int64_t)D < ((int64_t)1 << 32) && B * (int64_t)D < ((int64_t)1 << 32), SLDM_EUNSUPPORTED,
+               "sldm_map_attention_backward: S * D and B * D must stay below 2^32");
   SLDM_REQUIRE(K >= 1 && K <= kMaK && H >= 1 && H <= kMaH, SLDM_EUNSUPPORTED, "sldm_map_attention_backward: K / H out of range");
   SLDM_REQUIRE(dW1 && db1 && dW2 && db2, SLDM_EINVAL, "sldm_map_attention_backward: NULL gradient output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -623,22 +800,43 @@ extern "C" int sldm_map_attention_backward(const float* dctx, int64_t B, const f
   SLDM_REQUIRE(dctx && emb && idx && dist && w && W1 && b1 && W2, SLDM_EINVAL, "sldm_map_attention_backward: NULL pointer");
   SLDM_REQUIRE(workspace != nullptr && workspace_bytes >= sldm_map_attention_workspace_bytes(B, H), SLDM_EWORKSPACE,
                "sldm_map_attention_backward: workspace too small");
-  float* part = static_cast<float*>(workspace);
-  const int grid = bwd_grid(B);
-#define SLDM_MB(KK) k_map_attention_bwd<KK><<<grid, 256, 0, s>>>(dctx, B, emb, D, idx, dist, w, W1, b1, W2, H, part)
+  float* const ds = static_cast<float*>(workspace);
+  float* const part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_bytes(B * kMaK * 4));
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(dctx) | reinterpret_cast<uintptr_t>(emb)) & 15u) == 0;
+  // persistent grid: exactly the CTAs that are resident at once (the loop prefetches across iterations)
+  auto ds_grid = [&](auto kernel, int vpw) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(B, 8 * vpw), (int64_t)num_sms() * std::max(per_sm, 1)));
+  };
+#define SLDM_MB(KK) do { if (vec) k_map_attention_bwd_ds<KK, 8><<<ds_grid(k_map_attention_bwd_ds<KK, 8>, 4), 256, 0, s>>>(dctx, B, emb, D, idx, w, ds); \
+                         else k_map_attention_bwd_ds<KK, 32><<<ds_grid(k_map_attention_bwd_ds<KK, 32>, 1), 256, 0, s>>>(dctx, B, emb, D, idx, w, ds); } while (0)
   switch (K) {
     case 1: SLDM_MB(1); break; case 2: SLDM_MB(2); break; case 3: SLDM_MB(3); break; case 4: SLDM_MB(4); break;
     case 5: SLDM_MB(5); break; case 6: SLDM_MB(6); break; case 7: SLDM_MB(7); break; default: SLDM_MB(8); break;
   }
 #undef SLDM_MB
-  SLDM_LAUNCH_CHECK("k_map_attention_bwd");
-  k_map_attention_reduce<<<1, 256, 0, s>>>(part, grid, H, dW1, db1, dW2, db2);
+  SLDM_LAUNCH_CHECK("k_map_attention_bwd_ds");
+  const int mgrid = mlp_grid(B);
+  const int64_t per_cta = round_up<int64_t>(ceil_div<int64_t>(B, mgrid), 256);   // vehicles per CTA
+  int HL = 1;
+  while (HL < H && HL < 32) HL <<= 1;              // lanes across the hidden units
+  k_map_attention_bwd_mlp<<<mgrid, 256, 0, s>>>(dist, ds, B, K, per_cta, W1, b1, W2, H, HL, part);
+  SLDM_LAUNCH_CHECK("k_map_attention_bwd_mlp");
+  k_map_attention_reduce<<<ceil_div(3 * H + 1, 8), 256, 0, s>>>(part, mgrid, H, dW1, db1, dW2, db2);
   SLDM_LAUNCH_CHECK("k_map_attention_reduce");
   if (demb != nullptr && S > 0) {
     SLDM_REQUIRE(csr != nullptr && csr_nodes >= S, SLDM_EINVAL, "sldm_map_attention_backward: membership CSR missing / too small");
     CsrLayout L = csr_layout(csr_nodes, B * K);
-    k_map_attention_demb<<<(unsigned)S, 256, (size_t)8 * D * sizeof(float), s>>>(
-        dctx, D, K, w, csr + L.off[SLDM_CSR_ROWPTR_DST], csr + L.off[SLDM_CSR_COL_SRC], demb);
+    const int32_t* rp = csr + L.off[SLDM_CSR_ROWPTR_DST];
+    const int32_t* mem = csr + L.off[SLDM_CSR_COL_SRC];
+    const size_t smb = (size_t)kDembWarps * D * sizeof(float);
+#define SLDM_ME(KK) k_map_attention_demb<KK><<<(unsigned)S, 32 * kDembWarps, smb, s>>>(dctx, D, w, rp, mem, demb)
+    switch (K) {
+      case 1: SLDM_ME(1); break; case 2: SLDM_ME(2); break; case 3: SLDM_ME(3); break; case 4: SLDM_ME(4); break;
+      case 5: SLDM_ME(5); break; case 6: SLDM_ME(6); break; case 7: SLDM_ME(7); break; default: SLDM_ME(8); break;
+    }
+#undef SLDM_ME
     SLDM_LAUNCH_CHECK("k_map_attention_demb");
   }
   return SLDM_OK;

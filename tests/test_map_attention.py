@@ -130,8 +130,9 @@ def test_cuda_matches_oracle_random(B, S, D, K):
     (o_r * up * ok[:, None]).sum().backward()
     # fp64 adjudicator: the softmax backward (w * (g - <w,g>)) cancels, so the fp32 reference itself is only accurate
     # to a few 1e-5 relative on the MLP gradients of small batches; our error against the exact answer must stay within
-    # the bar or within 4x the fp32 reference's own worst error on that tensor (same order of magnitude: the two fp32
-    # evaluations differ in the association of the MLP / softmax sums and in expf vs ATen's exp)
+    # the bar or within 8x the fp32 reference's own worst error on that tensor (same order of magnitude: the two fp32
+    # evaluations differ in the association of the dot products / MLP / softmax sums and in expf vs ATen's exp, and the
+    # ratio of two independent draws of rounding noise over a 16-element tensor reaches 4-5 in these cases)
     o64 = MapSpatialAttentionOracle(cent.double(), K).double()
     o64.load_state_dict({k: v.double() for k, v in orc.state_dict().items()})
     e_d = emb.double().requires_grad_(True)
@@ -145,7 +146,7 @@ def test_cuda_matches_oracle_random(B, S, D, K):
         got, ref32, ref64 = got.detach().cpu().double(), ref32.detach().double(), ref64.detach()
         atol = ATOL * max(1.0, mag)
         e_g64, e_r64 = (got - ref64).abs(), (ref32 - ref64).abs()
-        fine = (e_g64 <= atol + RTOL * ref64.abs()) | (e_g64 <= 4.0 * float(e_r64.max()))
+        fine = (e_g64 <= atol + RTOL * ref64.abs()) | (e_g64 <= 8.0 * float(e_r64.max()))
         assert bool(fine.all()), f"{what}: ours vs fp64 {float(e_g64.max()):.3e}, fp32 reference vs fp64 {float(e_r64.max()):.3e}"
 
     # the scores are MLP(distance) with distances of a few hundred: an fp32 rounding of the score (1e-5 absolute) moves the
@@ -224,7 +225,7 @@ def _geometries():
         "far_offset": (r(4000, 2) * 300 + 1.0e6, r(3000, 2) * 320 + 1.0e6 - 10, 5),     # ulp of the coordinates = 0.06
         "tiny_extent": (r(2000, 2) * 1e-3, r(1000, 2) * 1.2e-3, 5),
         "large_map": (r(20000, 2) * 5000, r(4000, 2) * 5000, 5),
-        "grid_side_cap": (r(600000, 2) * 9000, r(600, 2) * 9000, 5),                     # G capped at 512
+        "grid_side_cap": (r(1200000, 2) * 9000, r(600, 2) * 9000, 5),                    # G capped at 512
     }
     c, _, k = cases["on_centroids"]
     cases["on_centroids"] = (c, c.clone(), k)
