@@ -541,12 +541,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="batch")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["c2"], default="batch")
+    ap.add_argument("--c2-graphs", type=int, default=1024, help="--workload c2: sequences (vehicle graphs) per GPU and step")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-kernel-timing", action="store_true",
                     help="skip the per-kernel-group timing (used for the ncu launch list: only whole steps are launched)")
     args = ap.parse_args()
+    if args.workload == "c2":                  # the full GruSage training step, its own metric (bench_c2.py)
+        import bench_c2
+        return bench_c2.main(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         main_reference(args, wl)

@@ -1,0 +1,176 @@
+"""The model around the block: GruSage, MapEncoder, MapZscoreNorm as drop-ins composed of this package's kernels.
+
+Reference: src/models/grusage.py:12-215 (GruSage), src/models/map/mapencoder.py:6-38 (MapEncoder),
+src/models/map/mapInputNorm.py:3-23 (MapZscoreNorm).  This is SURVEY 8(d)'s configuration C2 -- the full training step
+of the reference's model in an image without torch_geometric: the graph layers (SageBlock, twice: map graph and vehicle
+graph), the map attention and the readout are the CUDA paths of libsldm_sage.so; the station-type embedding, the GRU and
+the small fully connected stacks are torch library layers (cuDNN / cuBLAS), exactly as in the reference.
+
+Same constructor arguments, same module tree (`st_emb`, `gru`, `fc1s`, `map_encoder`, `map_attention`, `sage`, `fc2s`,
+`linout`), so the reference's checkpoints load strictly and `state_dict_no_mapenc()` / `input_params_dict()` /
+`grads()` keep their meaning.  `forward(data)` reads the same attributes of a PyG Batch (or of our GraphBatch):
+x [N,T,F], edge_index, xsttype, xdims, pos_raw, batch.  Differences, both invisible in the results:
+  * 'double' pooling is ONE fused mean|max readout kernel instead of two pools and a cat;
+  * the number of graphs is taken from `data.num_graphs` when the batch carries it (PyG reads `batch.max()` back from
+    the device, a host sync per step).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .map_attention import MapSpatialAttention
+from .readout import global_max_pool, global_mean_max_pool, global_mean_pool
+from .sageblock import SageBlock
+
+
+def _activation(negative_slope):
+    return nn.ReLU() if negative_slope is None else nn.LeakyReLU(negative_slope=negative_slope)
+
+
+def _fc_stack(widths, dropout, negative_slope) -> nn.ModuleList:
+    """Linear -> (Leaky)ReLU -> Dropout|Identity per consecutive pair of widths (grusage.py:63-70, 132-138)."""
+    return nn.ModuleList(
+        nn.Sequential(nn.Linear(a, b), _activation(negative_slope), nn.Identity() if dropout is None else nn.Dropout(p=dropout))
+        for a, b in zip(widths[:-1], widths[1:]))
+
+
+class MapZscoreNorm:
+    """Per-feature z-score over the segments, population variance, sigma clamped at 1e-8 (mapInputNorm.py:12-23)."""
+
+    def __init__(self, map_float_features: torch.Tensor):
+        n = map_float_features.shape[0]
+        self.mu = map_float_features.sum(dim=0, keepdim=True) / n
+        self.sigma = (((map_float_features - self.mu) ** 2).sum(dim=0, keepdim=True) / n).sqrt().clamp(min=1e-8)
+
+    def __call__(self, map_input: torch.Tensor) -> torch.Tensor:
+        return (map_input - self.mu) / self.sigma
+
+    @classmethod
+    def onfly(cls, map_float_features: torch.Tensor) -> torch.Tensor:
+        return cls(map_float_features)(map_float_features)
+
+
+class MapEncoder(nn.Module):
+    """Embeds the static map graph: [float | bool | lane-type embedding] features through a SageBlock
+    (mapencoder.py:6-38).  The map's edge_index is a buffer that never changes, so the block's CSR cache builds its CSR
+    once and every later step is gather + projection only."""
+
+    def __init__(self, map_float_features, map_bool_features, lane_type_cats, graph_edge_indexes, *, lane_embed_dim=2,
+                 sage_hidden_dims=[8, 8], dropout, negative_slope):
+        super().__init__()
+        feats = torch.cat([map_float_features, map_bool_features.to(map_float_features.dtype)], dim=1)
+        self.register_buffer("map_float_features", feats, persistent=False)
+        self.register_buffer("lane_type_cats", lane_type_cats, persistent=False)
+        self.register_buffer("graph_edge_indexes", graph_edge_indexes, persistent=False)
+        self.lane_embedding = nn.Embedding(int(lane_type_cats.max().item()) + 1, lane_embed_dim)
+        self.sage = SageBlock([feats.shape[1] + lane_embed_dim] + list(sage_hidden_dims), dropout=dropout,
+                              negative_slope=negative_slope)
+        self._out_dim = sage_hidden_dims[-1]
+
+    @property
+    def out_dim(self) -> int:
+        return self._out_dim
+
+    def forward(self) -> torch.Tensor:
+        x = torch.cat([self.map_float_features, self.lane_embedding(self.lane_type_cats)], dim=1)
+        return self.sage(x, self.graph_edge_indexes)
+
+
+_POOLS = {"mean": (global_mean_pool, 1), "max": (global_max_pool, 1), "double": (global_mean_max_pool, 2)}
+
+
+class GruSage(nn.Module):
+    def __init__(self, dynamic_features_num, frames_num, gru_hidden_size, gru_num_layers, fc1dims, sage_hidden_dims=[128, 128],
+                 fc2dims=[50, 50], out_dim=1, num_st_types=256, emb_dim=12, dropout=None, negative_slope=None,
+                 global_pooling="double", map_included=True, *, map_tensors=None, mapenc_sage_hdims=[8, 8],
+                 mapenc_lane_embdim=2, map_attention_topk=5, map_embeddings=None, map_centroids=None):
+        super().__init__()
+        if map_included:        # grusage.py:16-20
+            assert (map_tensors is not None) or (map_embeddings is not None), \
+                "If map_included is True, either map_tensors or map_embeddings must be provided"
+            assert map_attention_topk is not None, "If map_included is True, map_attention_topk must be provided"
+            assert (map_tensors is None) or (map_embeddings is None), "Provide either map_tensors or map_embeddings, not both"
+            assert (map_embeddings is None) == (map_centroids is None), \
+                "If providing map_embeddings directly, also provide map_centroids for attention"
+        assert len(sage_hidden_dims) >= 1, "sage_hidden_dims must contain at least one element"
+        if global_pooling not in _POOLS:
+            raise ValueError(f"Unsupported global_pooling method: {global_pooling}")
+        # the snapshot of the constructor arguments (grusage.py:23-42; the map tensors come back through the state dict)
+        self.config_dict = dict(
+            dynamic_features_num=dynamic_features_num, frames_num=frames_num, gru_hidden_size=gru_hidden_size,
+            gru_num_layers=gru_num_layers, fc1dims=fc1dims, sage_hidden_dims=sage_hidden_dims, fc2dims=fc2dims, out_dim=out_dim,
+            num_st_types=num_st_types, emb_dim=emb_dim, dropout=dropout, negative_slope=negative_slope,
+            global_pooling=global_pooling, map_included=map_included, map_attention_topk=map_attention_topk,
+            map_embeddings=map_embeddings, map_centroids=map_centroids)
+        self.dropout, self.negative_slope = dropout, negative_slope
+
+        self.st_emb = nn.Embedding(num_st_types, emb_dim)
+        self.gru = nn.GRU(input_size=dynamic_features_num, hidden_size=gru_hidden_size, num_layers=gru_num_layers, batch_first=True)
+        width = gru_hidden_size + 2 + emb_dim                       # last hidden state | xdims | station-type embedding
+        self.fc1s = _fc_stack([width] + list(fc1dims), dropout, negative_slope)
+        width = ([width] + list(fc1dims))[-1]
+
+        # NOTE the reference only defines these two attributes when map_included is True (grusage.py:74-76) and its
+        # forward() reads map_provided unconditionally; here they always exist
+        self.map_provided = bool(map_included)
+        self.map_tensors = map_included and map_tensors is not None
+        if map_included:
+            if map_tensors is not None:
+                self.map_encoder = MapEncoder(
+                    map_float_features=MapZscoreNorm.onfly(map_tensors["float_features"]),
+                    map_bool_features=map_tensors["bool_features"], lane_type_cats=map_tensors["lane_type_cats"],
+                    graph_edge_indexes=map_tensors["mgraph_edge_indexes"], lane_embed_dim=mapenc_lane_embdim,
+                    sage_hidden_dims=mapenc_sage_hdims, dropout=dropout, negative_slope=negative_slope)
+                self.map_attention = MapSpatialAttention(map_centroids=map_tensors["mseg_centroids"], k_neighbors=map_attention_topk)
+                width += self.map_encoder.out_dim
+            else:
+                self.register_buffer("map_embeddings", map_embeddings, persistent=False)
+                self.map_attention = MapSpatialAttention(map_centroids=map_centroids, k_neighbors=map_attention_topk)
+                width += map_embeddings.shape[1]
+
+        self.sage = SageBlock([width] + list(sage_hidden_dims), dropout=dropout, negative_slope=negative_slope)
+        self._pool, mult = _POOLS[global_pooling]
+        self.fc2s = _fc_stack([sage_hidden_dims[-1] * mult] + list(fc2dims), dropout, negative_slope)
+        self.linout = nn.Linear(([sage_hidden_dims[-1] * mult] + list(fc2dims))[-1], out_dim)
+
+    # the reference exposes the pooling as an attribute (grusage.py:113-120)
+    def global_pool(self, x, batch, size=None):
+        return self._pool(x, batch, size)
+
+    def state_dict_no_mapenc(self):
+        return {k: v for k, v in self.state_dict().items() if not k.startswith("map_encoder")}
+
+    def input_params_dict(self):
+        ipd = dict(self.config_dict)
+        with torch.no_grad():
+            ipd["map_embeddings"] = (self.map_encoder() if self.map_tensors else self.map_embeddings) if self.map_provided else None
+            ipd["map_centroids"] = self.map_attention.map_centroids if self.map_provided else None
+        return ipd
+
+    def forward(self, data):
+        h = self.gru(data.x)[1][-1]                                  # [N, T, F] -> last hidden state of the last layer
+        x = torch.cat([h, data.xdims, self.st_emb(data.xsttype)], dim=1)
+        for fc in self.fc1s:
+            x = fc(x)
+        if self.map_provided:
+            emb = self.map_encoder() if self.map_tensors else self.map_embeddings
+            ctx = self.map_attention(vehicle_last_positions=data.pos_raw[:, -1, :], map_embeddings=emb)
+            x = torch.cat([x, ctx], dim=1)
+        x = self.sage(x, data.edge_index)
+        x = self._pool(x, data.batch, getattr(data, "num_graphs", None))
+        for fc in self.fc2s:
+            x = fc(x)
+        return self.linout(x)
+
+    def grads(self):
+        """Gradient norms per group of layers and in total (grusage.py:197-215)."""
+        groups = {"StType Embedding": self.st_emb, "GRU Layer": self.gru, "FC Layers before SAGE": self.fc1s,
+                  "GraphSAGE Layers": self.sage, "FC Layers after SAGE": self.fc2s, "Final Output Layer": self.linout}
+        flat = {}
+        for name, module in groups.items():
+            parts = [p.grad.view(-1) for p in module.parameters() if p.requires_grad and p.grad is not None]
+            flat[name] = torch.cat(parts) if parts else None
+        present = [g for g in flat.values() if g is not None]
+        total = torch.cat(present).norm().item() if present else None
+        return total, {name: (g.norm().item() if g is not None else None) for name, g in flat.items()}
