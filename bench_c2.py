@@ -272,7 +272,7 @@ def main_ours(args):
 
 
 def _front(model, data):
-    h = model.gru(data.x)[1][-1]
+    h = model._last_hidden(data.x)
     x = torch.cat([h, data.xdims, model.st_emb(data.xsttype)], dim=1)
     for fc in model.fc1s:
         x = fc(x)

@@ -148,8 +148,18 @@ class GruSage(nn.Module):
             ipd["map_centroids"] = self.map_attention.map_centroids if self.map_provided else None
         return ipd
 
+    def _last_hidden(self, x):
+        """[N, T, F] -> last hidden state of the last GRU layer.  cuDNN's GRU indexes its gate workspace (N * T * 3H
+        elements) with 32 bits and faults beyond 2^31 (N = 822k sequences x 16 frames x 288 does); sequences are
+        independent, so large batches go through in slices -- same numbers, no limit."""
+        n, per_seq = x.size(0), x.size(1) * 3 * self.gru.hidden_size
+        rows = max(1, (1 << 30) // max(per_seq, 1))
+        if n <= rows:
+            return self.gru(x)[1][-1]
+        return torch.cat([self.gru(x[i:i + rows])[1][-1] for i in range(0, n, rows)], dim=0)
+
     def forward(self, data):
-        h = self.gru(data.x)[1][-1]                                  # [N, T, F] -> last hidden state of the last layer
+        h = self._last_hidden(data.x)
         x = torch.cat([h, data.xdims, self.st_emb(data.xsttype)], dim=1)
         for fc in self.fc1s:
             x = fc(x)
