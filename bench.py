@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- SageBlock fwd+bwd throughput (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload batch|c4|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload batch|c4|c1|infer|c2] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one training pass of the hot path over one batch: CSR build from a fresh
@@ -15,6 +15,11 @@ Workloads (all synthetic, seeded, random-init weights):
   c4              : one skewed graph, 1 M nodes / 10 M edges, SageBlock([128,128]): HBM
                     roofline stress (BASELINE configs[3]); replicas only at N > 1.
   c1              : 32 unit map graphs, SageBlock([64,64,64]) (BASELINE configs[0]).
+  infer           : the batch shape, forward only under inference_mode (BASELINE configs[2]).
+  c2              : BASELINE configs[1], the reference's FULL training step (GruSage + BCE + Adam) on our kernels; its own
+                    metric (graphs/s) and file (bench_c2.py).  It is not the default because BASELINE's metric is quoted on
+                    SageBlock fwd+bwd (edges/s, % of HBM roofline) and 97 % of that step is the cuDNN GRU the reference also
+                    calls (profiles/r01l_bench_c2_1024.json): the SageBlock edge rate cannot be read off it.
 value   = edge-layer traversals per second (E*L per step), whole job, inputs resident in HBM.
 e2e     = the same through the public module call with pinned HOST inputs: H2D of x and
           edge_index, fwd+bwd, D2H of the loss, all inside the timed region.
