@@ -10,7 +10,7 @@ slope 0.1, map encoder SageBlock [f+8, 32, 32] over a 2048-segment map graph, at
 Batch = G sequences, each one unit vehicle graph (~200 nodes, ~1000 edges) with x [n, 16 frames, 6 features].
 A step = zero_grad, forward, loss, backward, (gradient all-reduce at N > 1,) Adam step, loss.item() -- as in the
 reference's loop.  value = graphs (sequences) per second over all ranks; e2e adds the per-step H2D copy of the batch from
-pinned memory.  The GRU / Linear / Embedding layers are torch library code in the reference and here; `components`
+pinned memory.  The GRU / Linear / Embedding layers are torch library code in the reference and here; `components_ms`
 shows where the step's time goes.  cpu_baseline / --impl reference = oracle/grusage_oracle.py (the composition pinned
 against the reference's own classes) on all host threads, on a bounded sample of the same batch.
 """
@@ -260,8 +260,8 @@ def main_ours(args):
                 "e2e": {"value": G * world / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms2, "steps": e2e_steps},
                 "gpu_launches": int(launches), "components_ms": comp,
-                "roofline": None, "roofline_note": "the step is dominated by torch library layers (cuDNN GRU, cuBLAS) exactly as in the "
-                                                   "reference; the rooflines of our kernels are on the default workload's line"}
+                "roofline": None, "roofline_note": "the step is dominated by the GRU, a torch library layer as in the reference (ATen native path); "
+                                                   "the rooflines of our kernels are on the default workload's line"}
         if not args.no_cpu:
             r = run_cpu(G, min(G, 32), 1, 1, 10.0)
             line["cpu_baseline"] = {"value": r["graphs_per_s"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
