@@ -41,8 +41,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# anything NCCL prints (its version banner at init) must not land on stdout: stdout carries ONE JSON line
+# stdout carries ONE JSON line and nothing else.  NCCL prints its version banner with printf at communicator init
+# (NCCL_DEBUG_FILE does not catch it), so the real stdout is kept aside and file descriptor 1 is pointed at stderr for
+# everything else -- this process's own prints and any library's.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if __name__ == "__main__":
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+else:
+    _JSON_OUT = sys.stdout
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -257,7 +271,7 @@ def main_reference(args, wl):
         "e2e": {"value": r["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle/sage_oracle.py (torch CPU restatement of PyG 2.7.0 SAGEConv; torch-geometric is not installable offline)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(name, wl, N, E, graphs):
@@ -535,7 +549,7 @@ def main_ours(args, wl):
             line["cpu_baseline"] = {"value": c["edges_per_s"], "unit": "edges/s", "cores": c["cores"], "kind": "port",
                                     "sample": c["sample"] + f", {c['iters']} timed iterations (about 10 s) after 1 warm-up",
                                     "graphs_per_sec": c["graphs_per_s"], "ms_per_step": c["ms"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
