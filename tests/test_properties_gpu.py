@@ -71,3 +71,58 @@ def test_layer_properties(gr, cfg):
     N, ei, _ = gr
     hdims, slope = cfg
     check_pair(*run_pair(torch.device("cuda:0"), hdims, slope, ei, N))
+
+
+@st.composite
+def maps(draw):
+    S = draw(st.integers(1, 1500))
+    K = draw(st.integers(1, min(8, S)))
+    B = draw(st.integers(1, 600))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    layout = draw(st.sampled_from(["uniform", "clusters", "line", "lattice", "duplicates", "far_offset"]))
+    spread = draw(st.sampled_from(["inside", "wide", "on_centroids"]))
+    g = torch.Generator().manual_seed(seed)
+    if layout == "uniform":
+        cent = torch.rand(S, 2, generator=g) * 500
+    elif layout == "clusters":
+        cent = torch.randint(0, 5, (S, 1), generator=g).float() * 300 + torch.randn(S, 2, generator=g)
+    elif layout == "line":
+        cent = torch.stack([torch.rand(S, generator=g) * 100, torch.full((S,), 2.0)], 1)
+    elif layout == "lattice":
+        cent = torch.stack([torch.arange(S) % 37, torch.arange(S) // 37], 1).float()
+    elif layout == "duplicates":
+        cent = (torch.rand(max(1, S // 4), 2, generator=g) * 50)[torch.randint(0, max(1, S // 4), (S,), generator=g)]
+    else:
+        cent = torch.rand(S, 2, generator=g) * 200 + 3.0e5
+    lo, hi = cent.min(0).values, cent.max(0).values
+    if spread == "inside":
+        pos = lo + torch.rand(B, 2, generator=g) * (hi - lo)
+    elif spread == "wide":
+        pos = lo - 2 * (hi - lo + 1) + torch.rand(B, 2, generator=g) * 5 * (hi - lo + 1)
+    else:
+        pos = cent[torch.randint(0, S, (B,), generator=g)].clone()
+    return cent.contiguous(), pos.contiguous(), K, seed
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(maps(), st.sampled_from([1, 8, 32, 33, 100]))
+def test_map_attention_grid_search_is_the_exhaustive_scan(m, D):
+    """Any map geometry, any K <= 8: the grid ring search returns the same neighbours, distances, weights and context
+    vectors as the exhaustive scan, bit for bit; the neighbours are the true K nearest (fp64 check) in ascending order."""
+    from test_map_attention import _forward_raw
+    cent, pos, K, seed = m
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(seed ^ 0x9e37)
+    S = cent.size(0)
+    emb = torch.randn(S, D, generator=g).to(dev)
+    params = [t.to(dev) for t in (torch.randn(16, generator=g), torch.randn(16, generator=g), torch.randn(16, generator=g),
+                                  torch.randn(1, generator=g))]
+    a = _forward_raw("scan", pos.to(dev), cent.to(dev), emb, params, K)
+    b = _forward_raw("grid", pos.to(dev), cent.to(dev), emb, params, K)
+    for x, y, what in zip(a, b, ("idx", "dist", "w", "ctx")):
+        assert torch.equal(x, y), what
+    idx, dist = b[0].cpu(), b[1].cpu()
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())
+    full = torch.cdist(pos.double(), cent.double())
+    kth = full.gather(1, idx[:, -1:])
+    assert int(((full < kth * (1 - 1e-5) - 1e-9).sum(1) > K - 1).sum()) == 0
