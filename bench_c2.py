@@ -243,6 +243,7 @@ def main_ours(args):
             b.record(); torch.cuda.synchronize()
             return a.elapsed_time(b) / reps, out
 
+        comp["gru_last_hidden_fwd_training"], _ = timed(lambda: model._last_hidden(data.x))   # saves the gates for backward
         with torch.no_grad():
             comp["gru_fc1_embedding_fwd"], x1 = timed(lambda: _front(model, data))
             comp["map_encoder_sageblock_fwd"], emb = timed(lambda: model.map_encoder())
@@ -270,8 +271,7 @@ def main_ours(args):
                 "e2e": {"value": G * world / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms2, "steps": e2e_steps},
                 "gpu_launches": int(launches), "components_ms": comp,
-                "roofline": None, "roofline_note": "the step is dominated by the GRU, a torch library layer as in the reference (ATen native path); "
-                                                   "the rooflines of our kernels are on the default workload's line"}
+                "roofline": gru_roofline(N, comp.get("gru_last_hidden_fwd_training"), clocks)}
         if not args.no_cpu:
             r = run_cpu(G, min(G, 32), 1, 1, 10.0)
             line["cpu_baseline"] = {"value": r["graphs_per_s"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
@@ -279,6 +279,29 @@ def main_ours(args):
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gru_roofline(N, ms, clocks):
+    """The step's dominant kernel is k_gru_fwd / k_gru_bwd (csrc/gru.cu): FP32 FMA work, bound by the FP32 pipe
+    (128 FMA lanes per SM and clock), not by HBM or the tensor pipe -- reported against that peak at the SM clock
+    sampled during the run."""
+    import ctypes
+    from sldm_gnn_b200 import _lib
+    if not ms or os.environ.get("SLDM_DISABLE_FUSED_GRU", "0") == "1":
+        return None
+    sms = ctypes.c_int(0)
+    _lib.check(_lib.lib.sldm_device_sm_count(ctypes.byref(sms)))
+    mhz = float((clocks or {}).get("sm_mhz") or 0.0) or 1965.0
+    hid = MODEL_KW["gru_hidden_size"]
+    flops = 2.0 * N * T_FRAMES * 3 * hid * (hid + F_DYN)
+    peak = sms.value * 128 * 2 * mhz * 1e6 / 1e12
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "fp32_pipe", "kernel": "gru_last_hidden_fwd", "cuda_kernel": f"k_gru_fwd<{hid}, true>",
+            "achieved": round(ach, 2), "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+            "traffic": None, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
+            "peak_source": f"{sms.value} SMs x 128 FMA/clk x 2 x {mhz:.0f} MHz (SM clock sampled during the run)",
+            "note": "recurrent GEMM h.W_hh^T + gates, all T steps in one launch; SIMT FP32 (parity bar 1e-5 rules out "
+                    "plain TF32; a 3xTF32 tcgen05 version is the next step)"}
 
 
 def _front(model, data):

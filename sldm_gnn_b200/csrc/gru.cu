@@ -1,0 +1,402 @@
+// gru.cu -- fused single-layer GRU over short sequences (the sequence head in front of the vehicle-graph SageBlock).
+//
+// Replaces `gru_out, hlast = self.gru(x); x = hlast[-1]` (src/models/grusage.py:160-161; nn.GRU(input 6, hidden 96,
+// one layer, batch_first) built at grusage.py:55-60) and its autograd backward.  torch runs that as 16 x (2 GEMMs +
+// a cell kernel) forward and as many again backward, with every gate tensor making a round trip through HBM; here the
+// whole recurrence of a tile of 64 sequences stays on one SM:
+//
+//   forward  (k_gru_fwd):  W_hh [3H,H] lives in shared memory (row stride H+4 floats: conflict-free 128-bit loads with
+//            lane = hidden unit), a warp owns 8 sequences for all T steps (its h rows are read as shared-memory
+//            broadcasts), a lane owns H/32 hidden units x 3 gates x 8 rows = 72 fp32 accumulators at H = 96; the gate
+//            math of a (row, unit) is local to its thread, so the time loop needs no block-level barrier at all.
+//            When training it writes h_{t-1}, r, z, n and (W_hn h + b_hn) per step -- what torch's fused cell saves.
+//   backward (k_gru_bwd):  the same tiling walks t = T-1 .. 0 with W_hh transposed in shared memory
+//            (dh_{t-1} = dh_t z + [dr dz dn r] W_hh); it emits the hidden-gate gradients dgh [N,T,3H] for the one
+//            library GEMM that is left (dW_hh = dgh^T h_prev) and accumulates dW_ih, db_ih, db_hh per CTA in
+//            registers (fixed order; the per-CTA partials are summed by the caller).
+//
+// Arithmetic: FP32 FMA in sequential k order, expf / tanhf / IEEE division like ATen's gru_cell_forward, i.e. the
+// reference's own formulas (aten/src/ATen/native/cuda/RNN.cu); bound by the FP32 pipe (2*3H*H flops per sequence and
+// step each way), not by HBM.  Limits: H in {32, 64, 96}, input width <= 8, the tile's x must fit shared memory.
+#include "common.cuh"
+#include <algorithm>
+
+namespace sldm {
+namespace {
+
+constexpr int kGruRows = 64;      // sequences per CTA
+constexpr int kGruRpw = 8;        // sequences per warp
+constexpr int kGruThreads = 256;
+constexpr int kGruMaxI = 8;
+constexpr int kGruLdi = 9;        // W_ih row stride in shared memory (odd: conflict-free scalar loads)
+constexpr int64_t kGruSmemMax = 227 * 1024;
+
+__device__ __forceinline__ float gru_sigmoid(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ void fma4(float& acc, const float4& a, const float4& b) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+}
+
+__device__ __forceinline__ void load_x_tile(float* xs, const float* __restrict__ x, int64_t row0, int nrows, int TI) {
+  const float* xg = x + row0 * TI;
+  for (int i = threadIdx.x; i < kGruRows * TI; i += kGruThreads) xs[i] = i < nrows * TI ? __ldg(xg + i) : 0.f;
+}
+
+template <int H, bool SAVE>
+__global__ void __launch_bounds__(kGruThreads, 1)
+k_gru_fwd(const float* __restrict__ x, int64_t N, int T, int I,
+          const float* __restrict__ W_ih, const float* __restrict__ W_hh,
+          const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+          float* __restrict__ h_last, float* __restrict__ hp, float* __restrict__ sr,
+          float* __restrict__ sz, float* __restrict__ sn, float* __restrict__ shn) {
+  constexpr int U = H / 32, LDW = H + 4;
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                        // [3H][LDW]
+  float* hs = Ws + 3 * H * LDW;          // [64][H]   current hidden state of the tile
+  float* Wi = hs + kGruRows * H;         // [3H][9]
+  float* bs = Wi + 3 * H * kGruLdi;      // b_ir+b_hr | b_iz+b_hz | b_in | b_hn
+  float* xs = bs + 4 * H;                // [64][T*I]
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kGruRows;
+  const int nrows = (int)min((int64_t)kGruRows, N - row0);
+  const int TI = T * I;
+
+  for (int i = tid; i < 3 * H * (H / 4); i += kGruThreads) {
+    const int r = i / (H / 4), c = i % (H / 4);
+    *reinterpret_cast<float4*>(Ws + r * LDW + 4 * c) = __ldg(reinterpret_cast<const float4*>(W_hh) + i);
+  }
+  for (int i = tid; i < 3 * H * I; i += kGruThreads) Wi[(i / I) * kGruLdi + (i % I)] = __ldg(W_ih + i);
+  for (int i = tid; i < H; i += kGruThreads) {
+    bs[i] = __ldg(b_ih + i) + __ldg(b_hh + i);
+    bs[H + i] = __ldg(b_ih + H + i) + __ldg(b_hh + H + i);
+    bs[2 * H + i] = __ldg(b_ih + 2 * H + i);
+    bs[3 * H + i] = __ldg(b_hh + 2 * H + i);
+  }
+  for (int i = tid; i < kGruRows * H; i += kGruThreads) hs[i] = 0.f;
+  load_x_tile(xs, x, row0, nrows, TI);
+  __syncthreads();
+
+  const int r0 = w * kGruRpw;
+  const float* hrow = hs + r0 * H;
+  const float* wrow = Ws + l * LDW;
+  float hreg[kGruRpw][U];
+#pragma unroll
+  for (int i = 0; i < kGruRpw; ++i)
+#pragma unroll
+    for (int u = 0; u < U; ++u) hreg[i][u] = 0.f;
+
+  for (int t = 0; t < T; ++t) {
+    float ar[kGruRpw][U], az[kGruRpw][U], an[kGruRpw][U];
+#pragma unroll
+    for (int i = 0; i < kGruRpw; ++i)
+#pragma unroll
+      for (int u = 0; u < U; ++u) ar[i][u] = az[i][u] = an[i][u] = 0.f;
+
+    // hidden part: [8 rows] x [3 gates x U units] over k, h rows as broadcasts, weights one row per lane
+#pragma unroll 2
+    for (int k = 0; k < H; k += 4) {
+      float4 hv[kGruRpw];
+#pragma unroll
+      for (int i = 0; i < kGruRpw; ++i) hv[i] = *reinterpret_cast<const float4*>(hrow + i * H + k);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wrow + (u * 32) * LDW + k);
+        const float4 w1 = *reinterpret_cast<const float4*>(wrow + (H + u * 32) * LDW + k);
+        const float4 w2 = *reinterpret_cast<const float4*>(wrow + (2 * H + u * 32) * LDW + k);
+#pragma unroll
+        for (int i = 0; i < kGruRpw; ++i) {
+          fma4(ar[i][u], hv[i], w0);
+          fma4(az[i][u], hv[i], w1);
+          fma4(an[i][u], hv[i], w2);
+        }
+      }
+    }
+    if (SAVE) {
+#pragma unroll
+      for (int i = 0; i < kGruRpw; ++i)
+        if (r0 + i < nrows) {
+          const int64_t o = ((row0 + r0 + i) * T + t) * H + l;
+#pragma unroll
+          for (int u = 0; u < U; ++u) hp[o + 32 * u] = hreg[i][u];
+        }
+    }
+    // input part (I <= 8): r and z continue their accumulators, the n gate keeps its input half apart
+    float ai[kGruRpw][U];
+#pragma unroll
+    for (int i = 0; i < kGruRpw; ++i)
+#pragma unroll
+      for (int u = 0; u < U; ++u) ai[i][u] = 0.f;
+    for (int i2 = 0; i2 < I; ++i2) {
+      float xv[kGruRpw];
+#pragma unroll
+      for (int i = 0; i < kGruRpw; ++i) xv[i] = xs[(r0 + i) * TI + t * I + i2];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float wr = Wi[(l + 32 * u) * kGruLdi + i2];
+        const float wz = Wi[(H + l + 32 * u) * kGruLdi + i2];
+        const float wn = Wi[(2 * H + l + 32 * u) * kGruLdi + i2];
+#pragma unroll
+        for (int i = 0; i < kGruRpw; ++i) {
+          ar[i][u] = fmaf(xv[i], wr, ar[i][u]);
+          az[i][u] = fmaf(xv[i], wz, az[i][u]);
+          ai[i][u] = fmaf(xv[i], wn, ai[i][u]);
+        }
+      }
+    }
+    // gates (ATen gru_cell_forward): r, z = sigmoid, n = tanh(i_n + b_in + r (h_n + b_hn)), h' = n + z (h - n)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = l + 32 * u;
+      const float br = bs[j], bz = bs[H + j], bin = bs[2 * H + j], bhn = bs[3 * H + j];
+#pragma unroll
+      for (int i = 0; i < kGruRpw; ++i) {
+        const float rg = gru_sigmoid(ar[i][u] + br);
+        const float zg = gru_sigmoid(az[i][u] + bz);
+        const float hn = an[i][u] + bhn;
+        const float ng = tanhf(ai[i][u] + bin + rg * hn);
+        if (SAVE && r0 + i < nrows) {
+          const int64_t o = ((row0 + r0 + i) * T + t) * H + j;
+          sr[o] = rg; sz[o] = zg; sn[o] = ng; shn[o] = hn;
+        }
+        hreg[i][u] = ng + zg * (hreg[i][u] - ng);
+      }
+    }
+    __syncwarp();   // every lane has finished reading the warp's h rows
+#pragma unroll
+    for (int i = 0; i < kGruRpw; ++i)
+#pragma unroll
+      for (int u = 0; u < U; ++u) hs[(r0 + i) * H + l + 32 * u] = hreg[i][u];
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < kGruRpw; ++i)
+    if (r0 + i < nrows) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) h_last[(row0 + r0 + i) * H + l + 32 * u] = hreg[i][u];
+    }
+}
+
+// per-CTA partial layout (floats): [28*U][32 lanes]: v = (u*3+g)*8 + i2 -> dW_ih[g*H + 32u + lane][i2];
+// v = 24U + u*3 + g -> db_ih[g*H + 32u + lane]; v = 27U + u -> db_hh[2H + 32u + lane] (its r and z thirds equal db_ih's)
+template <int H>
+__global__ void __launch_bounds__(kGruThreads, 1)
+k_gru_bwd(const float* __restrict__ x, int64_t N, int T, int I, const float* __restrict__ W_hh,
+          const float* __restrict__ dh_last, const float* __restrict__ hp, const float* __restrict__ sr,
+          const float* __restrict__ sz, const float* __restrict__ sn, const float* __restrict__ shn,
+          float* __restrict__ dgh, float* __restrict__ gin_out, float* __restrict__ parts) {
+  constexpr int U = H / 32, G3 = 3 * H, LDT = 3 * H + 4, V = 28 * U;
+  extern __shared__ __align__(16) float sm[];
+  float* Wt = sm;                       // [H][LDT]: Wt[j][k] = W_hh[k][j]
+  float* gs = Wt + H * LDT;             // [64][3H]  hidden-gate gradients of the current step
+  float* xs = gs + kGruRows * G3;       // [64][T*I]
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kGruRows;
+  const int nrows = (int)min((int64_t)kGruRows, N - row0);
+  const int TI = T * I;
+
+  for (int i = tid; i < G3 * H; i += kGruThreads) Wt[(i % H) * LDT + (i / H)] = __ldg(W_hh + i);
+  load_x_tile(xs, x, row0, nrows, TI);
+  __syncthreads();
+
+  const int r0 = w * kGruRpw;
+  float dh[kGruRpw][U];
+#pragma unroll
+  for (int i = 0; i < kGruRpw; ++i)
+#pragma unroll
+    for (int u = 0; u < U; ++u) dh[i][u] = r0 + i < nrows ? __ldg(dh_last + (row0 + r0 + i) * H + l + 32 * u) : 0.f;
+  float dWi[U][3][kGruMaxI], dbi[U][3], dbn[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    dbn[u] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      dbi[u][g] = 0.f;
+#pragma unroll
+      for (int i2 = 0; i2 < kGruMaxI; ++i2) dWi[u][g][i2] = 0.f;
+    }
+  }
+  const float* grow = gs + r0 * G3;
+  const float* wrow = Wt + l * LDT;
+
+  for (int t = T - 1; t >= 0; --t) {
+    // cell backward (ATen gru_cell_backward) for the thread's (row, unit) pairs
+#pragma unroll
+    for (int i = 0; i < kGruRpw; ++i) {
+      const bool valid = r0 + i < nrows;
+      float xv[kGruMaxI];
+#pragma unroll
+      for (int i2 = 0; i2 < kGruMaxI; ++i2) xv[i2] = i2 < I ? xs[(r0 + i) * TI + t * I + i2] : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = l + 32 * u;
+        const int64_t o = ((row0 + r0 + i) * T + t) * H + j;
+        float rg = 0.f, zg = 0.f, ng = 0.f, hn = 0.f, hpv = 0.f;
+        if (valid) { rg = __ldg(sr + o); zg = __ldg(sz + o); ng = __ldg(sn + o); hn = __ldg(shn + o); hpv = __ldg(hp + o); }
+        const float g = dh[i][u];
+        const float gig = g * (hpv - ng) * (1.f - zg) * zg;
+        const float ghx = g * zg;
+        const float gin = g * (1.f - zg) * (1.f - ng * ng);
+        const float ghn = gin * rg;
+        const float grg = gin * hn * (1.f - rg) * rg;
+        if (valid) {
+          const int64_t og = ((row0 + r0 + i) * T + t) * G3 + j;
+          dgh[og] = grg; dgh[og + H] = gig; dgh[og + 2 * H] = ghn;
+          if (gin_out != nullptr) gin_out[o] = gin;
+        }
+        float* gr = gs + (r0 + i) * G3 + j;
+        gr[0] = grg; gr[H] = gig; gr[2 * H] = ghn;
+        dh[i][u] = ghx;
+        dbi[u][0] += grg; dbi[u][1] += gig; dbi[u][2] += gin; dbn[u] += ghn;
+#pragma unroll
+        for (int i2 = 0; i2 < kGruMaxI; ++i2) {
+          dWi[u][0][i2] = fmaf(grg, xv[i2], dWi[u][0][i2]);
+          dWi[u][1][i2] = fmaf(gig, xv[i2], dWi[u][1][i2]);
+          dWi[u][2][i2] = fmaf(gin, xv[i2], dWi[u][2][i2]);
+        }
+      }
+    }
+    __syncwarp();
+    // dh_{t-1} = dh_t z + dgh W_hh : [8 rows] x [U units] over k = 0..3H
+#pragma unroll 2
+    for (int k = 0; k < G3; k += 4) {
+      float4 gv[kGruRpw];
+#pragma unroll
+      for (int i = 0; i < kGruRpw; ++i) gv[i] = *reinterpret_cast<const float4*>(grow + i * G3 + k);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4 wv = *reinterpret_cast<const float4*>(wrow + (32 * u) * LDT + k);
+#pragma unroll
+        for (int i = 0; i < kGruRpw; ++i) fma4(dh[i][u], gv[i], wv);
+      }
+    }
+    __syncwarp();
+  }
+
+  // parameter-gradient partials: warps combined in index order
+  __syncthreads();
+  float* red = sm;   // [8 warps][V][32]  (fits in Wt + gs for every supported H)
+  {
+    float* mine = red + (w * V) * 32 + l;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int i2 = 0; i2 < kGruMaxI; ++i2) mine[((u * 3 + g) * 8 + i2) * 32] = dWi[u][g][i2];
+        mine[(24 * U + u * 3 + g) * 32] = dbi[u][g];
+      }
+      mine[(27 * U + u) * 32] = dbn[u];
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < V * 32; o += kGruThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kGruThreads / 32; ++ww) s += red[ww * V * 32 + o];
+    parts[(int64_t)blockIdx.x * (V * 32) + o] = s;
+  }
+}
+
+int64_t gru_fwd_smem(int H, int T, int I) {
+  return 4ll * (3ll * H * (H + 4) + (int64_t)kGruRows * H + 3ll * H * kGruLdi + 4ll * H + (int64_t)kGruRows * T * I);
+}
+int64_t gru_bwd_smem(int H, int T, int I) {
+  const int64_t main_part = (int64_t)H * (3 * H + 4) + (int64_t)kGruRows * 3 * H;
+  const int64_t red = 8ll * 28 * (H / 32) * 32;
+  return 4ll * (std::max(main_part, red) + (int64_t)kGruRows * T * I);
+}
+
+int gru_check(const char* who, int64_t N, int32_t T, int32_t I, int32_t H) {
+  SLDM_REQUIRE(N >= 0 && T >= 1 && I >= 1, SLDM_EINVAL, "%s: bad sizes N=%lld T=%d I=%d", who, (long long)N, T, I);
+  SLDM_REQUIRE(H == 32 || H == 64 || H == 96, SLDM_EUNSUPPORTED, "%s: hidden size %d (fused path: 32, 64, 96)", who, H);
+  SLDM_REQUIRE(I <= kGruMaxI, SLDM_EUNSUPPORTED, "%s: input width %d > %d", who, I, kGruMaxI);
+  SLDM_REQUIRE(std::max(gru_fwd_smem(H, T, I), gru_bwd_smem(H, T, I)) <= kGruSmemMax, SLDM_EUNSUPPORTED,
+               "%s: %d steps x %d inputs do not fit the shared-memory tile", who, T, I);
+  SLDM_REQUIRE(ceil_div<int64_t>(N, kGruRows) < (1ll << 31), SLDM_EUNSUPPORTED, "%s: N too large", who);
+  return SLDM_OK;
+}
+
+template <int H>
+int gru_fwd_launch(const float* x, int64_t N, int T, int I, const float* W_ih, const float* W_hh, const float* b_ih,
+                   const float* b_hh, float* h_last, float* hp, float* r, float* z, float* n, float* hn, cudaStream_t s) {
+  const int64_t smem = gru_fwd_smem(H, T, I);
+  const unsigned grid = (unsigned)ceil_div<int64_t>(N, kGruRows);
+  if (hp != nullptr) {
+    SLDM_OPT_IN_SMEM((k_gru_fwd<H, true>), kGruSmemMax);
+    k_gru_fwd<H, true><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, hp, r, z, n, hn);
+  } else {
+    SLDM_OPT_IN_SMEM((k_gru_fwd<H, false>), kGruSmemMax);
+    k_gru_fwd<H, false><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, nullptr,
+                                                                 nullptr, nullptr, nullptr, nullptr);
+  }
+  SLDM_LAUNCH_CHECK("k_gru_fwd");
+  return SLDM_OK;
+}
+
+template <int H>
+int gru_bwd_launch(const float* x, int64_t N, int T, int I, const float* W_hh, const float* dh_last, const float* hp,
+                   const float* r, const float* z, const float* n, const float* hn, float* dgh, float* gin, float* parts,
+                   cudaStream_t s) {
+  const int64_t smem = gru_bwd_smem(H, T, I);
+  const unsigned grid = (unsigned)ceil_div<int64_t>(N, kGruRows);
+  SLDM_OPT_IN_SMEM((k_gru_bwd<H>), kGruSmemMax);
+  k_gru_bwd<H><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_hh, dh_last, hp, r, z, n, hn, dgh, gin, parts);
+  SLDM_LAUNCH_CHECK("k_gru_bwd");
+  return SLDM_OK;
+}
+
+}  // namespace
+}  // namespace sldm
+
+using namespace sldm;
+
+extern "C" int sldm_gru_supported(int32_t T, int32_t I, int32_t H) {
+  return (H == 32 || H == 64 || H == 96) && T >= 1 && I >= 1 && I <= kGruMaxI &&
+         std::max(gru_fwd_smem(H, T, I), gru_bwd_smem(H, T, I)) <= kGruSmemMax;
+}
+
+extern "C" int64_t sldm_gru_partial_rows(int64_t N) { return N < 0 ? -1 : ceil_div<int64_t>(N, kGruRows); }
+extern "C" int64_t sldm_gru_partial_width(int32_t H) { return H > 0 && H % 32 == 0 ? 28ll * H : -1; }
+
+extern "C" int sldm_gru_forward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H,
+                                const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
+                                float* h_last, float* h_prev, float* gate_r, float* gate_z, float* gate_n,
+                                float* gate_hn, sldm_stream_t stream) {
+  int rc = gru_check("sldm_gru_forward", N, T, I, H);
+  if (rc) return rc;
+  if (N == 0) return SLDM_OK;
+  SLDM_REQUIRE(x && W_ih && W_hh && b_ih && b_hh && h_last, SLDM_EINVAL, "sldm_gru_forward: NULL pointer");
+  const bool save = h_prev != nullptr;
+  SLDM_REQUIRE(!save || (gate_r && gate_z && gate_n && gate_hn), SLDM_EINVAL,
+               "sldm_gru_forward: h_prev given without the four gate buffers");
+  SLDM_REQUIRE((reinterpret_cast<uintptr_t>(W_hh) & 15u) == 0, SLDM_EINVAL, "sldm_gru_forward: W_hh must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (H) {
+    case 32: return gru_fwd_launch<32>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, h_prev, gate_r, gate_z, gate_n, gate_hn, s);
+    case 64: return gru_fwd_launch<64>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, h_prev, gate_r, gate_z, gate_n, gate_hn, s);
+    default: return gru_fwd_launch<96>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, h_prev, gate_r, gate_z, gate_n, gate_hn, s);
+  }
+}
+
+extern "C" int sldm_gru_backward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H, const float* W_hh,
+                                 const float* dh_last, const float* h_prev, const float* gate_r, const float* gate_z,
+                                 const float* gate_n, const float* gate_hn, float* dgh, float* dgi_n, float* partials,
+                                 int64_t partial_rows, sldm_stream_t stream) {
+  int rc = gru_check("sldm_gru_backward", N, T, I, H);
+  if (rc) return rc;
+  if (N == 0) return SLDM_OK;
+  SLDM_REQUIRE(x && W_hh && dh_last && h_prev && gate_r && gate_z && gate_n && gate_hn && dgh && partials, SLDM_EINVAL,
+               "sldm_gru_backward: NULL pointer");
+  SLDM_REQUIRE(partial_rows >= ceil_div<int64_t>(N, kGruRows), SLDM_EWORKSPACE,
+               "sldm_gru_backward: %lld partial rows < %lld", (long long)partial_rows,
+               (long long)ceil_div<int64_t>(N, kGruRows));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (H) {
+    case 32: return gru_bwd_launch<32>(x, N, T, I, W_hh, dh_last, h_prev, gate_r, gate_z, gate_n, gate_hn, dgh, dgi_n, partials, s);
+    case 64: return gru_bwd_launch<64>(x, N, T, I, W_hh, dh_last, h_prev, gate_r, gate_z, gate_n, gate_hn, dgh, dgi_n, partials, s);
+    default: return gru_bwd_launch<96>(x, N, T, I, W_hh, dh_last, h_prev, gate_r, gate_z, gate_n, gate_hn, dgh, dgi_n, partials, s);
+  }
+}

@@ -17,9 +17,12 @@ x [N,T,F], edge_index, xsttype, xdims, pos_raw, batch.  Differences, both invisi
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
+from .gru import fused_gru_eligible, gru_last_hidden
 from .map_attention import MapSpatialAttention
 from .readout import global_max_pool, global_mean_max_pool, global_mean_pool
 from .sageblock import SageBlock
@@ -150,12 +153,20 @@ class GruSage(nn.Module):
         return ipd
 
     def _last_hidden(self, x):
-        """[N, T, F] -> last hidden state of the last GRU layer, through ATen's native GRU (one cuBLAS GEMM + one fused
-        cell kernel per step) rather than cuDNN's: measured on B200 at the C2 shape (205 k sequences x 16 frames, input 6,
-        hidden 96) the native path takes 35 ms forward + backward against 118 ms, and it computes in true fp32 -- cuDNN's
-        RNN runs TF32 under torch's default flags (2e-4 off the CPU result, tools/gru_probe.py), which is outside this
-        package's 1e-5 bar.  cuDNN also indexes its gate workspace (N * T * 3H elements) with 32 bits and faults beyond
-        2^31; sequences are independent, so very large batches go through in slices -- same numbers, no limit."""
+        """[N, T, F] -> last hidden state of the last GRU layer (grusage.py:160-161).
+
+        Default: the fused kernels of csrc/gru.cu (all T steps of a tile of sequences on one SM; gru.py) whenever the
+        module is one batch-first layer with hidden 32 / 64 / 96 and at most 8 input features -- the reference's
+        configuration (main.py:42-44: hidden 96, one layer, 6 dynamic features).  Anything else, or
+        SLDM_DISABLE_FUSED_GRU=1, goes through torch's library GRU, and there through ATen's native path (one cuBLAS
+        GEMM + one fused cell kernel per step) rather than cuDNN's: measured on B200 at the C2 shape (205 k sequences
+        x 16 frames, input 6, hidden 96) the native path takes 35 ms forward + backward against 118 ms, and it computes
+        in true fp32 -- cuDNN's RNN runs TF32 under torch's default flags (2e-4 off the CPU result,
+        tools/gru_probe.py), which is outside this package's 1e-5 bar.  cuDNN also indexes its gate workspace
+        (N * T * 3H elements) with 32 bits and faults beyond 2^31; sequences are independent, so very large batches go
+        through the library path in slices -- same numbers, no limit."""
+        if os.environ.get("SLDM_DISABLE_FUSED_GRU", "0") != "1" and fused_gru_eligible(self.gru, x):
+            return gru_last_hidden(self.gru, x)
         n, per_seq = x.size(0), x.size(1) * 3 * self.gru.hidden_size
         rows = max(1, (1 << 30) // max(per_seq, 1))
         with torch.backends.cudnn.flags(enabled=False):

@@ -1,0 +1,155 @@
+"""Fused GRU sequence head (csrc/gru.cu, sldm_gnn_b200/gru.py) against the reference's own layer.
+
+The reference computes this step with `torch.nn.GRU` (src/models/grusage.py:55-60, 160-161), so torch's CPU GRU *is*
+the reference implementation here: parity is pinned against it directly, in fp32 with the fp64 run as adjudicator
+(bar: rtol 1e-5 / atol 1e-6; parameter gradients, sums over all N*T rows, with atol scaled by their magnitude).
+"""
+import os
+
+import pytest
+import torch
+
+import sldm_gnn_b200 as sg
+from sldm_gnn_b200 import _lib
+from sldm_gnn_b200.gru import fused_gru_eligible, gru_last_hidden
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+# ------------------------------------------------------------------- CPU side --
+def test_support_queries_without_gpu():
+    lib = _lib.lib
+    assert lib.sldm_gru_supported(16, 6, 96) == 1          # the reference's configuration (main.py:42-44)
+    assert lib.sldm_gru_supported(16, 8, 64) == 1 and lib.sldm_gru_supported(1, 1, 32) == 1
+    assert lib.sldm_gru_supported(16, 6, 128) == 0         # hidden size outside the tile design
+    assert lib.sldm_gru_supported(16, 9, 96) == 0          # input too wide
+    assert lib.sldm_gru_supported(400, 8, 96) == 0         # x tile does not fit shared memory
+    assert lib.sldm_gru_supported(0, 6, 96) == 0
+    assert lib.sldm_gru_partial_rows(0) == 0 and lib.sldm_gru_partial_rows(64) == 1 and lib.sldm_gru_partial_rows(65) == 2
+    assert lib.sldm_gru_partial_rows(-1) == -1
+    assert lib.sldm_gru_partial_width(96) == 28 * 96 and lib.sldm_gru_partial_width(33) == -1
+
+
+def test_cpu_tensors_are_not_eligible_and_raise():
+    gru = torch.nn.GRU(6, 96, 1, batch_first=True)
+    x = torch.randn(4, 16, 6)
+    assert not fused_gru_eligible(gru, x)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        gru_last_hidden(gru, x)
+
+
+def test_unsupported_shapes_return_eunsupported_without_gpu():
+    rc = _lib.lib.sldm_gru_forward(None, 4, 16, 6, 128, None, None, None, None, None, None, None, None, None, None, None)
+    assert rc == _lib.EUNSUPPORTED
+    with pytest.raises(NotImplementedError, match="hidden size 128"):
+        _lib.check(rc)
+    assert _lib.lib.sldm_gru_forward(None, -1, 16, 6, 96, None, None, None, None, None, None, None, None, None, None,
+                                     None) == _lib.EINVAL
+
+
+# ------------------------------------------------------------------- GPU side --
+def _close(got, want, want64, what, scale_atol=False):
+    got, want, w64 = got.detach().cpu(), want.detach(), want64.detach().double()
+    atol = ATOL * (max(1.0, float(want.abs().max())) if scale_atol else 1.0)
+    err = (got - want).abs()
+    bad = err > atol + RTOL * want.abs()
+    if not bad.any():
+        return
+    e_g = (got.double() - w64).abs()[bad]
+    e_r = float((want.double() - w64).abs().max())
+    ok = (e_g <= atol + RTOL * w64.abs()[bad]) | (e_g <= 1.5 * e_r)
+    assert ok.all(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err {float(err.max()):.3e}; "
+                      f"vs fp64: ours {float(e_g.max()):.3e}, torch fp32 {e_r:.3e}")
+
+
+def _reference(gru, x, up, need_dx):
+    """torch's own GRU on the CPU, fp32 and fp64: (h, grads..., dx) each."""
+    out = []
+    for dt in (torch.float32, torch.float64):
+        g = torch.nn.GRU(gru.input_size, gru.hidden_size, 1, batch_first=True).to(dt)
+        g.load_state_dict({k: v.detach().cpu().to(dt) for k, v in gru.state_dict().items()})
+        xi = x.detach().cpu().to(dt).requires_grad_(need_dx)
+        h = g(xi)[1][-1]
+        h.backward(up.detach().cpu().to(dt))
+        out.append((h.detach(), {k: p.grad for k, p in g.named_parameters()}, xi.grad))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,T,I,H,need_dx", [
+    (1, 1, 1, 32, False), (5, 3, 6, 96, True), (64, 16, 6, 96, False), (65, 16, 6, 96, True), (1000, 16, 6, 96, False),
+    (300, 7, 8, 64, True), (130, 16, 3, 32, False), (4099, 16, 6, 96, False), (63, 25, 5, 96, True),
+])
+def test_fused_gru_matches_torch_gru(N, T, I, H, need_dx):
+    dev = torch.device("cuda:0")
+    torch.manual_seed(N * 131 + T * 7 + I + H)
+    gru = torch.nn.GRU(I, H, 1, batch_first=True).to(dev)
+    x = torch.randn(N, T, I, device=dev, requires_grad=need_dx)
+    up = torch.randn(N, H, device=dev)
+    assert fused_gru_eligible(gru, x)
+    before = _lib.lib.sldm_launch_count()
+    h = gru_last_hidden(gru, x)
+    h.backward(up)
+    torch.cuda.synchronize()
+    assert _lib.lib.sldm_launch_count() - before == 2, "forward and backward are one kernel each"
+    (h32, g32, dx32), (h64, g64, dx64) = _reference(gru, x, up, need_dx)
+    _close(h, h32, h64, "h_last")
+    for k, p in gru.named_parameters():
+        _close(p.grad, g32[k], g64[k], f"grad {k}", scale_atol=True)
+    if need_dx:
+        _close(x.grad, dx32, dx64, "dx")
+    else:
+        assert x.grad is None
+
+
+@pytest.mark.gpu
+def test_fused_gru_inference_equals_training_forward_and_is_deterministic():
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    gru = torch.nn.GRU(6, 96, 1, batch_first=True).to(dev)
+    x = torch.randn(777, 16, 6, device=dev)
+    up = torch.randn(777, 96, device=dev)
+    with torch.no_grad():
+        h0 = gru_last_hidden(gru, x)
+    with torch.inference_mode():
+        h1 = gru_last_hidden(gru, x)
+    grads = []
+    for _ in range(2):
+        gru.zero_grad()
+        h2 = gru_last_hidden(gru, x)
+        h2.backward(up)
+        grads.append([p.grad.clone() for p in gru.parameters()])
+    assert torch.equal(h0, h1) and torch.equal(h0, h2.detach())
+    assert all(torch.equal(a, b) for a, b in zip(*grads)), "parameter gradients are bit-identical run to run"
+
+
+@pytest.mark.gpu
+def test_grusage_uses_the_fused_gru_and_matches_the_library_path(monkeypatch):
+    """The model's sequence head goes through the kernels (launch counter) and agrees with torch's library GRU."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    m = sg.GruSage(dynamic_features_num=6, frames_num=16, gru_hidden_size=96, gru_num_layers=1, fc1dims=[96],
+                   sage_hidden_dims=[96, 96], fc2dims=[32], dropout=None, negative_slope=0.1,
+                   map_included=False).to(dev)
+    x = torch.randn(500, 16, 6, device=dev)
+    before = _lib.lib.sldm_launch_count()
+    h = m._last_hidden(x)
+    assert _lib.lib.sldm_launch_count() - before == 1
+    monkeypatch.setenv("SLDM_DISABLE_FUSED_GRU", "1")
+    before = _lib.lib.sldm_launch_count()
+    h_lib = m._last_hidden(x)
+    assert _lib.lib.sldm_launch_count() == before
+    assert torch.allclose(h, h_lib, rtol=1e-5, atol=2e-6), float((h - h_lib).abs().max())
+
+
+@pytest.mark.gpu
+def test_ineligible_modules_stay_on_the_library():
+    dev = torch.device("cuda:0")
+    x = torch.randn(8, 16, 6, device=dev)
+    assert not fused_gru_eligible(torch.nn.GRU(6, 96, 2, batch_first=True).to(dev), x)
+    assert not fused_gru_eligible(torch.nn.GRU(6, 96, 1, batch_first=False).to(dev), x)
+    assert not fused_gru_eligible(torch.nn.GRU(6, 128, 1, batch_first=True).to(dev), x)
+    assert not fused_gru_eligible(torch.nn.GRU(6, 96, 1, batch_first=True, bidirectional=True).to(dev), x)
+    assert not fused_gru_eligible(torch.nn.GRU(6, 96, 1, batch_first=True).to(dev), x.double())
+    with pytest.raises(NotImplementedError):
+        gru_last_hidden(torch.nn.GRU(6, 128, 1, batch_first=True).to(dev), x)

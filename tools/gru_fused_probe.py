@@ -1,0 +1,53 @@
+"""Fused GRU (csrc/gru.cu) vs torch's library GRU (ATen native path) at the C2 shape: time and agreement.
+usage: python tools/gru_fused_probe.py [N]      (default 205587 sequences = 1024 unit graphs; T=16, I=6, H=96)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sldm_gnn_b200.gru import gru_last_hidden
+from sldm_gnn_b200 import _lib
+
+dev = torch.device("cuda:0")
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 205_587
+T, I, H = 16, 6, 96
+torch.manual_seed(0)
+gru = torch.nn.GRU(I, H, 1, batch_first=True).to(dev)
+x = torch.randn(N, T, I, device=dev)
+up = torch.randn(N, H, device=dev)
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps, out
+
+
+def lib_fwd():
+    with torch.backends.cudnn.flags(enabled=False):
+        return gru(x)[1][-1]
+
+
+def step(fwd):
+    gru.zero_grad()
+    h = fwd()
+    h.backward(up)
+    return h.detach(), [p.grad.clone() for p in gru.parameters()]
+
+
+with torch.no_grad():
+    ms_f_lib, _ = timed(lib_fwd)
+    ms_f_fused, _ = timed(lambda: gru_last_hidden(gru, x))
+ms_lib, (h_lib, g_lib) = timed(lambda: step(lib_fwd), 3)
+ms_fused, (h_f, g_f) = timed(lambda: step(lambda: gru_last_hidden(gru, x)), 3)
+ms_ftrain, _ = timed(lambda: gru_last_hidden(gru, x))   # training forward (saves the gates)
+flops = 2.0 * N * T * 3 * H * (H + I)
+print(f"N={N} T={T} I={I} H={H}")
+print(f"forward (no grad): library {ms_f_lib:.2f} ms, fused {ms_f_fused:.2f} ms ({flops / ms_f_fused / 1e9:.1f} TFLOP/s fp32)")
+print(f"forward (training, saves 5 x [N,T,H]): fused {ms_ftrain:.2f} ms")
+print(f"forward + backward: library {ms_lib:.2f} ms, fused {ms_fused:.2f} ms")
+print("max |h - h_lib|", float((h_f - h_lib).abs().max()),
+      "max rel grad diff", max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(g_f, g_lib)))
+print("launches so far", _lib.lib.sldm_launch_count(), "peak mem GiB", torch.cuda.max_memory_allocated() / 2**30)
