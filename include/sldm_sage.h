@@ -26,6 +26,8 @@
  *   sldm_sage_layer_*     one whole iteration of the loop at
  *                         src/models/blocks/sageblock.py:17-19 (dropout excluded:
  *                         it stays torch's), forward and backward.
+ *   sldm_gru_*            the sequence head in front of the block: nn.GRU's last
+ *                         hidden state (src/models/grusage.py:55-60,160-161).
  *   sldm_sage_block_*_host  the whole SageBlock.forward
  *                         (src/models/blocks/sageblock.py:16-20) for hosts that
  *                         own no device memory: host buffers in, host buffers out.
@@ -260,13 +262,14 @@ int sldm_edge_build_fill(const float* x, int64_t V, int32_t T, int32_t F, float 
  * weight_ih_l0 / weight_hh_l0 / bias_ih_l0 / bias_hh_l0, gates ordered (r, z, n).  Same formulas as ATen's fused cell.
  *   supported: H in {32, 64, 96}, I <= 8, T*I small enough for the shared-memory tile (sldm_gru_supported() != 0);
  *              anything else returns SLDM_EUNSUPPORTED (the host module then keeps torch's library GRU).
- *   forward  : h_last [N,H].  Training: h_prev, gate_r, gate_z, gate_n, gate_hn, each [N,T,H] (all five or none):
- *              h_{t-1}, the three gates and W_hn h + b_hn of every step, saved for backward.
- *   backward : dh_last [N,H] in; dgh [N,T,3H] = gradients of the hidden-side gate pre-activations (dW_hh is the one
- *              GEMM left to the caller: dgh^T . h_prev over the N*T rows); dgi_n [N,T,H] (NULL unless dx is wanted:
- *              the input-side pre-activation gradients are [dgh[:, :2H] | dgi_n]); partials
- *              [sldm_gru_partial_rows(N)][sldm_gru_partial_width(H)]: per-tile sums the caller adds over rows, laid
- *              out as [28*H/32][32]: v = (u*3+g)*8 + i -> dW_ih[g*H + 32u + lane][i]; v = 24U + u*3 + g ->
+ *   forward  : h_last [N,H].  Training: saved [T,N,5,H] (NULL for inference) receives, per step and sequence,
+ *              h_{t-1} | r | z | n | W_hn h + b_hn -- what backward needs (time-major so that a tile's stores of one
+ *              step are contiguous).
+ *   backward : dh_last [N,H] in; dgh [T,N,3H] = gradients of the hidden-side gate pre-activations (dW_hh is the one
+ *              GEMM left to the caller: dgh^T . h_prev over the T*N rows, h_prev = saved[:, :, 0, :]); dgi_n [T,N,H]
+ *              (NULL unless dx is wanted: the input-side pre-activation gradients are [dgh[..., :2H] | dgi_n]);
+ *              partials [sldm_gru_partial_rows(N)][sldm_gru_partial_width(H)]: per-tile sums the caller adds over
+ *              rows, laid out as [28*H/32][32]: v = (u*3+g)*8 + i -> dW_ih[g*H + 32u + lane][i]; v = 24U + u*3 + g ->
  *              db_ih[g*H + 32u + lane]; v = 27U + u -> db_hh[2H + 32u + lane] (db_hh[:2H] = db_ih[:2H]), U = H/32.
  */
 int     sldm_gru_supported(int32_t T, int32_t I, int32_t H);
@@ -274,11 +277,9 @@ int64_t sldm_gru_partial_rows(int64_t N);
 int64_t sldm_gru_partial_width(int32_t H);
 int     sldm_gru_forward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H,
                          const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
-                         float* h_last, float* h_prev, float* gate_r, float* gate_z, float* gate_n, float* gate_hn,
-                         sldm_stream_t stream);
+                         float* h_last, float* saved, sldm_stream_t stream);
 int     sldm_gru_backward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H, const float* W_hh,
-                          const float* dh_last, const float* h_prev, const float* gate_r, const float* gate_z,
-                          const float* gate_n, const float* gate_hn, float* dgh, float* dgi_n, float* partials,
+                          const float* dh_last, const float* saved, float* dgh, float* dgi_n, float* partials,
                           int64_t partial_rows, sldm_stream_t stream);
 
 /* ---- whole block, host buffers in / host buffers out -----------------------

@@ -9,9 +9,11 @@
 //            lane = hidden unit), a warp owns 8 sequences for all T steps (its h rows are read as shared-memory
 //            broadcasts), a lane owns H/32 hidden units x 3 gates x 8 rows = 72 fp32 accumulators at H = 96; the gate
 //            math of a (row, unit) is local to its thread, so the time loop needs no block-level barrier at all.
-//            When training it writes h_{t-1}, r, z, n and (W_hn h + b_hn) per step -- what torch's fused cell saves.
+//            When training it writes h_{t-1}, r, z, n and (W_hn h + b_hn) per step -- what torch's fused cell saves --
+//            as one [T, N, 5, H] buffer: a warp's output of a step is 8 x 5H contiguous floats (with five [N, T, H]
+//            arrays the 128-byte pieces were 6 KB apart and the stores cost 3.6 ms on top of 5.7 ms of arithmetic).
 //   backward (k_gru_bwd):  the same tiling walks t = T-1 .. 0 with W_hh transposed in shared memory
-//            (dh_{t-1} = dh_t z + [dr dz dn r] W_hh); it emits the hidden-gate gradients dgh [N,T,3H] for the one
+//            (dh_{t-1} = dh_t z + [dr dz dn r] W_hh); it emits the hidden-gate gradients dgh [T,N,3H] for the one
 //            library GEMM that is left (dW_hh = dgh^T h_prev) and accumulates dW_ih, db_ih, db_hh per CTA in
 //            registers (fixed order; the per-CTA partials are summed by the caller).
 //
@@ -50,8 +52,7 @@ __global__ void __launch_bounds__(kGruThreads, 1)
 k_gru_fwd(const float* __restrict__ x, int64_t N, int T, int I,
           const float* __restrict__ W_ih, const float* __restrict__ W_hh,
           const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-          float* __restrict__ h_last, float* __restrict__ hp, float* __restrict__ sr,
-          float* __restrict__ sz, float* __restrict__ sn, float* __restrict__ shn) {
+          float* __restrict__ h_last, float* __restrict__ saved) {
   constexpr int U = H / 32, LDW = H + 4;
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                        // [3H][LDW]
@@ -118,9 +119,9 @@ k_gru_fwd(const float* __restrict__ x, int64_t N, int T, int I,
 #pragma unroll
       for (int i = 0; i < kGruRpw; ++i)
         if (r0 + i < nrows) {
-          const int64_t o = ((row0 + r0 + i) * T + t) * H + l;
+          float* o = saved + (((int64_t)t * N + row0 + r0 + i) * 5) * H + l;
 #pragma unroll
-          for (int u = 0; u < U; ++u) hp[o + 32 * u] = hreg[i][u];
+          for (int u = 0; u < U; ++u) o[32 * u] = hreg[i][u];
         }
     }
     // input part (I <= 8): r and z continue their accumulators, the n gate keeps its input half apart
@@ -158,8 +159,8 @@ k_gru_fwd(const float* __restrict__ x, int64_t N, int T, int I,
         const float hn = an[i][u] + bhn;
         const float ng = tanhf(ai[i][u] + bin + rg * hn);
         if (SAVE && r0 + i < nrows) {
-          const int64_t o = ((row0 + r0 + i) * T + t) * H + j;
-          sr[o] = rg; sz[o] = zg; sn[o] = ng; shn[o] = hn;
+          float* o = saved + (((int64_t)t * N + row0 + r0 + i) * 5) * H + j;
+          o[H] = rg; o[2 * H] = zg; o[3 * H] = ng; o[4 * H] = hn;
         }
         hreg[i][u] = ng + zg * (hreg[i][u] - ng);
       }
@@ -184,8 +185,7 @@ k_gru_fwd(const float* __restrict__ x, int64_t N, int T, int I,
 template <int H>
 __global__ void __launch_bounds__(kGruThreads, 1)
 k_gru_bwd(const float* __restrict__ x, int64_t N, int T, int I, const float* __restrict__ W_hh,
-          const float* __restrict__ dh_last, const float* __restrict__ hp, const float* __restrict__ sr,
-          const float* __restrict__ sz, const float* __restrict__ sn, const float* __restrict__ shn,
+          const float* __restrict__ dh_last, const float* __restrict__ saved,
           float* __restrict__ dgh, float* __restrict__ gin_out, float* __restrict__ parts) {
   constexpr int U = H / 32, G3 = 3 * H, LDT = 3 * H + 4, V = 28 * U;
   extern __shared__ __align__(16) float sm[];
@@ -232,9 +232,12 @@ k_gru_bwd(const float* __restrict__ x, int64_t N, int T, int I, const float* __r
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int j = l + 32 * u;
-        const int64_t o = ((row0 + r0 + i) * T + t) * H + j;
+        const int64_t tr = (int64_t)t * N + row0 + r0 + i;     // row of the [T, N, ...] buffers
         float rg = 0.f, zg = 0.f, ng = 0.f, hn = 0.f, hpv = 0.f;
-        if (valid) { rg = __ldg(sr + o); zg = __ldg(sz + o); ng = __ldg(sn + o); hn = __ldg(shn + o); hpv = __ldg(hp + o); }
+        if (valid) {
+          const float* o = saved + tr * 5 * H + j;
+          hpv = __ldg(o); rg = __ldg(o + H); zg = __ldg(o + 2 * H); ng = __ldg(o + 3 * H); hn = __ldg(o + 4 * H);
+        }
         const float g = dh[i][u];
         const float gig = g * (hpv - ng) * (1.f - zg) * zg;
         const float ghx = g * zg;
@@ -242,9 +245,9 @@ k_gru_bwd(const float* __restrict__ x, int64_t N, int T, int I, const float* __r
         const float ghn = gin * rg;
         const float grg = gin * hn * (1.f - rg) * rg;
         if (valid) {
-          const int64_t og = ((row0 + r0 + i) * T + t) * G3 + j;
-          dgh[og] = grg; dgh[og + H] = gig; dgh[og + 2 * H] = ghn;
-          if (gin_out != nullptr) gin_out[o] = gin;
+          float* og = dgh + tr * G3 + j;
+          og[0] = grg; og[H] = gig; og[2 * H] = ghn;
+          if (gin_out != nullptr) gin_out[tr * H + j] = gin;
         }
         float* gr = gs + (r0 + i) * G3 + j;
         gr[0] = grg; gr[H] = gig; gr[2 * H] = ghn;
@@ -321,29 +324,27 @@ int gru_check(const char* who, int64_t N, int32_t T, int32_t I, int32_t H) {
 
 template <int H>
 int gru_fwd_launch(const float* x, int64_t N, int T, int I, const float* W_ih, const float* W_hh, const float* b_ih,
-                   const float* b_hh, float* h_last, float* hp, float* r, float* z, float* n, float* hn, cudaStream_t s) {
+                   const float* b_hh, float* h_last, float* saved, cudaStream_t s) {
   const int64_t smem = gru_fwd_smem(H, T, I);
   const unsigned grid = (unsigned)ceil_div<int64_t>(N, kGruRows);
-  if (hp != nullptr) {
+  if (saved != nullptr) {
     SLDM_OPT_IN_SMEM((k_gru_fwd<H, true>), kGruSmemMax);
-    k_gru_fwd<H, true><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, hp, r, z, n, hn);
+    k_gru_fwd<H, true><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, saved);
   } else {
     SLDM_OPT_IN_SMEM((k_gru_fwd<H, false>), kGruSmemMax);
-    k_gru_fwd<H, false><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, nullptr,
-                                                                 nullptr, nullptr, nullptr, nullptr);
+    k_gru_fwd<H, false><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, nullptr);
   }
   SLDM_LAUNCH_CHECK("k_gru_fwd");
   return SLDM_OK;
 }
 
 template <int H>
-int gru_bwd_launch(const float* x, int64_t N, int T, int I, const float* W_hh, const float* dh_last, const float* hp,
-                   const float* r, const float* z, const float* n, const float* hn, float* dgh, float* gin, float* parts,
-                   cudaStream_t s) {
+int gru_bwd_launch(const float* x, int64_t N, int T, int I, const float* W_hh, const float* dh_last,
+                   const float* saved, float* dgh, float* gin, float* parts, cudaStream_t s) {
   const int64_t smem = gru_bwd_smem(H, T, I);
   const unsigned grid = (unsigned)ceil_div<int64_t>(N, kGruRows);
   SLDM_OPT_IN_SMEM((k_gru_bwd<H>), kGruSmemMax);
-  k_gru_bwd<H><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_hh, dh_last, hp, r, z, n, hn, dgh, gin, parts);
+  k_gru_bwd<H><<<grid, kGruThreads, (size_t)smem, s>>>(x, N, T, I, W_hh, dh_last, saved, dgh, gin, parts);
   SLDM_LAUNCH_CHECK("k_gru_bwd");
   return SLDM_OK;
 }
@@ -363,40 +364,34 @@ extern "C" int64_t sldm_gru_partial_width(int32_t H) { return H > 0 && H % 32 ==
 
 extern "C" int sldm_gru_forward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H,
                                 const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
-                                float* h_last, float* h_prev, float* gate_r, float* gate_z, float* gate_n,
-                                float* gate_hn, sldm_stream_t stream) {
+                                float* h_last, float* saved, sldm_stream_t stream) {
   int rc = gru_check("sldm_gru_forward", N, T, I, H);
   if (rc) return rc;
   if (N == 0) return SLDM_OK;
   SLDM_REQUIRE(x && W_ih && W_hh && b_ih && b_hh && h_last, SLDM_EINVAL, "sldm_gru_forward: NULL pointer");
-  const bool save = h_prev != nullptr;
-  SLDM_REQUIRE(!save || (gate_r && gate_z && gate_n && gate_hn), SLDM_EINVAL,
-               "sldm_gru_forward: h_prev given without the four gate buffers");
   SLDM_REQUIRE((reinterpret_cast<uintptr_t>(W_hh) & 15u) == 0, SLDM_EINVAL, "sldm_gru_forward: W_hh must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (H) {
-    case 32: return gru_fwd_launch<32>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, h_prev, gate_r, gate_z, gate_n, gate_hn, s);
-    case 64: return gru_fwd_launch<64>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, h_prev, gate_r, gate_z, gate_n, gate_hn, s);
-    default: return gru_fwd_launch<96>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, h_prev, gate_r, gate_z, gate_n, gate_hn, s);
+    case 32: return gru_fwd_launch<32>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, saved, s);
+    case 64: return gru_fwd_launch<64>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, saved, s);
+    default: return gru_fwd_launch<96>(x, N, T, I, W_ih, W_hh, b_ih, b_hh, h_last, saved, s);
   }
 }
 
 extern "C" int sldm_gru_backward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H, const float* W_hh,
-                                 const float* dh_last, const float* h_prev, const float* gate_r, const float* gate_z,
-                                 const float* gate_n, const float* gate_hn, float* dgh, float* dgi_n, float* partials,
+                                 const float* dh_last, const float* saved, float* dgh, float* dgi_n, float* partials,
                                  int64_t partial_rows, sldm_stream_t stream) {
   int rc = gru_check("sldm_gru_backward", N, T, I, H);
   if (rc) return rc;
   if (N == 0) return SLDM_OK;
-  SLDM_REQUIRE(x && W_hh && dh_last && h_prev && gate_r && gate_z && gate_n && gate_hn && dgh && partials, SLDM_EINVAL,
-               "sldm_gru_backward: NULL pointer");
+  SLDM_REQUIRE(x && W_hh && dh_last && saved && dgh && partials, SLDM_EINVAL, "sldm_gru_backward: NULL pointer");
   SLDM_REQUIRE(partial_rows >= ceil_div<int64_t>(N, kGruRows), SLDM_EWORKSPACE,
                "sldm_gru_backward: %lld partial rows < %lld", (long long)partial_rows,
                (long long)ceil_div<int64_t>(N, kGruRows));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (H) {
-    case 32: return gru_bwd_launch<32>(x, N, T, I, W_hh, dh_last, h_prev, gate_r, gate_z, gate_n, gate_hn, dgh, dgi_n, partials, s);
-    case 64: return gru_bwd_launch<64>(x, N, T, I, W_hh, dh_last, h_prev, gate_r, gate_z, gate_n, gate_hn, dgh, dgi_n, partials, s);
-    default: return gru_bwd_launch<96>(x, N, T, I, W_hh, dh_last, h_prev, gate_r, gate_z, gate_n, gate_hn, dgh, dgi_n, partials, s);
+    case 32: return gru_bwd_launch<32>(x, N, T, I, W_hh, dh_last, saved, dgh, dgi_n, partials, s);
+    case 64: return gru_bwd_launch<64>(x, N, T, I, W_hh, dh_last, saved, dgh, dgi_n, partials, s);
+    default: return gru_bwd_launch<96>(x, N, T, I, W_hh, dh_last, saved, dgh, dgi_n, partials, s);
   }
 }

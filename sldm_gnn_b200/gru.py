@@ -37,10 +37,9 @@ class _GruLastHiddenFn(torch.autograd.Function):
         x, W_ih, W_hh, b_ih, b_hh = (t.contiguous() for t in (x, W_ih, W_hh, b_ih, b_hh))
         with torch.cuda.device(dev):
             h_last = torch.empty((N, H), dtype=torch.float32, device=dev)
-            saved = torch.empty((5, N, T, H), dtype=torch.float32, device=dev) if save else None
-            ptrs = [saved[k].data_ptr() for k in range(5)] if save else [None] * 5
+            saved = torch.empty((T, N, 5, H), dtype=torch.float32, device=dev) if save else None
             check(lib.sldm_gru_forward(x.data_ptr(), N, T, I, H, W_ih.data_ptr(), W_hh.data_ptr(), b_ih.data_ptr(),
-                                       b_hh.data_ptr(), h_last.data_ptr(), *ptrs, _stream(dev)))
+                                       b_hh.data_ptr(), h_last.data_ptr(), _ptr(saved), _stream(dev)))
         if save:
             ctx.save_for_backward(x, W_ih, W_hh, saved)
         return h_last
@@ -56,23 +55,24 @@ class _GruLastHiddenFn(torch.autograd.Function):
         dh_last = dh_last.contiguous()
         with torch.cuda.device(dev):
             f32 = dict(dtype=torch.float32, device=dev)
-            dgh = torch.empty((N, T, 3 * H), **f32)
-            dgi_n = torch.empty((N, T, H), **f32) if need_dx else None
+            dgh = torch.empty((T, N, 3 * H), **f32)
+            dgi_n = torch.empty((T, N, H), **f32) if need_dx else None
             rows, width = int(lib.sldm_gru_partial_rows(N)), int(lib.sldm_gru_partial_width(H))
             parts = torch.empty((rows, width), **f32)
             check(lib.sldm_gru_backward(x.data_ptr(), N, T, I, H, W_hh.data_ptr(), dh_last.data_ptr(),
-                                        *[saved[k].data_ptr() for k in range(5)], dgh.data_ptr(), _ptr(dgi_n),
-                                        parts.data_ptr(), rows, _stream(dev)))
+                                        saved.data_ptr(), dgh.data_ptr(), _ptr(dgi_n), parts.data_ptr(), rows,
+                                        _stream(dev)))
             P = parts.sum(dim=0)
             dW_ih = P[:24 * U * 32].view(U, 3, 8, 32).permute(1, 0, 3, 2).reshape(3 * H, 8)[:, :I].contiguous()
             db_ih = P[24 * U * 32:27 * U * 32].view(U, 3, 32).permute(1, 0, 2).reshape(3 * H)
             db_hh = torch.cat([db_ih[:2 * H], P[27 * U * 32:]])
-            dgh2 = dgh.view(N * T, 3 * H)
-            dW_hh = dgh2.t() @ saved[0].view(N * T, H)      # the one plain GEMM left: library (cuBLAS, fp32)
+            dgh2 = dgh.view(T * N, 3 * H)
+            h_prev = saved.view(T * N, 5 * H)[:, :H]        # rows 5H apart: a strided GEMM operand, no copy
+            dW_hh = dgh2.t() @ h_prev                       # the one plain GEMM left: library (cuBLAS, fp32)
             dx = None
             if need_dx:
-                dgi = torch.cat([dgh2[:, :2 * H], dgi_n.view(N * T, H)], dim=1)
-                dx = (dgi @ W_ih).view(N, T, I)
+                dgi = torch.cat([dgh2[:, :2 * H], dgi_n.view(T * N, H)], dim=1)
+                dx = (dgi @ W_ih).view(T, N, I).transpose(0, 1).contiguous()
         return dx, dW_ih, dW_hh, db_ih, db_hh
 
 

@@ -39,12 +39,11 @@ def test_cpu_tensors_are_not_eligible_and_raise():
 
 
 def test_unsupported_shapes_return_eunsupported_without_gpu():
-    rc = _lib.lib.sldm_gru_forward(None, 4, 16, 6, 128, None, None, None, None, None, None, None, None, None, None, None)
+    rc = _lib.lib.sldm_gru_forward(None, 4, 16, 6, 128, None, None, None, None, None, None, None)
     assert rc == _lib.EUNSUPPORTED
     with pytest.raises(NotImplementedError, match="hidden size 128"):
         _lib.check(rc)
-    assert _lib.lib.sldm_gru_forward(None, -1, 16, 6, 96, None, None, None, None, None, None, None, None, None, None,
-                                     None) == _lib.EINVAL
+    assert _lib.lib.sldm_gru_forward(None, -1, 16, 6, 96, None, None, None, None, None, None, None) == _lib.EINVAL
 
 
 # ------------------------------------------------------------------- GPU side --

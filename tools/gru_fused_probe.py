@@ -43,6 +43,21 @@ with torch.no_grad():
 ms_lib, (h_lib, g_lib) = timed(lambda: step(lib_fwd), 3)
 ms_fused, (h_f, g_f) = timed(lambda: step(lambda: gru_last_hidden(gru, x)), 3)
 ms_ftrain, _ = timed(lambda: gru_last_hidden(gru, x))   # training forward (saves the gates)
+# backward pieces: the kernel alone (direct C call on preallocated buffers) and the dW_hh GEMM alone
+from sldm_gnn_b200.ops import _stream
+saved = torch.empty(T, N, 5, H, device=dev); h_last = torch.empty(N, H, device=dev)
+Wih, Whh, bih, bhh = gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0
+_lib.check(_lib.lib.sldm_gru_forward(x.data_ptr(), N, T, I, H, Wih.data_ptr(), Whh.data_ptr(), bih.data_ptr(), bhh.data_ptr(),
+                                     h_last.data_ptr(), saved.data_ptr(), _stream(dev)))
+dgh = torch.empty(T, N, 3 * H, device=dev)
+rows, width = _lib.lib.sldm_gru_partial_rows(N), _lib.lib.sldm_gru_partial_width(H)
+parts = torch.empty(rows, width, device=dev)
+ms_bk, _ = timed(lambda: _lib.check(_lib.lib.sldm_gru_backward(x.data_ptr(), N, T, I, H, Whh.data_ptr(), up.data_ptr(),
+                 saved.data_ptr(), dgh.data_ptr(), None, parts.data_ptr(), rows, _stream(dev))))
+ms_mm, _ = timed(lambda: dgh.view(T * N, 3 * H).t() @ saved.view(T * N, 5 * H)[:, :H])
+ms_ps, _ = timed(lambda: parts.sum(dim=0))
+print(f"backward pieces: k_gru_bwd {ms_bk:.2f} ms, dW_hh GEMM {ms_mm:.2f} ms, partial sum {ms_ps:.3f} ms")
+del saved, dgh
 flops = 2.0 * N * T * 3 * H * (H + I)
 print(f"N={N} T={T} I={I} H={H}")
 print(f"forward (no grad): library {ms_f_lib:.2f} ms, fused {ms_f_fused:.2f} ms ({flops / ms_f_fused / 1e9:.1f} TFLOP/s fp32)")
