@@ -265,12 +265,14 @@ int sldm_edge_build_fill(const float* x, int64_t V, int32_t T, int32_t F, float 
  *   forward  : h_last [N,H].  Training: saved [T,N,5,H] (NULL for inference) receives, per step and sequence,
  *              h_{t-1} | r | z | n | W_hn h + b_hn -- what backward needs (time-major so that a tile's stores of one
  *              step are contiguous).
- *   backward : dh_last [N,H] in; dgh [T,N,3H] = gradients of the hidden-side gate pre-activations (dW_hh is the one
- *              GEMM left to the caller: dgh^T . h_prev over the T*N rows, h_prev = saved[:, :, 0, :]); dgi_n [T,N,H]
+ *   backward : dh_last [N,H] in; dgh [T,N,3H] = gradients of the hidden-side gate pre-activations (input of
+ *              sldm_gru_wgrad); dgi_n [T,N,H]
  *              (NULL unless dx is wanted: the input-side pre-activation gradients are [dgh[..., :2H] | dgi_n]);
  *              partials [sldm_gru_partial_rows(N)][sldm_gru_partial_width(H)]: per-tile sums the caller adds over
  *              rows, laid out as [28*H/32][32]: v = (u*3+g)*8 + i -> dW_ih[g*H + 32u + lane][i]; v = 24U + u*3 + g ->
  *              db_ih[g*H + 32u + lane]; v = 27U + u -> db_hh[2H + 32u + lane] (db_hh[:2H] = db_ih[:2H]), U = H/32.
+ *   wgrad    : dW_hh = dgh^T . h_prev over the T*N rows (h_prev read in place from `saved`), as
+ *              sldm_gru_wgrad_tiles(N, T) partial [3H,H] tiles (one per persistent CTA) the caller adds up.
  */
 int     sldm_gru_supported(int32_t T, int32_t I, int32_t H);
 int64_t sldm_gru_partial_rows(int64_t N);
@@ -281,6 +283,9 @@ int     sldm_gru_forward(const float* x, int64_t N, int32_t T, int32_t I, int32_
 int     sldm_gru_backward(const float* x, int64_t N, int32_t T, int32_t I, int32_t H, const float* W_hh,
                           const float* dh_last, const float* saved, float* dgh, float* dgi_n, float* partials,
                           int64_t partial_rows, sldm_stream_t stream);
+int64_t sldm_gru_wgrad_tiles(int64_t N, int32_t T);
+int     sldm_gru_wgrad(const float* dgh, const float* saved, int64_t N, int32_t T, int32_t H,
+                       float* partials, int64_t partial_tiles, sldm_stream_t stream);
 
 /* ---- whole block, host buffers in / host buffers out -----------------------
  * For hosts that own no device memory (the reference-side stub in

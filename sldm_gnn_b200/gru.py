@@ -3,7 +3,7 @@
 Reference: src/models/grusage.py:55-60 (the nn.GRU it builds) and :160-161 (`gru_out, hlast = self.gru(x);
 x = hlast[-1]`).  The parameters stay in the caller's own `torch.nn.GRU` module (same state-dict keys
 `gru.weight_ih_l0` ...), only the arithmetic moves: one kernel runs all T steps of a tile of sequences on one SM
-(csrc/gru.cu), the backward is one more kernel plus a single library GEMM for dW_hh.  Shapes the kernels do not cover
+(csrc/gru.cu), the backward is two more kernels (the reverse recurrence, then dW_hh as a persistent split-K product).  Shapes the kernels do not cover
 (`fused_gru_eligible` is False) stay on torch's library GRU in the caller -- a GPU library layer, as in the reference.
 """
 from __future__ import annotations
@@ -66,9 +66,11 @@ class _GruLastHiddenFn(torch.autograd.Function):
             dW_ih = P[:24 * U * 32].view(U, 3, 8, 32).permute(1, 0, 3, 2).reshape(3 * H, 8)[:, :I].contiguous()
             db_ih = P[24 * U * 32:27 * U * 32].view(U, 3, 32).permute(1, 0, 2).reshape(3 * H)
             db_hh = torch.cat([db_ih[:2 * H], P[27 * U * 32:]])
+            tiles = int(lib.sldm_gru_wgrad_tiles(N, T))
+            wparts = torch.empty((tiles, 3 * H, H), **f32)
+            check(lib.sldm_gru_wgrad(dgh.data_ptr(), saved.data_ptr(), N, T, H, wparts.data_ptr(), tiles, _stream(dev)))
+            dW_hh = wparts.sum(dim=0)
             dgh2 = dgh.view(T * N, 3 * H)
-            h_prev = saved.view(T * N, 5 * H)[:, :H]        # rows 5H apart: a strided GEMM operand, no copy
-            dW_hh = dgh2.t() @ h_prev                       # the one plain GEMM left: library (cuBLAS, fp32)
             dx = None
             if need_dx:
                 dgi = torch.cat([dgh2[:, :2 * H], dgi_n.view(T * N, H)], dim=1)

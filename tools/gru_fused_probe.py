@@ -56,7 +56,13 @@ ms_bk, _ = timed(lambda: _lib.check(_lib.lib.sldm_gru_backward(x.data_ptr(), N, 
                  saved.data_ptr(), dgh.data_ptr(), None, parts.data_ptr(), rows, _stream(dev))))
 ms_mm, _ = timed(lambda: dgh.view(T * N, 3 * H).t() @ saved.view(T * N, 5 * H)[:, :H])
 ms_ps, _ = timed(lambda: parts.sum(dim=0))
-print(f"backward pieces: k_gru_bwd {ms_bk:.2f} ms, dW_hh GEMM {ms_mm:.2f} ms, partial sum {ms_ps:.3f} ms")
+tiles = _lib.lib.sldm_gru_wgrad_tiles(N, T)
+wparts = torch.empty(tiles, 3 * H, H, device=dev)
+ms_wg, _ = timed(lambda: _lib.check(_lib.lib.sldm_gru_wgrad(dgh.data_ptr(), saved.data_ptr(), N, T, H, wparts.data_ptr(), tiles, _stream(dev))))
+ms_ws, dW = timed(lambda: wparts.sum(dim=0))
+ref = dgh.view(T * N, 3 * H).t() @ saved.view(T * N, 5 * H)[:, :H]
+print(f"backward pieces: k_gru_bwd {ms_bk:.2f} ms, dW_hh: k_gru_wgrad {ms_wg:.2f} ms + tile sum {ms_ws:.3f} ms (cuBLAS GEMM {ms_mm:.2f} ms, "
+      f"max rel diff {float((dW - ref).abs().max() / ref.abs().max()):.2e}), partial sum {ms_ps:.3f} ms")
 del saved, dgh
 flops = 2.0 * N * T * 3 * H * (H + I)
 print(f"N={N} T={T} I={I} H={H}")
