@@ -18,8 +18,8 @@ Workloads (all synthetic, seeded, random-init weights):
   infer           : the batch shape, forward only under inference_mode (BASELINE configs[2]).
   c2              : BASELINE configs[1], the reference's FULL training step (GruSage + BCE + Adam) on our kernels; its own
                     metric (graphs/s) and file (bench_c2.py).  It is not the default because BASELINE's metric is quoted on
-                    SageBlock fwd+bwd (edges/s, % of HBM roofline) and 92 % of that step is the GRU, a torch library layer
-                    (profiles/r01l_bench_c2_1024.json): the SageBlock edge rate cannot be read off it.
+                    SageBlock fwd+bwd (edges/s, % of HBM roofline) and 80 % of that step is the GRU sequence head (our fused
+                    FP32 kernels, csrc/gru.cu; profiles/r01m_bench_c2_1024.json): the SageBlock edge rate cannot be read off it.
 value   = edge-layer traversals per second (E*L per step), whole job, inputs resident in HBM.
 e2e     = the same through the public module call with pinned HOST inputs: H2D of x and
           edge_index, fwd+bwd, D2H of the loss, all inside the timed region.

@@ -10,8 +10,9 @@ slope 0.1, map encoder SageBlock [f+8, 32, 32] over a 2048-segment map graph, at
 Batch = G sequences, each one unit vehicle graph (~200 nodes, ~1000 edges) with x [n, 16 frames, 6 features].
 A step = zero_grad, forward, loss, backward, (gradient all-reduce at N > 1,) Adam step, loss.item() -- as in the
 reference's loop.  value = graphs (sequences) per second over all ranks; e2e adds the per-step H2D copy of the batch from
-pinned memory.  The GRU / Linear / Embedding layers are torch library code in the reference and here; `components_ms`
-shows where the step's time goes.  cpu_baseline / --impl reference = oracle/grusage_oracle.py (the composition pinned
+pinned memory.  The GRU runs on the fused kernels of csrc/gru.cu (SLDM_DISABLE_FUSED_GRU=1: torch's library GRU); the
+Linear / Embedding layers are torch library code in the reference and here; `components_ms` shows where the step's time
+goes and `roofline` rates the GRU forward kernel, the longest of the step, against the FP32-pipe peak.  cpu_baseline / --impl reference = oracle/grusage_oracle.py (the composition pinned
 against the reference's own classes) on all host threads, on a bounded sample of the same batch.
 """
 from __future__ import annotations
