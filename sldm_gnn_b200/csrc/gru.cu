@@ -42,6 +42,27 @@ __device__ __forceinline__ void fma4(float& acc, const float4& a, const float4& 
   acc = fmaf(a.w, b.w, acc);
 }
 
+// Packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): two FMAs per issue slot at the same pipe rate (tools/ffma2_probe.cu).
+// Used by k_gru_wgrad (4.03 -> 3.75 ms).  In the recurrence kernels a k-paired FFMA2 main loop (even k in the low half of
+// an accumulator pair, odd k in the high half) measured no better than scalar FFMA (forward 5.70 vs 5.34 ms): they are not
+// issue-bound but at the register-operand rate of a register-tiled outer product, so they keep the scalar loop.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f32x2_dup(float v) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float f32x2_sum(f32x2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+
 __device__ __forceinline__ void load_x_tile(float* xs, const float* __restrict__ x, int64_t row0, int nrows, int TI) {
   const float* xg = x + row0 * TI;
   for (int i = threadIdx.x; i < kGruRows * TI; i += kGruThreads) xs[i] = i < nrows * TI ? __ldg(xg + i) : 0.f;
@@ -324,11 +345,11 @@ k_gru_wgrad(const float* __restrict__ dgh, const float* __restrict__ saved, int6
   float* Gs = sm;                  // [2][CH][3H]
   float* Ps = sm + 2 * CH * G3;    // [2][CH][H]
   const int tid = threadIdx.x, b = tid & 7, a = tid >> 3;
-  float acc[6][CW];
+  f32x2 acc[6][CW / 2];          // pairs of adjacent hidden columns (FFMA2: the gate value is duplicated, h_prev pairs are natural)
 #pragma unroll
   for (int m = 0; m < 6; ++m)
 #pragma unroll
-    for (int n = 0; n < CW; ++n) acc[m][n] = 0.f;
+    for (int n = 0; n < CW / 2; ++n) acc[m][n] = 0ull;
   const int64_t nchunks = ceil_div<int64_t>(rows, CH);
 
   auto load = [&](int stage, int64_t c) {
@@ -363,16 +384,14 @@ k_gru_wgrad(const float* __restrict__ dgh, const float* __restrict__ saved, int6
       const float2 g0 = *reinterpret_cast<const float2*>(g + r * G3);
       const float2 g1 = *reinterpret_cast<const float2*>(g + r * G3 + 2);
       const float2 g2 = *reinterpret_cast<const float2*>(g + r * G3 + 4);
-      const float gv[6] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y};
+      const f32x2 gv[6] = {f32x2_dup(g0.x), f32x2_dup(g0.y), f32x2_dup(g1.x), f32x2_dup(g1.y), f32x2_dup(g2.x), f32x2_dup(g2.y)};
 #pragma unroll
       for (int q = 0; q < CW / 4; ++q) {
-        const float4 pv = *reinterpret_cast<const float4*>(p + r * H + 4 * q);
+        const ulonglong2 pv = *reinterpret_cast<const ulonglong2*>(p + r * H + 4 * q);
 #pragma unroll
         for (int m = 0; m < 6; ++m) {
-          acc[m][4 * q + 0] = fmaf(gv[m], pv.x, acc[m][4 * q + 0]);
-          acc[m][4 * q + 1] = fmaf(gv[m], pv.y, acc[m][4 * q + 1]);
-          acc[m][4 * q + 2] = fmaf(gv[m], pv.z, acc[m][4 * q + 2]);
-          acc[m][4 * q + 3] = fmaf(gv[m], pv.w, acc[m][4 * q + 3]);
+          acc[m][2 * q + 0] = ffma2(gv[m], pv.x, acc[m][2 * q + 0]);
+          acc[m][2 * q + 1] = ffma2(gv[m], pv.y, acc[m][2 * q + 1]);
         }
       }
     }
@@ -383,9 +402,11 @@ k_gru_wgrad(const float* __restrict__ dgh, const float* __restrict__ saved, int6
 #pragma unroll
   for (int m = 0; m < 6; ++m)
 #pragma unroll
-    for (int q = 0; q < CW / 4; ++q)
-      st4(out + (6 * a + m) * H + CW * b + 4 * q,
-          make_float4(acc[m][4 * q], acc[m][4 * q + 1], acc[m][4 * q + 2], acc[m][4 * q + 3]));
+    for (int q = 0; q < CW / 4; ++q) {
+      ulonglong2 v;
+      v.x = acc[m][2 * q]; v.y = acc[m][2 * q + 1];
+      *reinterpret_cast<ulonglong2*>(out + (6 * a + m) * H + CW * b + 4 * q) = v;
+    }
 }
 
 int64_t gru_wgrad_tiles(int64_t rows) {

@@ -40,7 +40,52 @@ k_readout_fwd(const float* __restrict__ x, int32_t F, const int32_t* __restrict_
     for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int e = 0; e < 4; ++e) { s[q][e] = 0.f; m[q][e] = -INFINITY; }
-    for (int i = beg + warp; i < end; i += kRoWarps) {
+    // a warp walks rows beg+warp, +8, ...: four member ids are fetched first, then their four rows (independent loads
+    // in flight: one row at a time behind a dependent index load ran at 2.7 TB/s), accumulated in the same row order
+    int i = beg + warp;
+    for (; i + 3 * kRoWarps < end; i += 4 * kRoWarps) {
+      const float* row[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) row[k] = x + (int64_t)__ldg(members + i + k * kRoWarps) * F;
+      if (VEC) {
+        float4 v[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = c0 + (q * 32 + lane) * W;
+            if (c < F) v[k][q] = ldg4(row[k] + c);
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = c0 + (q * 32 + lane) * W;
+            if (c < F) {
+              s[q][0] += v[k][q].x; s[q][1] += v[k][q].y; s[q][2] += v[k][q].z; s[q][3] += v[k][q].w;
+              m[q][0] = fmaxf(m[q][0], v[k][q].x); m[q][1] = fmaxf(m[q][1], v[k][q].y);
+              m[q][2] = fmaxf(m[q][2], v[k][q].z); m[q][3] = fmaxf(m[q][3], v[k][q].w);
+            }
+          }
+      } else {
+        float v[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = c0 + (q * 32 + lane) * W;
+            if (c < F) v[k][q] = __ldg(row[k] + c);
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = c0 + (q * 32 + lane) * W;
+            if (c < F) { s[q][0] += v[k][q]; m[q][0] = fmaxf(m[q][0], v[k][q]); }
+          }
+      }
+    }
+    for (; i < end; i += kRoWarps) {
       const float* row = x + (int64_t)__ldg(members + i) * F;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -105,7 +150,29 @@ k_readout_coef(const float* __restrict__ x, int32_t F, const int32_t* __restrict
       float mx[4], n[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int e = 0; e < W; ++e) mx[e] = __ldg(out_max + (int64_t)g * ld_max + c + e);
-      for (int i = beg + warp; i < end; i += kRoWarps) {
+      int i = beg + warp;
+      for (; i + 3 * kRoWarps < end; i += 4 * kRoWarps) {   // four independent rows in flight (counts: order-free)
+        const float* row[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) row[k] = x + (int64_t)__ldg(members + i + k * kRoWarps) * F + c;
+        if (VEC) {
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = ldg4(row[k]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            n[0] += v[k].x == mx[0] ? 1.f : 0.f; n[1] += v[k].y == mx[1] ? 1.f : 0.f;
+            n[2] += v[k].z == mx[2] ? 1.f : 0.f; n[3] += v[k].w == mx[3] ? 1.f : 0.f;
+          }
+        } else {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = __ldg(row[k]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) n[0] += v[k] == mx[0] ? 1.f : 0.f;
+        }
+      }
+      for (; i < end; i += kRoWarps) {
         const float* row = x + (int64_t)__ldg(members + i) * F + c;
         if (VEC) {
           const float4 v = ldg4(row);
