@@ -14,6 +14,7 @@ from sldm_gnn_b200 import _lib
 from sldm_gnn_b200.gru import fused_gru_eligible, gru_last_hidden
 
 RTOL, ATOL = 1e-5, 1e-6
+GOLDEN = sorted(__import__("glob").glob(os.path.join(os.path.dirname(__file__), "golden", "gru", "*.pt")))
 
 
 # ------------------------------------------------------------------- CPU side --
@@ -44,6 +45,25 @@ def test_unsupported_shapes_return_eunsupported_without_gpu():
     with pytest.raises(NotImplementedError, match="hidden size 128"):
         _lib.check(rc)
     assert _lib.lib.sldm_gru_forward(None, -1, 16, 6, 96, None, None, None, None, None, None, None) == _lib.EINVAL
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_golden_fixtures_are_what_torch_gru_computes(path):
+    """The committed vectors (tests/golden/make_golden_gru.py) are reproduced by this image's torch.nn.GRU on the CPU:
+    a drift of the library under the fixtures would show here, not as a false alarm in the GPU parity test."""
+    fix = torch.load(path)
+    c = fix["cfg"]
+    g = torch.nn.GRU(c["I"], c["H"], 1, batch_first=True)
+    g.load_state_dict(fix["state_dict"])
+    x = fix["x"].clone().requires_grad_(True)
+    h = g(x)[1][-1]
+    h.backward(fix["up"])
+    assert torch.allclose(h, fix["f32"]["h"], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(x.grad, fix["f32"]["dx"], rtol=1e-5, atol=1e-6)
+    for k, p in g.named_parameters():
+        want = fix["f32"]["grads"][k]
+        assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-6 * max(1.0, float(want.abs().max()))), k
+    assert len(GOLDEN) == 3
 
 
 # ------------------------------------------------------------------- GPU side --
@@ -99,6 +119,25 @@ def test_fused_gru_matches_torch_gru(N, T, I, H, need_dx):
         _close(x.grad, dx32, dx64, "dx")
     else:
         assert x.grad is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_fused_gru_matches_golden(path):
+    """Against the committed vectors of the reference's layer (no torch GRU call on this side)."""
+    dev = torch.device("cuda:0")
+    fix = torch.load(path)
+    c = fix["cfg"]
+    gru = torch.nn.GRU(c["I"], c["H"], 1, batch_first=True)
+    gru.load_state_dict(fix["state_dict"])
+    gru = gru.to(dev)
+    x = fix["x"].to(dev).requires_grad_(True)
+    h = gru_last_hidden(gru, x)
+    h.backward(fix["up"].to(dev))
+    _close(h, fix["f32"]["h"], fix["f64"]["h"], "h_last")
+    _close(x.grad, fix["f32"]["dx"], fix["f64"]["dx"], "dx")
+    for k, p in gru.named_parameters():
+        _close(p.grad, fix["f32"]["grads"][k], fix["f64"]["grads"][k], f"grad {k}", scale_atol=True)
 
 
 @pytest.mark.gpu
