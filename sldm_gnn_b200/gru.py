@@ -9,6 +9,7 @@ x = hlast[-1]`).  The parameters stay in the caller's own `torch.nn.GRU` module 
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from ._lib import lib, check
 from .ops import _ptr, _require_cuda, _stream
@@ -45,6 +46,7 @@ class _GruLastHiddenFn(torch.autograd.Function):
         return h_last
 
     @staticmethod
+    @once_differentiable   # hand-written first-order gradients: a double backward raises instead of returning garbage
     def backward(ctx, dh_last):
         x, W_ih, W_hh, saved = ctx.saved_tensors
         N, T, I = x.shape

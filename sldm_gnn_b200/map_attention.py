@@ -15,6 +15,7 @@ from __future__ import annotations
 import os
 
 import torch
+from torch.autograd.function import once_differentiable
 import torch.nn as nn
 
 from . import _lib
@@ -45,6 +46,7 @@ class _MapAttentionFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable   # hand-written first-order gradients: a double backward raises instead of returning garbage
     def backward(ctx, dout):
         emb, idx, dist, w, W1, b1, W2 = ctx.saved_tensors
         B, K, S, D, H = idx.size(0), ctx.K, ctx.S, emb.size(1), W1.numel()

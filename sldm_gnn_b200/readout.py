@@ -10,6 +10,7 @@ we -- pass `size` (PyG's `Batch.num_graphs`) to stay sync-free.  CUDA only: the 
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import lib, check
@@ -54,6 +55,7 @@ class _ReadoutFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable   # hand-written first-order gradients: a double backward raises instead of returning garbage
     def backward(ctx, dout):
         x, batch, out = ctx.saved_tensors
         want_mean, want_max = ctx.want

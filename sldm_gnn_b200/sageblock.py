@@ -19,6 +19,7 @@ from __future__ import annotations
 import math
 
 import torch
+from torch.autograd.function import once_differentiable
 import torch.nn as nn
 
 from . import ops
@@ -77,6 +78,7 @@ class _SageLayerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable   # hand-written first-order gradients: a double backward raises instead of returning garbage
     def backward(ctx, dout):
         x, agg, xhat, rstd, W_l, W_r, ln_w, ln_b = ctx.saved_tensors
         need_dx = ctx.needs_input_grad[0]

@@ -445,3 +445,16 @@ def test_c4_full_size_forward_backward_properties(dev):
     assert_close(y.detach().cpu()[rows], want, "sampled rows of the 1M-node graph")
     # gradient checksum: d(sum y)/d b_l summed over rows equals column sums of dz -> finite & nonzero
     assert all(torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0 for p in ours.parameters())
+
+
+def test_double_backward_raises_instead_of_returning_garbage(dev):
+    """The backward passes are hand-written first-order formulas (torch's own layers support create_graph=True; these
+    do not): asking for a second derivative must fail loudly."""
+    torch.manual_seed(5)
+    ei, _, N = unit_map_graphs(2, seed=3)
+    blk = sg.SageBlock([16, 16], negative_slope=0.1).to(dev)
+    x = torch.randn(N, 16, device=dev, requires_grad=True)
+    y = blk(x, ei.to(dev))
+    (g,) = torch.autograd.grad(y.square().sum(), x, create_graph=True)
+    with pytest.raises(RuntimeError, match="once_differentiable|differentiate twice"):
+        g.sum().backward()
