@@ -66,6 +66,26 @@ def test_golden_fixtures_are_what_torch_gru_computes(path):
     assert len(GOLDEN) == 3
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_numpy_oracle_reproduces_the_golden_vectors(path):
+    """oracle/gru_oracle.py (the recurrence and the backward decomposition csrc/gru.cu implements, as numpy loops) against
+    the vectors of the reference's layer, in fp64."""
+    from oracle.gru_oracle import gru_last_hidden_oracle, gru_last_hidden_backward_oracle
+    fix = torch.load(path)
+    sd = {k: v.double().numpy() for k, v in fix["state_dict"].items()}
+    x = fix["x"].double().numpy()
+    args = (sd["weight_ih_l0"], sd["weight_hh_l0"], sd["bias_ih_l0"], sd["bias_hh_l0"])
+    h, tape = gru_last_hidden_oracle(x, *args)
+    want = fix["f64"]
+    assert abs(h - want["h"].numpy()).max() < 1e-12
+    dx, dW_ih, dW_hh, db_ih, db_hh = gru_last_hidden_backward_oracle(fix["up"].double().numpy(), x, args[0], args[1], tape)
+    got = {"weight_ih_l0": dW_ih, "weight_hh_l0": dW_hh, "bias_ih_l0": db_ih, "bias_hh_l0": db_hh}
+    for k, g in got.items():
+        w = want["grads"][k].numpy()
+        assert abs(g - w).max() <= 1e-10 * max(1.0, abs(w).max()), k
+    assert abs(dx - want["dx"].numpy()).max() < 1e-10
+
+
 # ------------------------------------------------------------------- GPU side --
 def _close(got, want, want64, what, scale_atol=False):
     got, want, w64 = got.detach().cpu(), want.detach(), want64.detach().double()
