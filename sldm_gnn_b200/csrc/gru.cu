@@ -13,9 +13,9 @@
 //            as one [T, N, 5, H] buffer: a warp's output of a step is 8 x 5H contiguous floats (with five [N, T, H]
 //            arrays the 128-byte pieces were 6 KB apart and the stores cost 3.6 ms on top of 5.7 ms of arithmetic).
 //   backward (k_gru_bwd):  the same tiling walks t = T-1 .. 0 with W_hh transposed in shared memory
-//            (dh_{t-1} = dh_t z + [dr dz dn r] W_hh); it emits the hidden-gate gradients dgh [T,N,3H] for the one
-//            library GEMM that is left (dW_hh = dgh^T h_prev) and accumulates dW_ih, db_ih, db_hh per CTA in
-//            registers (fixed order; the per-CTA partials are summed by the caller).
+//            (dh_{t-1} = dh_t z + [dr dz dn r] W_hh); it emits the hidden-gate gradients dgh [T,N,3H] and accumulates
+//            dW_ih, db_ih, db_hh per CTA in registers (fixed order; the per-CTA partials are summed by the caller).
+//   wgrad    (k_gru_wgrad): dW_hh = dgh^T h_prev over the T*N rows, one persistent CTA per SM (below).
 //
 // Arithmetic: FP32 FMA in sequential k order, expf / tanhf / IEEE division like ATen's gru_cell_forward, i.e. the
 // reference's own formulas (aten/src/ATen/native/cuda/RNN.cu); bound by the FP32 pipe (2*3H*H flops per sequence and
@@ -42,10 +42,11 @@ __device__ __forceinline__ void fma4(float& acc, const float4& a, const float4& 
   acc = fmaf(a.w, b.w, acc);
 }
 
-// Packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): two FMAs per issue slot at the same pipe rate (tools/ffma2_probe.cu).
-// Used by k_gru_wgrad (4.03 -> 3.75 ms).  In the recurrence kernels a k-paired FFMA2 main loop (even k in the low half of
-// an accumulator pair, odd k in the high half) measured no better than scalar FFMA (forward 5.70 vs 5.34 ms): they are not
-// issue-bound but at the register-operand rate of a register-tiled outer product, so they keep the scalar loop.
+// Packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): two FMAs per issue slot at the same pipe rate (tools/ffma2_probe.cu:
+// a register-tiled 8 x 9 outer product reaches 56 TFLOP/s with FFMA and 65 with FFMA2 on B200).  Used by k_gru_wgrad
+// (4.03 -> 3.75 ms).  In the recurrence kernels a k-paired FFMA2 main loop (even k in the low half of an accumulator pair,
+// odd k in the high half) measured slower than scalar FFMA (forward 5.70 vs 5.34 ms: 144 accumulator registers and ~80
+// pair-shuffling MOVs per 288 FFMA2), so they keep the scalar loop.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 d;
@@ -57,12 +58,6 @@ __device__ __forceinline__ f32x2 f32x2_dup(float v) {
   asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
   return r;
 }
-__device__ __forceinline__ float f32x2_sum(f32x2 v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return lo + hi;
-}
-
 __device__ __forceinline__ void load_x_tile(float* xs, const float* __restrict__ x, int64_t row0, int nrows, int TI) {
   const float* xg = x + row0 * TI;
   for (int i = threadIdx.x; i < kGruRows * TI; i += kGruThreads) xs[i] = i < nrows * TI ? __ldg(xg + i) : 0.f;
