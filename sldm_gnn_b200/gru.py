@@ -28,6 +28,19 @@ def fused_gru_eligible(gru: torch.nn.GRU, x: torch.Tensor) -> bool:
         and lib.sldm_gru_supported(int(x.size(1)), int(x.size(2)), int(gru.hidden_size)))
 
 
+def decode_partials(P: torch.Tensor, H: int, I: int):
+    """Summed per-tile partials of sldm_gru_backward -> (dW_ih [3H,I], db_ih [3H], db_hh [3H]).
+
+    Layout (include/sldm_sage.h): [28*U][32 lanes], U = H/32; v = (u*3+g)*8 + i -> dW_ih[g*H + 32u + lane][i];
+    v = 24U + u*3 + g -> db_ih[g*H + 32u + lane]; v = 27U + u -> db_hh[2H + 32u + lane]; db_hh[:2H] = db_ih[:2H]
+    (the r and z gates see the same pre-activation gradient on the input and the hidden side)."""
+    U = H // 32
+    dW_ih = P[:24 * U * 32].view(U, 3, 8, 32).permute(1, 0, 3, 2).reshape(3 * H, 8)[:, :I].contiguous()
+    db_ih = P[24 * U * 32:27 * U * 32].view(U, 3, 32).permute(1, 0, 2).reshape(3 * H)
+    db_hh = torch.cat([db_ih[:2 * H], P[27 * U * 32:]])
+    return dW_ih, db_ih, db_hh
+
+
 class _GruLastHiddenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W_ih, W_hh, b_ih, b_hh):
@@ -51,7 +64,6 @@ class _GruLastHiddenFn(torch.autograd.Function):
         x, W_ih, W_hh, saved = ctx.saved_tensors
         N, T, I = x.shape
         H = W_hh.shape[1]
-        U = H // 32
         dev = x.device
         need_dx = ctx.needs_input_grad[0]
         dh_last = dh_last.contiguous()
@@ -64,10 +76,7 @@ class _GruLastHiddenFn(torch.autograd.Function):
             check(lib.sldm_gru_backward(x.data_ptr(), N, T, I, H, W_hh.data_ptr(), dh_last.data_ptr(),
                                         saved.data_ptr(), dgh.data_ptr(), _ptr(dgi_n), parts.data_ptr(), rows,
                                         _stream(dev)))
-            P = parts.sum(dim=0)
-            dW_ih = P[:24 * U * 32].view(U, 3, 8, 32).permute(1, 0, 3, 2).reshape(3 * H, 8)[:, :I].contiguous()
-            db_ih = P[24 * U * 32:27 * U * 32].view(U, 3, 32).permute(1, 0, 2).reshape(3 * H)
-            db_hh = torch.cat([db_ih[:2 * H], P[27 * U * 32:]])
+            dW_ih, db_ih, db_hh = decode_partials(parts.sum(dim=0), H, I)
             tiles = int(lib.sldm_gru_wgrad_tiles(N, T))
             wparts = torch.empty((tiles, 3 * H, H), **f32)
             check(lib.sldm_gru_wgrad(dgh.data_ptr(), saved.data_ptr(), N, T, H, wparts.data_ptr(), tiles, _stream(dev)))

@@ -31,6 +31,29 @@ def test_support_queries_without_gpu():
     assert lib.sldm_gru_partial_width(96) == 28 * 96 and lib.sldm_gru_partial_width(33) == -1
 
 
+@pytest.mark.parametrize("H,I", [(96, 6), (64, 8), (32, 1)])
+def test_partial_layout_decode(H, I):
+    """Host half of the backward: the [28*H/32][32] per-tile layout of include/sldm_sage.h, written here element by
+    element the way k_gru_bwd's lanes do, decodes to the torch parameter layouts."""
+    from sldm_gnn_b200.gru import decode_partials
+    U = H // 32
+    g = torch.Generator().manual_seed(H + I)
+    dW = torch.randn(3 * H, 8, generator=g)
+    dW[:, I:] = 0
+    dbi, dbn = torch.randn(3 * H, generator=g), torch.randn(H, generator=g)
+    P = torch.zeros(int(_lib.lib.sldm_gru_partial_width(H)))
+    for u in range(U):
+        for lane in range(32):
+            for gate in range(3):
+                for i in range(8):
+                    P[((u * 3 + gate) * 8 + i) * 32 + lane] = dW[gate * H + 32 * u + lane, i]
+                P[(24 * U + u * 3 + gate) * 32 + lane] = dbi[gate * H + 32 * u + lane]
+            P[(27 * U + u) * 32 + lane] = dbn[32 * u + lane]
+    dW_ih, db_ih, db_hh = decode_partials(P, H, I)
+    assert dW_ih.shape == (3 * H, I) and torch.equal(dW_ih, dW[:, :I])
+    assert torch.equal(db_ih, dbi) and torch.equal(db_hh, torch.cat([dbi[:2 * H], dbn]))
+
+
 def test_cpu_tensors_are_not_eligible_and_raise():
     gru = torch.nn.GRU(6, 96, 1, batch_first=True)
     x = torch.randn(4, 16, 6)
