@@ -62,11 +62,11 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 WORKLOADS = {
-    "batch": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=256),
+    "batch": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=4096),
     "c1": dict(kind="graphs", graphs=32, hdims=[64, 64, 64], cpu_sample_graphs=32),
     "c4": dict(kind="skewed", nodes=1_000_000, edges=10_000_000, hdims=[128, 128], cpu_sample_graphs=None),
     # BASELINE configs[2]: batched inference, hidden 128 -- one mega-batch of 4096 graphs, forward only (inference_mode)
-    "infer": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=256, forward_only=True),
+    "infer": dict(kind="graphs", graphs=4096, hdims=[128, 128, 128], cpu_sample_graphs=4096, forward_only=True),
 }
 SLOPE = 0.1
 METRIC = "sageblock_fwd_bwd_edges_per_sec"     # --workload infer reports forward-only traversals under the same name, flagged in config.step
@@ -85,7 +85,7 @@ def measured_peaks():
 
 
 def make_inputs(wl, seed):
-    from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+    from workloads import unit_map_graphs, skewed_graph
     g = torch.Generator().manual_seed(1000 + seed)
     if wl["kind"] == "graphs":
         ei, bv, N = unit_map_graphs(wl["graphs"], seed=seed)
@@ -101,21 +101,28 @@ def make_inputs(wl, seed):
 # CUDA kernel behind each timed group, and how many times it runs per layer and step (fwd+bwd)
 KERNEL_NAMES = {"segment_mean_fwd": "k_segment_rows_lean", "project_ln_act_fwd": "k_sage_tc<NT, MODE_FWD>",
                 "segment_sum_bwd": "k_segment_rows_lean (transpose CSR)", "ln_bwd": "k_ln_bwd_rows",
+                "dgrad": "k_split_weights_t + k_sage_tc<NT, MODE_DGRAD>", "wgrad": "k_wgrad_tc<NB> + k_reduce_parts x2",
                 "csr_build": "k_convert + k_digit_hist + k_onesweep_pass x3 + k_rowptr_from_sorted",
                 "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean",
                 "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_coef + k_readout_bwd",
                 "map_attention_fwd": "k_map_attention_fwd", "map_attention_bwd": "k_map_attention_bwd + membership CSR + k_map_attention_demb",
                 "collate_32_graphs": "k_concat_chunks x5 + k_collate_edge_index + k_batch_from_ptr (+ host table upload)"}
-KERNEL_LAUNCHES_PER_LAYER = {"segment_mean_fwd": 1, "project_ln_act_fwd": 1, "segment_sum_bwd": 1}
+# every group that is ONE dominant kernel (the candidates of `roofline`), launches per layer and step
+KERNEL_LAUNCHES_PER_LAYER = {"segment_mean_fwd": 1, "project_ln_act_fwd": 1, "ln_bwd": 1, "dgrad": 1, "wgrad": 1,
+                             "segment_sum_bwd": 1}
 
 
-def measured_traffic(workload, group):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def committed_ncu_traffic(workload, group):
+    """DRAM bytes per launch from the latest committed ncu --set full capture (profiles/*_traffic.json), or None.
+    Reported beside the roofline as `traffic_ncu_committed`: it is NOT a measurement of this run (`traffic` is null)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    path = files[-1] if files else ""
     if group is None or not os.path.exists(path):
         return None
     try:
-        return json.load(open(path)).get(workload, {}).get(group)
+        v = json.load(open(path)).get(workload, {}).get(group)
+        return None if v is None else {"bytes_per_launch": v, "source": os.path.relpath(path, ROOT)}
     except Exception:
         return None
 
@@ -124,6 +131,11 @@ def measured_traffic(workload, group):
 def layer_bytes_fwd_bwd(N, E, Fin, Fout, s=4):
     """2E(Fin s + 4) + N s (6 Fin + 5 Fout) + 28 N per layer, fwd+bwd (training)."""
     return 2 * E * (Fin * s + 4) + N * s * (6 * Fin + 5 * Fout) + 28 * N
+
+
+def layer_bytes_fwd_bwd_cache_perfect(N, E, Fin, Fout, s=4):
+    """8d's own lower bound: the two gathers read every row once (E*Fin*s -> N*Fin*s), indices still cost 4 B per edge."""
+    return 2 * (4 * E + N * Fin * s) + N * s * (6 * Fin + 5 * Fout) + 28 * N
 
 
 def csr_bytes(N, E):
@@ -205,35 +217,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU legs --
-def cpu_reference_step(block, x, ei, forward_only=False):
+def upstream_gradient(N, width):
+    """dL/dout of the step, the same tensor in both arms: stands in for whatever follows the block."""
+    return torch.randn(N, width, generator=torch.Generator().manual_seed(7 + N))
+
+
+def cpu_reference_step(block, x, ei, w, forward_only=False):
     if forward_only:
         with torch.inference_mode():
             block(x, ei)
         return
     xr = x.clone().requires_grad_(True)
     y = block(xr, ei)
-    y.square().mean().backward()
+    y.backward(w)
     block.zero_grad(set_to_none=True)
 
 
 def cpu_sample(wl, seed=0):
-    """Bounded sample of the same workload for the CPU legs."""
-    from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+    """The workload of the CPU legs: the WHOLE batch for the graph workloads (seed 0, the GPU arm's first batch);
+    a 1/10-scale graph for c4 (the full one is ~4 s per step and tens of GB of [E, F] intermediates)."""
+    from workloads import skewed_graph
     if wl["kind"] == "graphs":
-        n = wl["cpu_sample_graphs"]
-        ei, _, N = unit_map_graphs(n, seed=seed)
-        desc = f"{n} of {wl['graphs']} unit map graphs of one batch, fwd+bwd"
-        graphs = n
+        x, ei, N, graphs, _ = make_inputs(wl, seed)
+        desc = f"the full batch: {graphs} unit map graphs, {N} nodes, {ei.size(1)} edges"
     else:
         N, E = wl["nodes"] // 10, wl["edges"] // 10
         ei = skewed_graph(N, E, seed=seed)
-        desc = f"1/10-scale skewed graph ({N} nodes, {E} edges), fwd+bwd"
+        x = torch.randn(N, wl["hdims"][0], generator=torch.Generator().manual_seed(1000 + seed))
+        desc = f"1/10-scale skewed graph ({N} nodes, {E} edges) -- NOT the full configuration"
         graphs = 1
-    x = torch.randn(N, wl["hdims"][0], generator=torch.Generator().manual_seed(seed))
     return x, ei, N, graphs, desc
 
 
-def run_cpu(wl, steps, warmup, min_seconds=0.0):
+def run_cpu(wl, steps, warmup, min_seconds=0.0, max_seconds=1e9):
     """The reference's CPU path: oracle/sage_oracle.py restates PyG 2.7.0 SAGEConv with the same ATen
     CPU operators (torch-geometric is not installable here), all host threads."""
     from oracle.sage_oracle import SageBlockOracle
@@ -242,34 +258,42 @@ def run_cpu(wl, steps, warmup, min_seconds=0.0):
     torch.manual_seed(0)
     blk = SageBlockOracle(wl["hdims"], dropout=None, negative_slope=SLOPE)
     x, ei, N, graphs, desc = cpu_sample(wl)
+    w = upstream_gradient(N, wl["hdims"][-1])
     fo = bool(wl.get("forward_only"))
     for _ in range(warmup):
-        cpu_reference_step(blk, x, ei, fo)
+        cpu_reference_step(blk, x, ei, w, fo)
     t0 = time.perf_counter()
     done = 0
-    while done < steps or (time.perf_counter() - t0) < min_seconds:     # cpu_baseline: about 10 s of CPU work
-        cpu_reference_step(blk, x, ei, fo)
+    while (done < steps or (time.perf_counter() - t0) < min_seconds) and (done == 0 or (time.perf_counter() - t0) < max_seconds):
+        cpu_reference_step(blk, x, ei, w, fo)
         done += 1
     steps = done
     dt = (time.perf_counter() - t0) / steps
     L = len(wl["hdims"]) - 1
-    return dict(edges_per_s=ei.size(1) * L / dt, graphs_per_s=graphs / dt, ms=dt * 1e3, cores=cores, sample=desc, iters=steps)
+    return dict(edges_per_s=ei.size(1) * L / dt, graphs_per_s=graphs / dt, ms=dt * 1e3, cores=cores,
+                sample=desc + (", forward only" if fo else ", fwd+bwd from the fixed upstream gradient"), iters=steps,
+                N=N, E=ei.size(1), graphs=graphs)
 
 
 def main_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port; PyG is not installable
+    here) on all host cores, the same workload, loss and config keys as the GPU arm.  Rank 0 only."""
     rank, _, world = env_rank()
     if rank != 0:
         return
-    r = run_cpu(wl, max(1, args.steps), max(1, args.warmup))
+    r = run_cpu(wl, max(1, args.steps), max(1, args.warmup), max_seconds=240.0)
+    full = wl["kind"] == "graphs"
+    cfg = workload_config(args.workload, wl, r["N"] if full else wl["nodes"], r["E"] if full else wl["edges"], r["graphs"])
     line = {
         "impl": "reference", "metric": METRIC, "value": r["edges_per_s"], "unit": "edges/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
+        "steps": r["iters"], "warmup": max(1, args.warmup), "ms_per_step": r["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, wl, None, None, None),
+        "config": cfg,
         "graphs_per_sec": r["graphs_per_s"],
         "cpu_baseline": {"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "oracle/sage_oracle.py (torch CPU restatement of PyG 2.7.0 SAGEConv; torch-geometric is not installable offline)",
+        "note": "oracle/sage_oracle.py (torch CPU restatement of PyG 2.7.0 SAGEConv; torch-geometric is not installable offline); "
+                "one process, all host cores, whatever --gpus says",
     }
     emit(line)
 
@@ -300,7 +324,7 @@ def widened_groups(sg, x, out, batch_vec, num_graphs, N, s):
     groups["readout_bwd"] = (lambda: torch.autograd.grad(ro, xo, dro, retain_graph=True), 2 * N * Fo * s + N * Fo * s + 8 * N)
     # mini-batch assembly at the reference's DataLoader batch size: 32 device-resident unit graphs with the
     # fields of a pack (x [n,T,6], edge_index, xsttype, xdims, pos_raw, y); timed end to end (host tables + kernels)
-    from sldm_gnn_b200.synth import unit_map_graphs
+    from workloads import unit_map_graphs
     items, nb = [], 0
     for gidx in range(32):
         eg, _, ng = unit_map_graphs(1, seed=100 + gidx)
@@ -323,7 +347,7 @@ def widened_groups(sg, x, out, batch_vec, num_graphs, N, s):
     return groups
 
 
-def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=None):
+def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=None, only=None):
     """Per-kernel-group CUDA-event timing of layer 0 (through the C-ABI, on torch's current stream)."""
     import sldm_gnn_b200 as sg
     from sldm_gnn_b200 import ops
@@ -346,12 +370,20 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
         return ts[len(ts) // 2]
 
     s = 4
+    from sldm_gnn_b200 import _lib as L_
+    bb = ops.backward_buffers(N, Fin, Fout, E, x.device, True)
+    bargs = (dout, x, agg, xhat, rstd, csr, p[0], p[2], p[3], p[4], SLOPE, True)
+    ops.layer_backward(*bargs, bufs=bb)          # fills dz / dagg / dxroot / partials for the single-stage launches
     groups = {
         "csr_build": (lambda: sg.build_csr(ei, N), csr_bytes(N, E)),
         "segment_mean_fwd": (lambda: sg.segment_reduce(x, csr), E * (Fin * s + 4) + 4 * (N + 1) + N * Fin * s),
         "project_ln_act_fwd": (lambda: ops.project_forward(agg, x, *p, ln.eps, SLOPE, True), N * s * (2 * Fin + 2 * Fout) + 4 * N),
         "layer_backward": (lambda: ops.layer_backward(dout, x, agg, xhat, rstd, csr, p[0], p[2], p[3], p[4], SLOPE, True),
                            N * s * (3 * Fout + 4 * Fin) + 12 * N + E * (Fin * s + 4) + 4 * (N + 1)),
+        # the kernels of layer_backward one at a time (include/sldm_sage.h SLDM_BWD_STAGE_*), on the buffers of a full call
+        "ln_bwd": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_LN, bufs=bb), 3 * N * s * Fout + 4 * N),
+        "dgrad": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_DGRAD, bufs=bb), N * s * (Fout + 2 * Fin) + 4 * N),
+        "wgrad": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_WGRAD, bufs=bb), N * s * (Fout + 2 * Fin)),
         "segment_sum_bwd": (lambda: sg.segment_reduce(agg, csr, transpose=True, mean=False, addend=x),
                             E * (Fin * s + 4) + 4 * (N + 1) + 2 * N * Fin * s),
     }
@@ -361,8 +393,10 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
         except Exception as exc:
             groups["widened_components"] = (lambda: (_ for _ in ()).throw(RuntimeError(repr(exc)[:200])), 0)
     res = {}
-    core = ("csr_build", "segment_mean_fwd", "project_ln_act_fwd", "layer_backward", "segment_sum_bwd")
+    core = ("csr_build", "segment_mean_fwd", "project_ln_act_fwd", "layer_backward", "ln_bwd", "dgrad", "wgrad", "segment_sum_bwd")
     for k, (fn, nbytes) in groups.items():
+        if only is not None and k not in only:
+            continue
         try:
             fn(); torch.cuda.synchronize()
             ms = timed(fn)
@@ -374,6 +408,46 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
         res[k] = {"ms": round(ms, 4), "algorithmic_bytes": nbytes, "gbs": round(nbytes / ms / 1e6, 1),
                   "frac_hbm": round(nbytes / ms / 1e6 / peak_gbs, 4)}
     return res
+
+
+def c4_record(dev, peak_gbs, steps=10):
+    """BASELINE configs[3] inside the default line (so the driver-run record carries the HBM-stress configuration):
+    one skewed graph, 1 M nodes / 10 M edges, SageBlock([128,128]), CSR build + forward + backward."""
+    import sldm_gnn_b200 as sg
+    wl = WORKLOADS["c4"]
+    hdims = wl["hdims"]
+    x_h, ei_h, N, _, _ = make_inputs(wl, 0)
+    E = ei_h.size(1)
+    torch.manual_seed(0)
+    blk = sg.SageBlock(hdims, dropout=None, negative_slope=SLOPE).to(dev)
+    x = x_h.to(dev).requires_grad_(True)
+    ei = ei_h.to(dev)
+    w = upstream_gradient(N, hdims[-1]).to(dev)
+
+    def step():
+        blk.clear_cache()
+        blk.zero_grad(set_to_none=True)
+        x.grad = None
+        blk(x, ei).backward(w)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    t1.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    nbytes = layer_bytes_fwd_bwd(N, E, hdims[0], hdims[1]) + csr_bytes(N, E)
+    kern = time_kernels(blk, x.detach(), ei, N, E, hdims, peak_gbs,
+                        only=("segment_mean_fwd", "project_ln_act_fwd", "dgrad", "wgrad", "segment_sum_bwd", "csr_build"))
+    return {"workload": "c4", "nodes": N, "edges": E, "hdims": hdims, "steps": steps, "ms_per_step": ms,
+            "edges_per_sec": E * (len(hdims) - 1) / (ms * 1e-3),
+            "roofline_step_frac": nbytes / ms / 1e6 / peak_gbs, "algorithmic_bytes": nbytes,
+            "gather_frac": kern["segment_mean_fwd"]["frac_hbm"], "kernels": kern,
+            "note": "true random gather (no L2 absorption): SURVEY 8d's byte model is honest here"}
 
 
 def main_ours(args, wl):
@@ -403,7 +477,7 @@ def main_ours(args, wl):
         b["x"] = b["x_h"].to(dev).requires_grad_(True)
         b["ei"] = b["ei_h"].to(dev)
         # fixed upstream gradient dL/dout: stands in for whatever follows the block (pooling, head, loss)
-        b["w"] = torch.randn(b["N"], hdims[-1], generator=torch.Generator().manual_seed(7 + b["N"])).to(dev)
+        b["w"] = upstream_gradient(b["N"], hdims[-1]).to(dev)
     N, E, graphs = batches[0]["N"], batches[0]["E"], batches[0]["graphs"]
 
     fwd_only = bool(wl.get("forward_only"))
@@ -472,11 +546,18 @@ def main_ours(args, wl):
             ev.record(copy_stream)
         return b, xd, eid, ev
 
+    out_h = torch.empty((N, hdims[-1]), dtype=torch.float32).pin_memory() if fwd_only else None
+
     def consume(item):
         b, xd, eid, ev = item
         main_stream.wait_event(ev)
         xd.record_stream(main_stream); eid.record_stream(main_stream)
-        return step(b, xd if fwd_only else xd.requires_grad_(True), eid).sum().item()   # .item(): the D2H read of the step's metric
+        y = step(b, xd if fwd_only else xd.requires_grad_(True), eid)
+        if fwd_only:                      # inference: the result IS the [N, Fout] output -- it comes back to the host
+            out_h[: y.size(0)].copy_(y[: out_h.size(0)], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return float(out_h[0, 0])
+        return y.sum().item()             # training: .item() = the D2H read of the step's metric
 
     nxt = prefetch(0)
     for i in range(2):
@@ -509,16 +590,20 @@ def main_ours(args, wl):
         e2e_ms = e2e_ms_total / e2e_steps
         if fwd_only:   # SURVEY 8d FWD_inf per layer: E(Fin s + 4) + 4(N+1) + N s (Fin + Fout)
             step_bytes = sum(E * (hdims[l] * 4 + 4) + 4 * (N + 1) + N * 4 * (hdims[l] + hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+            # cache-perfect lower bound: every source row read once (E*Fin*s -> N*Fin*s)
+            step_bytes_cp = sum(4 * E + 4 * (N + 1) + N * 4 * (2 * hdims[l] + hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
         else:
             step_bytes = sum(layer_bytes_fwd_bwd(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+            step_bytes_cp = sum(layer_bytes_fwd_bwd_cache_perfect(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
         if kern is None:
             kern, top = {}, None
         else:
-            # the dominant KERNEL: the largest single-kernel group (layer_backward is a sequence of kernels and is
-            # reported under "kernels" only)
-            single = [k for k in KERNEL_LAUNCHES_PER_LAYER if k in kern]
+            # the dominant KERNEL: the single-kernel group with the largest ms x launches, backward kernels included
+            # (layer_backward is the sequence of them and is reported under "kernels" only)
+            single = [k for k in KERNEL_LAUNCHES_PER_LAYER if k in kern and "ms" in kern[k]]
+            single = [k for k in single if not (fwd_only and k in ("ln_bwd", "dgrad", "wgrad", "segment_sum_bwd"))]
             top = max(single, key=lambda k: kern[k]["ms"] * KERNEL_LAUNCHES_PER_LAYER[k])
-        traffic = measured_traffic(args.workload, top)
+        traffic_ncu = committed_ncu_traffic(args.workload, top)
         line = {
             "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
@@ -528,22 +613,37 @@ def main_ours(args, wl):
             "clocks": clocks,
             "e2e": {"value": E_all * L / (e2e_ms * 1e-3), "unit": "edges/s",
                     "h2d_bytes_per_step": batches[0]["x_h"].numel() * 4 + batches[0]["ei_h"].numel() * 8,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "d2h_bytes_per_step": (N * hdims[-1] * 4 if fwd_only else 4), "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "graphs_per_sec": graphs_all / (e2e_ms * 1e-3)},
             "host_numa_bound_cpus": numa,
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
             "roofline": None if top is None else {
                 "bound": "hbm", "kernel": top, "cuda_kernel": KERNEL_NAMES[top], "achieved": kern[top]["gbs"], "peak": peak_gbs,
-                "unit": "GB/s", "frac": kern[top]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": kern[top]["frac_hbm"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kern[top]["algorithmic_bytes"], "ms_per_launch": kern[top]["ms"],
-                "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None},
+                "traffic_note": "DRAM bytes cannot be measured inside a plain run; the committed ncu --set full capture is quoted beside it",
+                "traffic_ncu_committed": traffic_ncu,
+                "candidates": {k: {"ms": kern[k]["ms"], "frac": kern[k]["frac_hbm"]} for k in single}},
             "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / ms_step / 1e6,
                               "peak": peak_gbs, "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / peak_gbs,
+                              # the same step against the two other byte counts: on block-diagonal
+                              # batches the L2 absorbs the E*Fin gather re-reads, so 8d's figure flatters the step
+                              "frac_cache_perfect": step_bytes_cp / ms_step / 1e6 / peak_gbs,
+                              "algorithmic_bytes_cache_perfect": step_bytes_cp,
+                              "frac_measured_dram": None,
+                              "frac_measured_dram_note": "needs ncu dram__bytes of every kernel of the step; see profiles/ for the latest capture",
                               "model": ("SURVEY 8d FWD_inf: sum_l [E(Fin*4+4) + 4(N+1) + 4N(Fin+Fout)] + 24E + 8(N+1)" if fwd_only else
                                         "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)")},
             "kernels": kern,
         }
+        if world == 1 and args.workload == "batch" and not args.no_c4:
+            for b in batches:                      # release the batch workload's device buffers first
+                b.pop("x", None); b.pop("ei", None); b.pop("w", None)
+            try:
+                line["c4"] = c4_record(dev, peak_gbs)
+            except Exception as exc:               # must never take the headline line down
+                line["c4"] = {"error": repr(exc)[:300]}
         if world == 1 and not args.no_cpu:
             c = run_cpu(wl, steps=3, warmup=1, min_seconds=10.0)
             line["cpu_baseline"] = {"value": c["edges_per_s"], "unit": "edges/s", "cores": c["cores"], "kind": "port",
@@ -564,6 +664,7 @@ def main():
     ap.add_argument("--c2-graphs", type=int, default=1024, help="--workload c2: sequences (vehicle graphs) per GPU and step")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the c4 sub-record of the default line")
     ap.add_argument("--skip-kernel-timing", action="store_true",
                     help="skip the per-kernel-group timing (used for the ncu launch list: only whole steps are launched)")
     args = ap.parse_args()

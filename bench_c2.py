@@ -44,7 +44,7 @@ def make_map(seed=0):
 
 
 def make_batch(graphs, seed):
-    from sldm_gnn_b200.synth import unit_map_graphs
+    from workloads import unit_map_graphs
     ei, bv, N = unit_map_graphs(graphs, seed=seed)
     g = torch.Generator().manual_seed(seed)
     return dict(x=torch.randn(N, T_FRAMES, F_DYN, generator=g), edge_index=ei, xsttype=torch.randint(0, 256, (N,), generator=g),

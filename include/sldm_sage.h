@@ -171,6 +171,26 @@ int     sldm_sage_layer_backward(const float* dout, const float* x, const float*
                                  void* workspace, int64_t workspace_bytes,
                                  sldm_stream_t stream);
 
+/* Profiling entry point: the same backward with a mask of the kernels to launch, so that a caller (bench.py) can time
+ * each of them alone with CUDA events.  A stage that is masked out must have run before on the same buffers (dz, dagg,
+ * dxroot and the workspace carry its results).  SLDM_BWD_STAGE_ALL == sldm_sage_layer_backward. */
+#define SLDM_BWD_STAGE_LN     1   /* LayerNorm / activation backward: dz + column partials (k_ln_bwd_rows)           */
+#define SLDM_BWD_STAGE_DGRAD  2   /* dagg = (dz W_l)/count, dxroot = dz W_r (k_sage_tc<MODE_DGRAD>)                 */
+#define SLDM_BWD_STAGE_WGRAD  4   /* dW_l, dW_r (k_wgrad_tc) + the fixed-order reductions of all partials           */
+#define SLDM_BWD_STAGE_GATHER 8   /* dx = dxroot + transpose segment sum of dagg (k_segment_rows_lean)              */
+#define SLDM_BWD_STAGE_ALL    15
+int     sldm_sage_layer_backward_stages(const float* dout, const float* x, const float* agg,
+                                        const float* xhat, const float* rstd,
+                                        int64_t N, int32_t Fin, int32_t Fout,
+                                        const int32_t* csr, int64_t E,
+                                        const float* W_l, const float* W_r,
+                                        const float* ln_w, const float* ln_b, float slope,
+                                        float* dx, float* dW_l, float* db_l, float* dW_r,
+                                        float* dln_w, float* dln_b,
+                                        float* dz, float* dagg, float* dxroot,
+                                        void* workspace, int64_t workspace_bytes,
+                                        sldm_stream_t stream, int32_t stages);
+
 /* ---- graph readout (the consumer of the SageBlock output) -----------------
  * Replaces global_mean_pool / global_max_pool of PyG 2.7.0 (nn/pool/glob.py -> utils/_scatter.py::scatter with
  * reduce='mean' / 'max') as used at src/models/grusage.py:113-120 (choice) and :185 (x = self.global_pool(x, batch)):

@@ -137,6 +137,31 @@ class SageBlockOracle(nn.Module):
         return x
 
 
+# ---- one layer, forward + backward, for graphs too large to materialise [E, F] -----
+def layer_fwd_bwd_chunked(x, ei, state, hdims, slope, w, dtype, chunk=1_000_000):
+    """One SageBlock layer fwd+bwd on a graph too large to materialise [E, F] in fp64: the aggregation (a3/a4 of SURVEY
+    8a) and its transpose are applied in edge chunks with index_add_ (edge order preserved), the dense part runs through
+    torch autograd.  Same arithmetic as SageBlockOracle, restated; used as the fp64 adjudicator only."""
+    N = x.size(0)
+    xd = x.to(dtype)
+    src, dst = ei[0], ei[1]
+    cnt = torch.bincount(dst, minlength=N).clamp(min=1).to(dtype)
+    agg = torch.zeros(N, hdims[0], dtype=dtype)
+    for s in range(0, src.numel(), chunk):
+        agg.index_add_(0, dst[s:s + chunk], xd.index_select(0, src[s:s + chunk]))
+    agg = (agg / cnt[:, None]).requires_grad_(True)
+    xroot = xd.clone().requires_grad_(True)
+    p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in state.items()}
+    z = F.linear(agg, p["convs.0.lin_l.weight"], p["convs.0.lin_l.bias"]) + F.linear(xroot, p["convs.0.lin_r.weight"])
+    y = F.leaky_relu(F.layer_norm(z, (hdims[1],), p["posts.0.0.weight"], p["posts.0.0.bias"], 1e-5), slope)
+    y.backward(w.to(dtype))
+    dmsg = agg.grad / cnt[:, None]
+    dx = xroot.grad.clone()
+    for s in range(0, src.numel(), chunk):
+        dx.index_add_(0, src[s:s + chunk], dmsg.index_select(0, dst[s:s + chunk]))
+    return y.detach(), dx, {k: v.grad for k, v in p.items()}
+
+
 # ---- index oracle (bit-exact contract of the CSR build) ------------------------
 def csr_oracle(edge_index: torch.Tensor, num_nodes: int):
     """rowptr/col pairs the device CSR must equal bit for bit.

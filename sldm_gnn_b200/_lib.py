@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLDM_LIB_PATH") or os.path.join(_HERE, "lib", "libsldm_sage.so")
 
 OK, EINVAL, ESHAPE, ECUDA, EWORKSPACE, EUNSUPPORTED, ENODEVICE = range(7)
+BWD_STAGE_LN, BWD_STAGE_DGRAD, BWD_STAGE_WGRAD, BWD_STAGE_GATHER, BWD_STAGE_ALL = 1, 2, 4, 8, 15
 HUB_DEGREE = 256
 HUB_CHUNK = 2048
 CSR_SECTIONS = ("meta", "rowptr_dst", "col_src", "rowptr_src", "col_dst", "hub_dst", "hub_src", "total")
@@ -50,6 +51,8 @@ _PROTOS = {
     "sldm_sage_layer_bwd_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),
     "sldm_sage_layer_backward": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _f,
                                            _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "sldm_sage_layer_backward_stages": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _f,
+                                                  _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i32]),
     "sldm_readout_workspace_bytes": (_i64, [_i64, _i32]),
     "sldm_readout_forward": (C.c_int, [_p, _i64, _i32, _p, _i64, _i64, _p, _p, _i64, _p]),
     "sldm_readout_backward": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _p, _p, _i64, _p]),

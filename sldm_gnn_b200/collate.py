@@ -69,8 +69,13 @@ def collate(data_list) -> GraphBatch:
     flat = list(ptr_h) + [0] * ((-(G + 1)) % 4)
     plan = []
     with torch.cuda.device(dev):
+        for g, d in enumerate(data_list):                   # every graph carries the same attributes (PyG's collate assumes it)
+            if set(d.keys()) != set(keys):
+                raise ValueError(f"collate: graph {g} has attributes {sorted(d.keys())}, graph 0 has {sorted(keys)}")
         for k in keys:
             vals = [getattr(d, k) for d in data_list]
+            if k == "edge_index" and not all(isinstance(v, torch.Tensor) for v in vals):
+                raise ValueError("collate: `edge_index` must be a tensor in every graph")
             if not all(isinstance(v, torch.Tensor) for v in vals):
                 setattr(out, k, vals)                       # non-tensor attributes: a list, like PyG
                 continue
@@ -121,6 +126,7 @@ def collate(data_list) -> GraphBatch:
             else:
                 check(lib.sldm_concat_chunks(tb + 8 * row0, G, mx, res.data_ptr() if total > 0 else None, stream))
             setattr(out, k, res)
+        assert have_batch or N == 0, "collate: the edge_index launch fills `batch`"   # edge_index is always a tensor here
         out.batch = batch
         out.ptr = table[:G + 1]
         out.num_graphs = G

@@ -103,6 +103,22 @@ extern "C" int sldm_sage_layer_backward(const float* dout, const float* x, const
                                         float* dz, float* dagg, float* dxroot,
                                         void* workspace, int64_t workspace_bytes,
                                         sldm_stream_t stream) {
+  return sldm_sage_layer_backward_stages(dout, x, agg, xhat, rstd, N, Fin, Fout, csr, E, W_l, W_r, ln_w, ln_b, slope,
+                                         dx, dW_l, db_l, dW_r, dln_w, dln_b, dz, dagg, dxroot, workspace,
+                                         workspace_bytes, stream, SLDM_BWD_STAGE_ALL);
+}
+
+extern "C" int sldm_sage_layer_backward_stages(const float* dout, const float* x, const float* agg,
+                                               const float* xhat, const float* rstd,
+                                               int64_t N, int32_t Fin, int32_t Fout,
+                                               const int32_t* csr, int64_t E,
+                                               const float* W_l, const float* W_r,
+                                               const float* ln_w, const float* ln_b, float slope,
+                                               float* dx, float* dW_l, float* db_l, float* dW_r,
+                                               float* dln_w, float* dln_b,
+                                               float* dz, float* dagg, float* dxroot,
+                                               void* workspace, int64_t workspace_bytes,
+                                               sldm_stream_t stream, int32_t stages) {
   SLDM_REQUIRE(N >= 0 && E >= 0, SLDM_EINVAL, "sldm_sage_layer_backward: negative N or E");
   SLDM_REQUIRE(Fin >= 1 && Fout >= 1, SLDM_ESHAPE, "sldm_sage_layer_backward: Fin=%d Fout=%d", Fin, Fout);
   SLDM_REQUIRE(dW_l && db_l && dW_r && dln_w && dln_b, SLDM_EINVAL, "sldm_sage_layer_backward: NULL gradient output");
@@ -121,8 +137,8 @@ extern "C" int sldm_sage_layer_backward(const float* dout, const float* x, const
   if (N > 0) rowptr_dst = csr + csr_layout(N, E).off[SLDM_CSR_ROWPTR_DST];
   int rc = layer_backward_launch(dout, x, agg, xhat, rstd, N, Fin, Fout, rowptr_dst, W_l, W_r, ln_w, ln_b, slope,
                                  need_dx, dW_l, db_l, dW_r, dln_w, dln_b, dz, dagg, dxroot,
-                                 static_cast<char*>(workspace) + seg_ws, workspace_bytes - seg_ws, s);
-  if (rc || !need_dx || N == 0) return rc;
+                                 static_cast<char*>(workspace) + seg_ws, workspace_bytes - seg_ws, s, stages);
+  if (rc || !need_dx || N == 0 || !(stages & SLDM_BWD_STAGE_GATHER)) return rc;
   // dx[j] = dxroot[j] + sum_{e: src[e]=j} dagg[dst[e]]   (dagg already divided by the count)
   return sldm_segment_reduce(dagg, N, Fin, csr, E, /*transpose=*/1, /*mean=*/0, dxroot, dx,
                              workspace, seg_ws, stream);

@@ -108,7 +108,7 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
                           bool need_dx,
                           float* dW_l, float* db_l, float* dW_r, float* dln_w, float* dln_b,
                           float* dz, float* dagg, float* dxroot,
-                          void* ws, int64_t ws_bytes, cudaStream_t s);
+                          void* ws, int64_t ws_bytes, cudaStream_t s, int stages = SLDM_BWD_STAGE_ALL);
 int64_t layer_backward_ws_bytes(int64_t N, int32_t Fin, int32_t Fout);
 
 bool dgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* dagg, const float* dxroot);

@@ -213,7 +213,10 @@ k_readout_bwd(const float* __restrict__ x, int64_t N, int32_t F, const int64_t* 
   const int64_t nw = (int64_t)gridDim.x * 8;
   for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < N; i += nw) {
     int64_t g = batch ? batch[i] : 0;
-    const bool ok = g >= 0 && g < G;            // out-of-range graph ids take no gradient
+    // out-of-range graph ids: clamped exactly like the membership CSR of the forward (k_convert), so forward and
+    // backward agree; the build has raised meta[2] and the host reports it (ops._IndexChecks)
+    const bool ok = G > 0;
+    g = g < 0 ? 0 : (g >= G ? G - 1 : g);
     g = ok ? g : 0;
     const float* ca = coef + g * 2 * F;
     for (int c = lane * W; c < F; c += 32 * W) {

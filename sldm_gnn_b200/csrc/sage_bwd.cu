@@ -544,7 +544,7 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
                           bool need_dx,
                           float* dW_l, float* db_l, float* dW_r, float* dln_w, float* dln_b,
                           float* dz, float* dagg, float* dxroot,
-                          void* ws, int64_t ws_bytes, cudaStream_t s) {
+                          void* ws, int64_t ws_bytes, cudaStream_t s, int stages) {
   SLDM_REQUIRE(Fin >= 1 && Fout >= 1, SLDM_ESHAPE, "backward: Fin=%d Fout=%d must be >= 1", Fin, Fout);
   SLDM_REQUIRE(Fout <= 256, SLDM_EUNSUPPORTED, "backward: Fout=%d > 256 is not covered by the kernels", Fout);
   const int64_t wcount = (int64_t)Fout * Fin;
@@ -577,7 +577,9 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
   int rc = SLDM_OK;
   int ncolparts = p.grid1;
   const bool ln_stream = !simt_dx && (Fout % 4 == 0) && b16(dout) && b16(xhat) && b16(dz) && b16(ln_w) && b16(ln_b);
-  if (ln_stream) {
+  if (!(stages & SLDM_BWD_STAGE_LN)) {
+    ncolparts = ln_stream ? p.grid_ln : p.grid1;   // profiling: dz / column partials of an earlier full call are reused
+  } else if (ln_stream) {
     ncolparts = p.grid_ln;
     if (Fout <= 128)
       k_ln_bwd_rows<1><<<p.grid_ln, 256, 0, s>>>(dout, xhat, rstd, ln_w, ln_b, slope, N, Fout, dz, colpart);
@@ -597,12 +599,13 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
 #undef SLDM_B1
   }
   if (rc) return rc;
-  if (tc_dgrad) {
+  if (tc_dgrad && (stages & SLDM_BWD_STAGE_DGRAD)) {
     rc = dgrad_tc_launch(dz, N, Fin, Fout, W_l, W_r, rowptr_dst, dagg, dxroot, static_cast<char*>(ws) + p.tc_off,
                          p.total - p.tc_off, s);
     if (rc) return rc;
   }
 
+  if (!(stages & SLDM_BWD_STAGE_WGRAD)) return SLDM_OK;
   int nparts = p.S;
   if (wgrad_tc_eligible(N, Fin, Fout, dz, agg, x)) {
     part = reinterpret_cast<float*>(static_cast<char*>(ws) + p.wg_off);

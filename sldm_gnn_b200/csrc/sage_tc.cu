@@ -42,12 +42,22 @@ using namespace tc;
 
 constexpr int kTcThreads = 768;   // 6 warpgroups: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 4
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
-constexpr int kTcStages = 5;        // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
+// Epilogue stores: 1 = 256-bit st.global straight from the accumulator registers (a thread owns 8*NT consecutive
+// columns of its row = whole 32-byte sectors; fire and forget, no shared-memory patch, no TMA queue), 0 = the round-1
+// path (swizzled patch + cp.async.bulk.tensor store per warp), kept for A/B builds (-DSLDM_TC_DIRECT_STORE=0).
+#ifndef SLDM_TC_DIRECT_STORE
+#define SLDM_TC_DIRECT_STORE 1
+#endif
+#ifndef SLDM_TC_STAGES
+#define SLDM_TC_STAGES (SLDM_TC_DIRECT_STORE ? 8 : 5)
+#endif
+constexpr bool kTcDirectStore = SLDM_TC_DIRECT_STORE != 0;
+constexpr int kTcStages = SLDM_TC_STAGES;   // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
 constexpr int kTcBStages = 2;       // B ring: weight chunks B_hi | B_lo (L2 resident, short latency)
 constexpr int kTcBM = 128;
 constexpr int kTcAcc = 3;          // TMEM accumulator ring (one K chunk each), columns [0, 3*32*NT): look-ahead of the MMA stream
 constexpr int kTcASlots = 2;       // TMEM A slots (own ring, own "free" barriers: shorter than the smem stage ring)
-constexpr int kTcPatchBytes = 16 * 4 * 1024;   // TMA-store patches: 16 epilogue warps x 4 x [32 rows][8 cols]
+constexpr int kTcPatchBytes = kTcDirectStore ? 0 : 16 * 4 * 1024;   // TMA-store patches: 16 epilogue warps x 4 x [32 rows][8 cols]
 constexpr int kTcACol0 = 384;      // TMEM columns of the A ring: kTcASlots x {A_hi[32] | A_lo[32]}
 constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
 
@@ -84,6 +94,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 
 // debug timeline (SLDM_TC_TRACE=<file>): CTA 0 stamps clock64() per role / chunk / event
@@ -224,11 +240,24 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
     //      rows >= N / columns >= Fout. ----
     float* const patch = a.s_stage + ew * (4 * 256);
     const uint32_t prow = smem_u32(patch) + lane * (32 * NT);
-    const uint32_t swz = (NT == 4) ? (uint32_t)(lane & 7) : (NT == 2) ? (uint32_t)((lane >> 1) & 3)
+    [[maybe_unused]] const uint32_t swz = (NT == 4) ? (uint32_t)(lane & 7) : (NT == 2) ? (uint32_t)((lane >> 1) & 3)
                          : (NT == 1) ? (uint32_t)((lane >> 2) & 1) : 0u;
-    const int grow0 = (int)(tile * kTcBM) + q * 32;       // first global row of this warp's sub-tile
-    const bool any_col = FULL || c_lo < Fout;
-    auto push = [&](const CUtensorMap* tm, int ev0) {
+    [[maybe_unused]] const int grow0 = (int)(tile * kTcBM) + q * 32;       // first global row of this warp's sub-tile
+    [[maybe_unused]] const bool any_col = FULL || c_lo < Fout;
+    auto push = [&](const CUtensorMap* tm, float* gbase, int ev0) {
+      if constexpr (kTcDirectStore) {
+        // the thread's 8*NT consecutive columns leave as NT 256-bit stores: every lane writes whole 32-byte sectors
+        // of its own row, nothing is staged and nothing is waited for (the round-1 patch + TMA store spent ~1.0k
+        // cycles per push queueing behind the operand loads and ~0.8k waiting for the patch to be read back)
+        if (tid == 256) TC_TRACE(ev0, it - 1);
+        if (row < a.N) {
+          float* const gp = gbase + row * (int64_t)Fout + c_lo;
+#pragma unroll
+          for (int g8 = 0; g8 < NT; ++g8)
+            if (FULL || c_lo + 8 * g8 < Fout) stg256(gp + 8 * g8, &z[8 * g8]);
+        }
+        if (tid == 256) TC_TRACE(ev0 + 3, it - 1);
+      } else {
       if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading the patch
       __syncwarp();
       if (tid == 256) TC_TRACE(ev0, it - 1);
@@ -244,9 +273,10 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
         tma_store_commit();
       }
       if (tid == 256) TC_TRACE(ev0 + 3, it - 1);
+      }
     };
     if constexpr (MODE == MODE_FWD) {
-      if (a.xhat != nullptr) push(a.tm_o1, 20);
+      if (a.xhat != nullptr) push(a.tm_o1, a.xhat, 20);
 #pragma unroll
       for (int j4 = 0; j4 < HC / 4; ++j4) {
         const float4 g4 = *reinterpret_cast<const float4*>(gam + 4 * j4);
@@ -259,17 +289,17 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs a) {
         }
       }
       if (tid == 256) TC_TRACE(19, it - 1);
-      push(a.tm_o0, 24);
+      push(a.tm_o0, a.out, 24);
     } else {
       if (grp == 0) {
 #pragma unroll
         for (int j = 0; j < HC; ++j) z[j] = __fdiv_rn(z[j], cnt);
       }
-      push(grp == 0 ? a.tm_o0 : a.tm_o1, 24);      // DGRAD: dagg / dxroot
+      push(grp == 0 ? a.tm_o0 : a.tm_o1, grp == 0 ? a.out : a.xhat, 24);      // DGRAD: dagg / dxroot
     }
    }
   }
-  if (lane == 0) tma_store_wait_all<0>();   // all global writes of this warp are complete before the CTA exits
+  if (!kTcDirectStore && lane == 0) tma_store_wait_all<0>();   // all global writes of this warp are complete before the CTA exits
 }
 
 template <int NT, int MODE>  // NT = ceil(Nout / 32) in 1..4
@@ -662,15 +692,17 @@ static bool tc_disabled() {
   return disabled != 0;
 }
 static bool p16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// outputs of the epilogue: 32-byte aligned for the 256-bit stores (row pitch and column offsets are multiples of 32 B)
+static bool pout(const void* p) { return (reinterpret_cast<uintptr_t>(p) & (kTcDirectStore ? 31u : 15u)) == 0; }
 
 bool project_forward_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* agg, const float* x,
                                  const float* out, const float* xhat) {
   return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fin % 32 == 0 && Fin >= 32 && Fout % 16 == 0 &&
-         Fout >= 16 && Fout <= 128 && p16(agg) && p16(x) && p16(out) && p16(xhat);
+         Fout >= 16 && Fout <= 128 && p16(agg) && p16(x) && pout(out) && pout(xhat);
 }
 bool dgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* dagg, const float* dxroot) {
   return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fout % 32 == 0 && Fout >= 32 && Fin % 16 == 0 &&
-         Fin >= 16 && Fin <= 128 && p16(dz) && p16(dagg) && p16(dxroot);
+         Fin >= 16 && Fin <= 128 && p16(dz) && pout(dagg) && pout(dxroot);
 }
 
 int64_t project_forward_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64_t)4 * Fin * Fout * 4); }

@@ -23,7 +23,8 @@ def fused_gru_eligible(gru: torch.nn.GRU, x: torch.Tensor) -> bool:
         and getattr(gru, "proj_size", 0) == 0
         and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
         and x.size(2) == gru.input_size and x.size(1) >= 1
-        and gru.weight_hh_l0.device == x.device and gru.weight_hh_l0.dtype == torch.float32
+        and all(t.device == x.device and t.dtype == torch.float32
+                for t in (gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0))
         and gru.weight_hh_l0.data_ptr() % 16 == 0
         and lib.sldm_gru_supported(int(x.size(1)), int(x.size(2)), int(gru.hidden_size)))
 

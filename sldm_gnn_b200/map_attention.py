@@ -83,18 +83,26 @@ class MapSpatialAttention(nn.Module):
         self.attn_mlp = nn.Sequential(nn.Linear(1, 16), nn.ReLU(), nn.Linear(16, 1))
         self._grid, self._grid_key = None, None
 
-    def _centroid_grid(self, cent):
-        """Uniform grid over the centroids, built on first use and whenever the buffer changes (new tensor, new device,
-        in-place write)."""
-        key = (cent.data_ptr(), cent._version, cent.size(0), cent.device)
-        if self._grid is None or self._grid_key != key:
+    def _centroid_grid(self):
+        """(fp32 contiguous centroids, uniform grid over them): built on first use and whenever the REGISTERED buffer
+        changes (new tensor, new device, in-place write).  The cache is keyed on the buffer itself, not on a converted
+        temporary -- under torch.inference_mode() (test.py:136, rcv.py:80) a temporary is an inference tensor without
+        a version counter and would never match."""
+        buf = self.map_centroids
+        try:
+            version = buf._version
+        except RuntimeError:               # the buffer itself is an inference tensor: rebuild every call
+            version = None
+        key = (buf.data_ptr(), version, buf.size(0), buf.device, buf.dtype)
+        if self._grid is None or version is None or self._grid_key != key:
+            cent = buf.detach().float().contiguous()       # converted once, kept beside the grid
             S, dev = cent.size(0), cent.device
             nbytes = int(lib.sldm_map_grid_bytes(S))
             with torch.cuda.device(dev):
                 grid = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 check(lib.sldm_map_grid_build(_ptr(cent), S, grid.data_ptr(), nbytes, _stream(dev)))
-            self._grid, self._grid_key, self._grid_src = grid, key, cent     # keep `cent` alive: the key holds its address
-        return self._grid
+            self._grid, self._grid_key, self._grid_cent, self._grid_src = grid, key, cent, buf
+        return self._grid_cent, self._grid
 
     def forward(self, vehicle_last_positions, map_embeddings):
         pos, emb, cent = vehicle_last_positions, map_embeddings, self.map_centroids
@@ -108,7 +116,14 @@ class MapSpatialAttention(nn.Module):
         if cent.size(0) < self.k:
             raise RuntimeError("selected index k out of range")      # torch.topk's error
         l1, l2 = self.attn_mlp[0], self.attn_mlp[2]
-        cent = cent.float().contiguous()
-        grid = None if os.environ.get("SLDM_MAP_ATTENTION_SCAN") == "1" else self._centroid_grid(cent)
+        for name, t in (("attn_mlp.0.weight", l1.weight), ("attn_mlp.0.bias", l1.bias), ("attn_mlp.2.weight", l2.weight),
+                        ("attn_mlp.2.bias", l2.bias)):
+            if t.dtype != torch.float32 or t.device != pos.device:     # raw fp32 pointers go to the kernels
+                raise RuntimeError(f"MapSpatialAttention: parameter {name} is {t.dtype} on {t.device}; expected float32 on {pos.device}")
+        if os.environ.get("SLDM_MAP_ATTENTION_SCAN") == "1":
+            cent, grid = cent.float().contiguous(), None
+        else:
+            cent, grid = self._centroid_grid()
         return _MapAttentionFn.apply(pos.float().contiguous(), cent, emb.float().contiguous(),
-                                     l1.weight.reshape(-1), l1.bias, l2.weight.reshape(-1), l2.bias, int(self.k), grid)
+                                     l1.weight.reshape(-1).contiguous(), l1.bias.contiguous(),
+                                     l2.weight.reshape(-1).contiguous(), l2.bias.contiguous(), int(self.k), grid)

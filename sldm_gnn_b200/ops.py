@@ -4,6 +4,10 @@ the tensors' device and never synchronises the host.
 """
 from __future__ import annotations
 
+import collections
+import os
+import threading
+
 import torch
 
 from . import _lib
@@ -35,6 +39,76 @@ def check_edge_index(edge_index) -> None:
         raise ValueError(f"Expected 'edge_index' to be two-dimensional (got {edge_index.dim()} dimensions)")
     if edge_index.size(0) != 2:
         raise ValueError(f"Expected 'edge_index' to have size '2' in the first dimension (got '{edge_index.size(0)}')")
+
+
+class _IndexChecks:
+    """Out-of-range node / graph ids without a host sync on the hot path.
+
+    The reference stack fails on them (CPU: IndexError from index_select / scatter_add_; CUDA: a device-side assert
+    that surfaces at a later synchronisation).  The CSR build clamps such ids so that no kernel leaves its buffers and
+    raises meta[2]; here that flag is copied to pinned host memory behind the build (asynchronously) and looked at
+    when the copy has landed -- at the latest on the next call into this package -- where it raises IndexError, i.e.
+    the error is deferred like a CUDA device assert, never silent.  SLDM_CHECK_INDICES=1 checks synchronously at the
+    build (one host sync per new edge_index), =0 switches the check off.
+    """
+
+    SLOTS = 256
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.pending = collections.deque()
+        self.ring = {}
+
+    @staticmethod
+    def mode() -> str:
+        return os.environ.get("SLDM_CHECK_INDICES", "deferred")
+
+    def watch(self, meta: torch.Tensor, what: str) -> None:
+        mode = self.mode()
+        if mode == "0":
+            return
+        if mode == "1":
+            if int(meta[2]) != 0:
+                raise IndexError(f"{what}: index out of range")
+            return
+        dev = meta.device
+        if torch.cuda.is_current_stream_capturing():
+            return
+        with self.lock:
+            if len(self.pending) >= self.SLOTS - 1:
+                self._drain(block=True)
+            ring = self.ring.get(dev)
+            if ring is None:
+                ring = self.ring[dev] = [torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory(), 0]
+            slot = ring[0][ring[1] % self.SLOTS: ring[1] % self.SLOTS + 1]
+            ring[1] += 1
+            slot.copy_(meta[2:3], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self.pending.append((ev, slot, what))
+
+    def _drain(self, block: bool) -> None:
+        bad = None
+        while self.pending:
+            ev, slot, what = self.pending[0]
+            if not block and not ev.query():
+                break
+            ev.synchronize()
+            self.pending.popleft()
+            if int(slot[0]) != 0 and bad is None:
+                bad = what
+        if bad is not None:
+            raise IndexError(f"{bad}: index out of range (reported by an earlier device-side CSR build; "
+                             "SLDM_CHECK_INDICES=1 raises at the call that passed it)")
+
+    def poll(self, block: bool = False) -> None:
+        if not self.pending:
+            return
+        with self.lock:
+            self._drain(block)
+
+
+index_checks = _IndexChecks()
 
 
 class Csr:
@@ -70,6 +144,7 @@ class Csr:
 def build_csr(edge_index: torch.Tensor, num_nodes: int) -> Csr:
     check_edge_index(edge_index)
     _require_cuda(edge_index, "edge_index")
+    index_checks.poll()
     ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
     E = int(ei.size(1))
     N = int(num_nodes)
@@ -81,7 +156,10 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int) -> Csr:
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if E > 0 else None
         check(lib.sldm_csr_build(_ptr(ei) if E > 0 else None, E, N, buf.data_ptr(), _ptr(ws), wsb if E > 0 else 0,
                                  _stream(dev)))
-    return Csr(buf, N, E, layout)
+        csr = Csr(buf, N, E, layout)
+        if E > 0:
+            index_checks.watch(csr.meta, f"edge_index (num_nodes = {N})")
+    return csr
 
 
 def segment_reduce(src: torch.Tensor, csr: Csr, *, transpose: bool = False, mean: bool = True,
@@ -137,31 +215,38 @@ def layer_forward(x, csr: Csr, W_l, b_l, W_r, ln_w, ln_b, eps: float, slope: flo
     return out, agg, xhat, rstd
 
 
-def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slope: float, need_dx: bool):
-    """Returns (dx | None, dW_l, db_l, dW_r, dln_w, dln_b)."""
+def backward_buffers(N: int, Fin: int, Fout: int, E: int, dev, need_dx: bool) -> dict:
+    """Outputs, scratch and workspace of one layer_backward call."""
+    with torch.cuda.device(dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        b = dict(dW_l=torch.empty((Fout, Fin), **f32), dW_r=torch.empty((Fout, Fin), **f32),
+                 db_l=torch.empty((Fout,), **f32), dln_w=torch.empty((Fout,), **f32), dln_b=torch.empty((Fout,), **f32),
+                 dz=torch.empty((N, Fout), **f32), dx=None, dagg=None, dxroot=None)
+        if need_dx:
+            b.update(dx=torch.empty((N, Fin), **f32), dagg=torch.empty((N, Fin), **f32),
+                     dxroot=torch.empty((N, Fin), **f32))
+        wsb = int(lib.sldm_sage_layer_bwd_workspace_bytes(N, E, Fin, Fout))
+        b["wsb"] = wsb
+        b["ws"] = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    return b
+
+
+def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slope: float, need_dx: bool,
+                   stages: int = _lib.BWD_STAGE_ALL, bufs: dict | None = None):
+    """Returns (dx | None, dW_l, db_l, dW_r, dln_w, dln_b).
+
+    `stages` / `bufs` are for profiling (bench.py): launch only the masked kernels on the buffers of an earlier
+    full call (include/sldm_sage.h, SLDM_BWD_STAGE_*)."""
     N, Fin = x.shape
     Fout = W_l.shape[0]
     dev = x.device
     dout = dout.contiguous()
+    b = bufs if bufs is not None else backward_buffers(N, Fin, Fout, csr.E, dev, need_dx)
     with torch.cuda.device(dev):
-        f32 = dict(dtype=torch.float32, device=dev)
-        dW_l = torch.empty((Fout, Fin), **f32)
-        dW_r = torch.empty((Fout, Fin), **f32)
-        db_l = torch.empty((Fout,), **f32)
-        dln_w = torch.empty((Fout,), **f32)
-        dln_b = torch.empty((Fout,), **f32)
-        dz = torch.empty((N, Fout), **f32)
-        dx = dagg = dxroot = None
-        if need_dx:
-            dx = torch.empty((N, Fin), **f32)
-            dagg = torch.empty((N, Fin), **f32)
-            dxroot = torch.empty((N, Fin), **f32)
-        wsb = int(lib.sldm_sage_layer_bwd_workspace_bytes(N, csr.E, Fin, Fout))
-        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
-        check(lib.sldm_sage_layer_backward(dout.data_ptr(), x.data_ptr(), agg.data_ptr(), xhat.data_ptr(),
-                                           rstd.data_ptr(), N, Fin, Fout, csr.buf.data_ptr(), csr.E,
-                                           W_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
-                                           float(slope), _ptr(dx), dW_l.data_ptr(), db_l.data_ptr(),
-                                           dW_r.data_ptr(), dln_w.data_ptr(), dln_b.data_ptr(),
-                                           dz.data_ptr(), _ptr(dagg), _ptr(dxroot), ws.data_ptr(), wsb, _stream(dev)))
-    return dx, dW_l, db_l, dW_r, dln_w, dln_b
+        check(lib.sldm_sage_layer_backward_stages(
+            dout.data_ptr(), x.data_ptr(), agg.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), N, Fin, Fout,
+            csr.buf.data_ptr(), csr.E, W_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), float(slope),
+            _ptr(b["dx"]), b["dW_l"].data_ptr(), b["db_l"].data_ptr(), b["dW_r"].data_ptr(), b["dln_w"].data_ptr(),
+            b["dln_b"].data_ptr(), b["dz"].data_ptr(), _ptr(b["dagg"]), _ptr(b["dxroot"]), b["ws"].data_ptr(), b["wsb"],
+            _stream(dev), int(stages)))
+    return b["dx"], b["dW_l"], b["db_l"], b["dW_r"], b["dln_w"], b["dln_b"]

@@ -14,7 +14,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import lib, check
-from .ops import Csr, _ptr, _require_cuda, _stream
+from .ops import Csr, _ptr, _require_cuda, _stream, index_checks
 
 
 def _membership_csr(batch: torch.Tensor, N: int, G: int) -> Csr:
@@ -31,9 +31,13 @@ def _membership_csr(batch: torch.Tensor, N: int, G: int) -> Csr:
         buf = torch.empty(layout["total"], dtype=torch.int32, device=dev)
         wsb = int(lib.sldm_csr_workspace_bytes(nodes, N))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if N > 0 else None
+        index_checks.poll()
         check(lib.sldm_csr_build_pairs(None, batch.data_ptr() if N > 0 else None, N, nodes, buf.data_ptr(), _ptr(ws),
                                        wsb if N > 0 else 0, _stream(dev)))
-    return Csr(buf, nodes, N, layout)
+        csr = Csr(buf, nodes, N, layout)
+        if N > 0:
+            index_checks.watch(csr.meta, f"batch vector (num_graphs = {G})")
+    return csr
 
 
 class _ReadoutFn(torch.autograd.Function):

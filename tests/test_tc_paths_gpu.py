@@ -15,7 +15,7 @@ SCRIPT = r"""
 import sys, torch
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 import sldm_gnn_b200 as sg
-from sldm_gnn_b200.synth import unit_map_graphs
+from workloads import unit_map_graphs
 from test_gpu_parity import run_pair, check_pair
 dev = torch.device('cuda:0')
 for hdims, slope in (([128, 128, 128], 0.1), ([64, 96, 32], None), ([32, 16, 48], 0.2), ([96, 128], 0.1)):
@@ -47,7 +47,7 @@ def test_tc_kernels_are_in_the_library():
 GATHER_SCRIPT = r"""
 import hashlib, torch
 import sldm_gnn_b200 as sg
-from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+from workloads import unit_map_graphs, skewed_graph
 dev = torch.device("cuda:0")
 out = []
 for kind, F in (("batch", 128), ("batch", 96), ("batch", 64), ("batch", 32), ("batch", 16), ("skew", 128), ("skew", 40)):

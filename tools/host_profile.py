@@ -3,7 +3,7 @@ import sys, os, cProfile, pstats
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import sldm_gnn_b200 as sg
-from sldm_gnn_b200.synth import unit_map_graphs
+from workloads import unit_map_graphs
 dev = torch.device("cuda:0")
 ei, _, N = unit_map_graphs(32, seed=0)
 ei = ei.to(dev)
@@ -31,7 +31,7 @@ pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("tottime").print_stats(18)
 
 # ---- collate: ours vs a torch.cat restatement on the device (what PyG's collate launches) -------------------------
-from sldm_gnn_b200.synth import unit_map_graphs as _umg
+from workloads import unit_map_graphs as _umg
 items = []
 for g in range(32):
     eg, _, ng = _umg(1, seed=100 + g)

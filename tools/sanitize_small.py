@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import sldm_gnn_b200 as sg
-from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+from workloads import unit_map_graphs, skewed_graph
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)

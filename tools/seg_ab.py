@@ -4,7 +4,7 @@ import sys, os, hashlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import sldm_gnn_b200 as sg
-from sldm_gnn_b200.synth import unit_map_graphs, skewed_graph
+from workloads import unit_map_graphs, skewed_graph
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "batch"
 F = int(sys.argv[2]) if len(sys.argv) > 2 else 128

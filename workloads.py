@@ -1,4 +1,6 @@
-"""Seeded synthetic workloads of SURVEY 8(d) -- shared by tests and bench.py.
+"""Seeded synthetic workloads of SURVEY 8(d) -- shared by tests, tools and bench.py (both arms).
+
+Lives outside the package on purpose: the reference arm of bench.py imports it without loading libsldm_sage.so.
 
 Plain torch on the CPU (inputs are generated on the host and copied, as the
 reference's DataLoader would deliver them)."""
