@@ -13,7 +13,7 @@
 // fp64 (tools/tc_probe2.cu, K=128): max 3.2e-7 / rms 7.3e-8 versus 7.8e-7 / 1.1e-7 for a
 // sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
 //
-// Pipeline (one persistent CTA per SM, 768 threads, 128 rows x Fout per tile; setmaxnreg 40 / 72 / 88 of the 80 x 768 pool):
+// Pipeline (one persistent CTA per SM, 896 threads = 7 warpgroups, 128 rows x Fout per tile; setmaxnreg 40 / 72 / 80 / 64):
 //   warp 0        TMA producer A: raw activation chunks [128 x 32] (agg, then x) into a 5-deep ring -- the HBM stream;
 //                                a stage is handed back by the CONVERTER as soon as the tile is in registers
 //   warp 2        TMA producer B: pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk into a 2-deep ring (L2 hits)
@@ -23,41 +23,36 @@
 //                                take A from TMEM, so shared memory only carries the raw tile once and the weights
 //   warps 1, 3    MMA issuers  : alternate K chunks; 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8), A from TMEM, B
 //                                from smem descriptors, into one of three TMEM accumulators; tcgen05.commit frees the
-//                                weight stage and the TMEM A slot and signals the epilogue
-//   warps 8-23    epilogue     : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add into
-//                                registers; after the last chunk: + bias, LayerNorm (one exchange of per-quarter
-//                                (sum, M2) through smem, Chan's merge), xhat out, (Leaky)ReLU, out -- through
-//                                swizzled full-row patches and cp.async.bulk.tensor stores
+//                                weight stage and the TMEM A slot and signals the drain
+//   warps 8-23    drain        : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add into
+//                                registers (round-to-nearest); after the last chunk of a tile the raw sums are parked in
+//                                a swizzled shared-memory tile [128 x Fout] and the warp goes straight on to the next
+//                                tile's chunks: its tail is ~0.3k cycles, the MMA stream never waits for it
+//   warps 24-27   finisher     : one warp per 32-row quadrant of the parked tile, LANE = 4 CONSECUTIVE COLUMNS: + bias,
+//                                LayerNorm (two-pass mean / variance by warp shuffles), xhat out, (Leaky)ReLU, out --
+//                                every store instruction writes whole 512-byte rows (DGRAD: / max(deg,1), dagg | dxroot)
 // Tensor memory (512 columns): three accumulators [0, 384), two A slots [384, 512).
-// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  Measured (profiles/r01c traces): 14.7k cycles per
-// 128-row tile against an HBM floor of 11.4k: 6.8k epilogue tail (statistics 1.9k, two TMA pushes that queue behind the
-// operand loads) during which the MMA stream can only run three accumulators ahead, then a drain paced by the
-// MMA -> free TMEM slot -> converter -> MMA chain (~1.25k cycles per chunk).  Tensor memory is the binding resource:
-// 2 accumulators + 4 slots, 3 + 2 (this), and an SS-mode variant with 4 accumulators all land within 4% of 0.40 ms.
+// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  History (profiles/r01c traces): with the epilogue
+// warps doing statistics and stores themselves a tile took 14.7k cycles against an HBM floor of 11.4k: a 6.4k-cycle tail
+// (statistics 1.9k, two TMA-store pushes that queued ~1.0k each behind the operand loads in the TMA engine and waited
+// 0.8k for the patch to be read back) during which the MMA stream could only run three accumulators ahead.  Round 2:
+// (a) 256-bit st.global straight from the accumulator registers (lane = row, 32 B per lane) was SLOWER (0.507 vs
+// 0.398 ms: 32 rows x 32 B per instruction are partial-line writes); (b) the finisher above: the tail leaves the
+// drain warps, stores are full-line and never touch the TMA engine.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace sldm {
 using namespace tc;
 
-constexpr int kTcThreads = 768;   // 6 warpgroups: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 4
+constexpr int kTcThreads = 896;   // 7 warpgroups: {TMA, MMA, alloc+TMA B, MMA} {converter x4} {drain x4} x 4 {finisher x4}
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
-// Epilogue stores: 1 = 256-bit st.global straight from the accumulator registers (a thread owns 8*NT consecutive
-// columns of its row = whole 32-byte sectors; fire and forget, no shared-memory patch, no TMA queue), 0 = the round-1
-// path (swizzled patch + cp.async.bulk.tensor store per warp), kept for A/B builds (-DSLDM_TC_DIRECT_STORE=0).
-#ifndef SLDM_TC_DIRECT_STORE
-#define SLDM_TC_DIRECT_STORE 1
-#endif
-#ifndef SLDM_TC_STAGES
-#define SLDM_TC_STAGES (SLDM_TC_DIRECT_STORE ? 8 : 5)
-#endif
-constexpr bool kTcDirectStore = SLDM_TC_DIRECT_STORE != 0;
-constexpr int kTcStages = SLDM_TC_STAGES;   // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
+constexpr int kTcStages = 5;        // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
 constexpr int kTcBStages = 2;       // B ring: weight chunks B_hi | B_lo (L2 resident, short latency)
 constexpr int kTcBM = 128;
 constexpr int kTcAcc = 3;          // TMEM accumulator ring (one K chunk each), columns [0, 3*32*NT): look-ahead of the MMA stream
 constexpr int kTcASlots = 2;       // TMEM A slots (own ring, own "free" barriers: shorter than the smem stage ring)
-constexpr int kTcPatchBytes = kTcDirectStore ? 0 : 16 * 4 * 1024;   // TMA-store patches: 16 epilogue warps x 4 x [32 rows][8 cols]
+constexpr int kTcZBytes = kTcBM * 128 * 4;     // hand-off tile drain -> finisher: [128 rows][<= 128 fp32], chunk-swizzled
 constexpr int kTcACol0 = 384;      // TMEM columns of the A ring: kTcASlots x {A_hi[32] | A_lo[32]}
 constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
 
@@ -96,217 +91,200 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane
-__device__ __forceinline__ void stg256(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-}
-
 // debug timeline (SLDM_TC_TRACE=<file>): CTA 0 stamps clock64() per role / chunk / event
 constexpr int kTraceIts = 96, kTraceEv = 32;
 #define TC_TRACE(ev, itv) \
   do { if (trace != nullptr && blockIdx.x == 0 && (itv) < kTraceIts) trace[(itv) * kTraceEv + (ev)] = clock64(); } while (0)
 
-struct EpiArgs {
-  int64_t N; int Fout; int64_t ntiles; int nchunks; int ngroups; float eps, slope;
-  float* out; float* xhat; float* rstd; const int32_t* rowptr; uint32_t tmem_base;
-  uint64_t* bar_acc_full; uint64_t* bar_acc_empty;
-  const float* s_bias; const float* s_gamma; const float* s_beta;
-  float* s_sum; float* s_var; float* s_stage; long long* trace;
-  const CUtensorMap* tm_o0; const CUtensorMap* tm_o1;   // TMA store maps: FWD out / xhat, DGRAD dagg / dxroot
-};
-
-// Epilogue role: 16 warps (512 threads).  Thread (quadrant q, lane, column quarter CQ) owns tile row q*32+lane and the
-// columns [CQ*8*NT, (CQ+1)*8*NT).  The role is latency bound per warp (TMEM round trips, smem parameter reads, store
-// fences), so it is spread over many warps.  FULL = (Fout == 32*NT): no column masking needed.
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
-template <int NT, bool FULL, int MODE>
-__device__ __forceinline__ void epilogue_role(const EpiArgs a) {
+// Hand-off tile in shared memory: row r (0..127) has 8*NT 16-byte chunks; chunk j sits at position j ^ (r & 7) of its
+// row (XOR on the low three bits).  Drain writes (8 lanes of a quarter warp = 8 consecutive rows, same j) and finisher
+// reads (the lanes of a row = consecutive j) both touch every bank group exactly once per phase.
+template <int NT>
+__device__ __forceinline__ uint32_t z_chunk_addr(uint32_t zbase, int r, int j) {
+  return zbase + (uint32_t)r * (128u * NT) + ((uint32_t)(j ^ (r & 7)) << 4);
+}
+
+struct DrainArgs {
+  int64_t ntiles; int nchunks; int ngroups; uint32_t tmem_base; uint32_t zbase;
+  uint64_t* bar_acc_full; uint64_t* bar_acc_empty; uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
+};
+
+// Drain role: 16 warps (512 threads).  Thread (quadrant q, lane, column quarter CQ) owns tile row q*32+lane and the
+// columns [CQ*8*NT, (CQ+1)*8*NT): one tcgen05.ld round trip per K chunk, fp32 register accumulation.
+template <int NT>
+__device__ __forceinline__ void drain_role(const DrainArgs a) {
   constexpr int HC = 8 * NT;               // columns per thread
   constexpr int ACC_COLS = 32 * NT;
   long long* trace = a.trace;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3;                  // TMEM lane quadrant of this warp
   const int rloc = q * 32 + lane;
-  const int ew = warp - 8;                 // 0..15
-  const int cq = ew >> 2;                  // column quarter
-  const int c_lo = cq * HC;
-  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + c_lo;
-  const float fF = (float)a.Fout;
-  const int Fout = a.Fout;
-  const float* const bias = a.s_bias + c_lo;
-  const float* const gam = a.s_gamma + c_lo;
-  const float* const bet = a.s_beta + c_lo;
-  uint32_t it = 0, tcount = 0;
-  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
-   for (int grp = 0; grp < a.ngroups; ++grp) {
-    float z[HC];
-    for (int c = 0; c < a.nchunks; ++c, ++it) {
-      const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
-      if (tid == 256) TC_TRACE(8, it);
-      mbar_wait(&a.bar_acc_full[ab], aph);
-      if (tid == 256) TC_TRACE(9, it);
-      tc_fence_after();
-      uint32_t rr[NT][8];
+  const int cq = (warp - 8) >> 2;          // column quarter
+  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + cq * HC;
+  uint32_t it = 0, hand = 0;
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int grp = 0; grp < a.ngroups; ++grp, ++hand) {
+      float z[HC];
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
+        if (tid == 256) TC_TRACE(8, it);
+        mbar_wait(&a.bar_acc_full[ab], aph);
+        if (tid == 256) TC_TRACE(9, it);
+        tc_fence_after();
+        uint32_t rr[NT][8];
 #pragma unroll
-      for (int g0 = 0; g0 < NT; ++g0) tmem_ld_32x8(tq + ab * ACC_COLS + g0 * 8, rr[g0]);
-      tmem_ld_wait();
-      tc_fence_before();                   // values are in registers: release the accumulator
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a.bar_acc_empty[ab]);
-      if (tid == 256) TC_TRACE(10, it);
-      if (c == 0) {
+        for (int g0 = 0; g0 < NT; ++g0) tmem_ld_32x8(tq + ab * ACC_COLS + g0 * 8, rr[g0]);
+        tmem_ld_wait();
+        tc_fence_before();                   // values are in registers: release the accumulator
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a.bar_acc_empty[ab]);
+        if (tid == 256) TC_TRACE(10, it);
+        if (c == 0) {
 #pragma unroll
-        for (int g0 = 0; g0 < NT; ++g0)
+          for (int g0 = 0; g0 < NT; ++g0)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[g0 * 8 + j] = __uint_as_float(rr[g0][j]);
-      } else {
+            for (int j = 0; j < 8; ++j) z[g0 * 8 + j] = __uint_as_float(rr[g0][j]);
+        } else {
 #pragma unroll
-        for (int g0 = 0; g0 < NT; ++g0)
+          for (int g0 = 0; g0 < NT; ++g0)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[g0 * 8 + j] += __uint_as_float(rr[g0][j]);
-      }
-    }
-    if (tid == 256) TC_TRACE(11, it - 1);
-    const int64_t row = tile * kTcBM + rloc;
-    float rs = 1.f;            // FWD: rstd of the row;  DGRAD: unused
-    float cnt = 1.f;           // DGRAD group 0: max(deg,1)
-    if constexpr (MODE == MODE_FWD) {
-      // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q.
-      //      Each quarter computes its own (sum, M2 about its own mean); ONE exchange through smem on a 128-thread
-      //      named barrier and Chan's merge give the row mean and variance:
-      //         M2 = sum_q M2_q + sum_q n_q (m_q - mean)^2        (two-pass accuracy, one barrier instead of two)
-      //      Sums run as four interleaved chains. ----
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j4 = 0; j4 < HC / 4; ++j4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j4);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 4 * j4 + e;
-          z[j] += bb[e];
-          ps[e] += (FULL || c_lo + j < Fout) ? z[j] : 0.f;
+            for (int j = 0; j < 8; ++j) z[g0 * 8 + j] += __uint_as_float(rr[g0][j]);
         }
       }
-      const int nq_i = FULL ? HC : max(0, min(HC, Fout - c_lo));     // valid columns of this quarter
-      const float nq = (float)nq_i;
-      const float sq = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-      const float mq = nq_i > 0 ? __fdiv_rn(sq, nq) : 0.f;
-      float pv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < HC; ++j) {
-        const float d = z[j] - mq;
-        pv[j & 3] += (FULL || c_lo + j < Fout) ? d * d : 0.f;
-      }
-      // buffers alternate per tile: a warp can only be one barrier ahead of its three partners, so the values of
-      // tile t are never overwritten (by tile t+2) before everybody has read them
-      float* const sS = a.s_sum + (tcount & 1) * 512;
-      float* const sV = a.s_var + (tcount & 1) * 512;
-      sS[cq * 128 + rloc] = sq;
-      sV[cq * 128 + rloc] = (pv[0] + pv[1]) + (pv[2] + pv[3]);
-      named_bar_sync(2 + q, 128);
-      float s4[4], m2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) s4[k] = sS[k * 128 + rloc];
-      const float mean = __fdiv_rn((s4[0] + s4[1]) + (s4[2] + s4[3]), fF);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int nk_i = FULL ? HC : max(0, min(HC, Fout - k * HC));
-        const float nk = (float)nk_i;
-        const float dm = (nk_i > 0 ? __fdiv_rn(s4[k], nk) : mean) - mean;
-        m2 += sV[k * 128 + rloc] + nk * dm * dm;
-      }
-      rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(m2, fF) + a.eps));
-#pragma unroll
-      for (int j = 0; j < HC; ++j) z[j] = (z[j] - mean) * rs;      // z now holds xhat
-      if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
-      if (tid == 256) TC_TRACE(14, it - 1);
-    } else {
-      if (grp == 0 && row < a.N) {
-        int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
-        deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
-        cnt = (float)deg;
-      }
-    }
-    // ---- stores.  Each warp owns a [32 rows x 8*NT columns] sub-tile and pushes it out through ONE private patch
-    //      ([32 rows][8*NT cols], rows of 32*NT bytes, TMA-swizzled so that the 128-bit writes of a quarter warp hit
-    //      distinct banks) with a single cp.async.bulk.tensor store: full 128-byte rows at NT = 4.  (Narrow 32-byte
-    //      boxes made the TMA engine the bottleneck: 4x the requests, 1.9k cycles to issue them; plain coalesced
-    //      global stores read back from the patch were slower still -- traces in profiles/r01c.)  FWD stores xhat
-    //      first and computes the activation in place while the engine drains the patch; the engine clips
-    //      rows >= N / columns >= Fout. ----
-    float* const patch = a.s_stage + ew * (4 * 256);
-    const uint32_t prow = smem_u32(patch) + lane * (32 * NT);
-    [[maybe_unused]] const uint32_t swz = (NT == 4) ? (uint32_t)(lane & 7) : (NT == 2) ? (uint32_t)((lane >> 1) & 3)
-                         : (NT == 1) ? (uint32_t)((lane >> 2) & 1) : 0u;
-    [[maybe_unused]] const int grow0 = (int)(tile * kTcBM) + q * 32;       // first global row of this warp's sub-tile
-    [[maybe_unused]] const bool any_col = FULL || c_lo < Fout;
-    auto push = [&](const CUtensorMap* tm, float* gbase, int ev0) {
-      if constexpr (kTcDirectStore) {
-        // the thread's 8*NT consecutive columns leave as NT 256-bit stores: every lane writes whole 32-byte sectors
-        // of its own row, nothing is staged and nothing is waited for (the round-1 patch + TMA store spent ~1.0k
-        // cycles per push queueing behind the operand loads and ~0.8k waiting for the patch to be read back)
-        if (tid == 256) TC_TRACE(ev0, it - 1);
-        if (row < a.N) {
-          float* const gp = gbase + row * (int64_t)Fout + c_lo;
-#pragma unroll
-          for (int g8 = 0; g8 < NT; ++g8)
-            if (FULL || c_lo + 8 * g8 < Fout) stg256(gp + 8 * g8, &z[8 * g8]);
-        }
-        if (tid == 256) TC_TRACE(ev0 + 3, it - 1);
-      } else {
-      if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading the patch
-      __syncwarp();
-      if (tid == 256) TC_TRACE(ev0, it - 1);
+      // ---- park the finished sums for the finisher warp of this quadrant and move on
+      if (tid == 256) TC_TRACE(11, it - 1);
+      mbar_wait(&a.bar_z_empty[q], (hand & 1) ^ 1);      // the previous tile of this quadrant has been read
+      if (tid == 256) TC_TRACE(12, it - 1);
 #pragma unroll
       for (int c = 0; c < 2 * NT; ++c)
-        sts128(prow + (((uint32_t)c ^ swz) << 4), make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
-      if (tid == 256) TC_TRACE(ev0 + 1, it - 1);
-      fence_proxy_async_smem();
+        sts128(z_chunk_addr<NT>(a.zbase, rloc, cq * 2 * NT + c), make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
       __syncwarp();
-      if (tid == 256) TC_TRACE(ev0 + 2, it - 1);
-      if (lane == 0 && any_col) {
-        tma_store_2d(tm, patch, c_lo, grow0);
-        tma_store_commit();
-      }
-      if (tid == 256) TC_TRACE(ev0 + 3, it - 1);
-      }
-    };
-    if constexpr (MODE == MODE_FWD) {
-      if (a.xhat != nullptr) push(a.tm_o1, a.xhat, 20);
+      if (lane == 0) mbar_arrive(&a.bar_z_full[q]);       // release: the finisher's wait acquires these writes
+      if (tid == 256) TC_TRACE(13, it - 1);
+    }
+  }
+}
+
+struct FinArgs {
+  int64_t N; int Fout; int64_t ntiles; int ngroups; float eps, slope;
+  float* out; float* xhat; float* rstd; const int32_t* rowptr; uint32_t zbase;
+  const float* bias; const float* gamma; const float* beta;       // global pointers (FWD)
+  uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
+};
+
+// Finisher role: 4 warps, warp q owns rows [32q, 32q+32) of the parked tile.  A row is spread over LPRW = 8*NT lanes
+// (lane = 4 consecutive columns), RPI = 32 / LPRW rows per instruction (NT = 3: 24 of 32 lanes active), U of them in
+// flight so that the shuffle chains of the LayerNorm overlap.
+template <int NT, int MODE>
+__device__ __forceinline__ void finisher_role(const FinArgs a) {
+  constexpr int LPRW = (NT == 1) ? 8 : (NT == 2) ? 16 : 32;
+  constexpr int RPI = 32 / LPRW;
+  constexpr int U = 4;
+  long long* trace = a.trace;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int q = (tid >> 5) & 3;
+  const int lig = lane % LPRW, sub = lane / LPRW;
+  const int Fout = a.Fout;
+  const int c0 = 4 * lig;
+  const bool cvalid = c0 < Fout;                      // Fout % 4 == 0: a lane's four columns are valid together
+  const float fF = (float)Fout;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gam4 = bias4, bet4 = bias4;
+  if (MODE == MODE_FWD && cvalid) {
+    bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0));
+    gam4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
+    bet4 = __ldg(reinterpret_cast<const float4*>(a.beta + c0));
+  }
+  uint32_t hand = 0;
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int grp = 0; grp < a.ngroups; ++grp, ++hand) {
+      if (tid == 768) TC_TRACE(16, hand);
+      mbar_wait(&a.bar_z_full[q], hand & 1);
+      if (tid == 768) TC_TRACE(17, hand);
+      float* const o_main = (MODE == MODE_FWD) ? a.out : (grp == 0 ? a.out : a.xhat);   // DGRAD: dagg | dxroot
+#pragma unroll 1
+      for (int i = 0; i < 32; i += U * RPI) {
+        float4 v[U];
+        int rl[U];
 #pragma unroll
-      for (int j4 = 0; j4 < HC / 4; ++j4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(gam + 4 * j4);
-        const float4 b4 = *reinterpret_cast<const float4*>(bet + 4 * j4);
-        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int u = 0; u < U; ++u) {
+          rl[u] = q * 32 + i + u * RPI + sub;
+          v[u] = cvalid ? lds128(z_chunk_addr<NT>(a.zbase, rl[u], lig)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (i + U * RPI >= 32) {
+          // last rows of the quadrant are in registers: hand the tile back (the loads must have RETURNED first)
+          float guard = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float y = fmaf(z[4 * j4 + e], gg[e], bb[e]);
-          z[4 * j4 + e] = y > 0.f ? y : a.slope * y;
+          for (int u = 0; u < U; ++u) guard += v[u].x;
+          asm volatile("" ::"f"(guard) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a.bar_z_empty[q]);
+        }
+        if constexpr (MODE == MODE_FWD) {
+          float s[U], m2[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            v[u].x += bias4.x; v[u].y += bias4.y; v[u].z += bias4.z; v[u].w += bias4.w;
+            s[u] = cvalid ? (v[u].x + v[u].y) + (v[u].z + v[u].w) : 0.f;
+          }
+#pragma unroll
+          for (int o = LPRW / 2; o >= 1; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float mean = __fdiv_rn(s[u], fF);
+            v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
+            m2[u] = cvalid ? (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w) : 0.f;
+          }
+#pragma unroll
+          for (int o = LPRW / 2; o >= 1; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) m2[u] += __shfl_xor_sync(0xffffffffu, m2[u], o);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(m2[u], fF) + a.eps));
+            const int64_t row = tile * kTcBM + rl[u];
+            if (row < a.N && cvalid) {
+              float4 xh = make_float4(v[u].x * rs, v[u].y * rs, v[u].z * rs, v[u].w * rs);
+              if (a.xhat != nullptr) *reinterpret_cast<float4*>(a.xhat + row * Fout + c0) = xh;
+              if (a.rstd != nullptr && lig == 0) a.rstd[row] = rs;
+              float4 y;
+              y.x = fmaf(xh.x, gam4.x, bet4.x); y.y = fmaf(xh.y, gam4.y, bet4.y);
+              y.z = fmaf(xh.z, gam4.z, bet4.z); y.w = fmaf(xh.w, gam4.w, bet4.w);
+              y.x = y.x > 0.f ? y.x : a.slope * y.x; y.y = y.y > 0.f ? y.y : a.slope * y.y;
+              y.z = y.z > 0.f ? y.z : a.slope * y.z; y.w = y.w > 0.f ? y.w : a.slope * y.w;
+              *reinterpret_cast<float4*>(o_main + row * Fout + c0) = y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t row = tile * kTcBM + rl[u];
+            if (row < a.N && cvalid) {
+              if (grp == 0) {
+                int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+                deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
+                const float cnt = (float)deg;
+                v[u].x = __fdiv_rn(v[u].x, cnt); v[u].y = __fdiv_rn(v[u].y, cnt);
+                v[u].z = __fdiv_rn(v[u].z, cnt); v[u].w = __fdiv_rn(v[u].w, cnt);
+              }
+              *reinterpret_cast<float4*>(o_main + row * Fout + c0) = v[u];
+            }
+          }
         }
       }
-      if (tid == 256) TC_TRACE(19, it - 1);
-      push(a.tm_o0, a.out, 24);
-    } else {
-      if (grp == 0) {
-#pragma unroll
-        for (int j = 0; j < HC; ++j) z[j] = __fdiv_rn(z[j], cnt);
-      }
-      push(grp == 0 ? a.tm_o0 : a.tm_o1, grp == 0 ? a.out : a.xhat, 24);      // DGRAD: dagg / dxroot
+      if (tid == 768) TC_TRACE(18, hand);
     }
-   }
   }
-  if (!kTcDirectStore && lane == 0) tma_store_wait_all<0>();   // all global writes of this warp are complete before the CTA exits
 }
 
 template <int NT, int MODE>  // NT = ceil(Nout / 32) in 1..4
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CUtensorMap tm_x,
-          const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_o0,
-          const __grid_constant__ CUtensorMap tm_o1, const TcProblem pb,
+          const __grid_constant__ CUtensorMap tm_w, const TcProblem pb,
           const float* __restrict__ b_l, const float* __restrict__ gamma,
           const float* __restrict__ beta, float eps, float slope,
           float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
@@ -319,16 +297,15 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   __shared__ uint64_t bar_bfull[kTcBStages], bar_bempty[kTcBStages];   // B ring: TMA -> MMA -> TMA
   __shared__ uint64_t bar_conv[kTcASlots], bar_afree[kTcASlots];       // TMEM A slots: converter -> MMA -> converter
   __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
+  __shared__ uint64_t bar_z_full[4], bar_z_empty[4];                   // hand-off tile, per 32-row quadrant: drain -> finisher -> drain
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float s_bias[128], s_gamma[128], s_beta[128];
-  __shared__ float s_sum[2][4][128], s_var[2][4][128];   // double buffered by tile parity (one barrier per tile)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
   const uint32_t b_bytes = (uint32_t)Fout * 128;
-  // shared memory: A ring (kTcStages raw tiles) | B ring (kTcBStages x {B_hi, B_lo}) | epilogue patches
+  // shared memory: A ring (kTcStages raw tiles) | B ring (kTcBStages x {B_hi, B_lo}) | hand-off tile [128 x 32*NT]
   uint8_t* const smem_b = smem + (size_t)kTcStages * a_bytes;
-  uint8_t* const smem_patch = smem_b + (size_t)kTcBStages * 2 * b_bytes;
+  uint8_t* const smem_z = smem_b + (size_t)kTcBStages * 2 * b_bytes;
   constexpr int ACC_COLS = 32 * NT;
   constexpr uint32_t TMEM_COLS = 512;                   // accumulators [0, 384) + A slots [384, 512)
   static_assert(kTcAcc * 128 <= kTcACol0 && kTcACol0 + 64 * kTcASlots <= 512, "TMEM budget");
@@ -338,12 +315,6 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   const int ngroups = pb.ngroups;
   const int64_t ntiles = (N + kTcBM - 1) / kTcBM;
 
-  if (MODE == MODE_FWD && tid < 128) {
-    const bool cv = tid < Fout;
-    s_bias[tid] = cv ? b_l[tid] : 0.f;
-    s_gamma[tid] = cv ? gamma[tid] : 0.f;
-    s_beta[tid] = cv ? beta[tid] : 0.f;
-  }
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -358,6 +329,10 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     for (int a = 0; a < kTcAcc; ++a) {
       mbar_init(&bar_acc_full[a], 1);
       mbar_init(&bar_acc_empty[a], 16);
+    }
+    for (int qd = 0; qd < 4; ++qd) {
+      mbar_init(&bar_z_full[qd], 4);     // the four column-quarter drain warps of the quadrant
+      mbar_init(&bar_z_empty[qd], 1);    // its finisher warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&tm_agg);
@@ -513,14 +488,18 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
         if (tid == 128) TC_TRACE(7, it);
       }
     }
+  } else if (warp < 24) {
+    reg_inc<80>();
+    // ------------------------------------------------------------------- drain --
+    DrainArgs da{ntiles, nchunks, ngroups, tmem_base, smem_u32(smem_z), bar_acc_full, bar_acc_empty, bar_z_full,
+                 bar_z_empty, trace};
+    drain_role<NT>(da);
   } else {
-    reg_inc<88>();
-    // ---------------------------------------------------------------- epilogue --
-    EpiArgs ea{N, Fout, ntiles, nchunks, ngroups, eps, slope, out, xhat, rstd, rowptr, tmem_base, bar_acc_full,
-               bar_acc_empty, s_bias, s_gamma, s_beta, &s_sum[0][0][0], &s_var[0][0][0],
-               reinterpret_cast<float*>(smem_patch), trace, &tm_o0, &tm_o1};
-    const bool full = (Fout == 32 * NT);
-    if (full) epilogue_role<NT, true, MODE>(ea); else epilogue_role<NT, false, MODE>(ea);
+    reg_dec<64>();
+    // ---------------------------------------------------------------- finisher --
+    FinArgs fa{N, Fout, ntiles, ngroups, eps, slope, out, xhat, rstd, rowptr, smem_u32(smem_z), b_l, gamma, beta,
+               bar_z_full, bar_z_empty, trace};
+    finisher_role<NT, MODE>(fa);
   }
   tc_fence_before();
   __syncthreads();
@@ -692,17 +671,15 @@ static bool tc_disabled() {
   return disabled != 0;
 }
 static bool p16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-// outputs of the epilogue: 32-byte aligned for the 256-bit stores (row pitch and column offsets are multiples of 32 B)
-static bool pout(const void* p) { return (reinterpret_cast<uintptr_t>(p) & (kTcDirectStore ? 31u : 15u)) == 0; }
 
 bool project_forward_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* agg, const float* x,
                                  const float* out, const float* xhat) {
   return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fin % 32 == 0 && Fin >= 32 && Fout % 16 == 0 &&
-         Fout >= 16 && Fout <= 128 && p16(agg) && p16(x) && pout(out) && pout(xhat);
+         Fout >= 16 && Fout <= 128 && p16(agg) && p16(x) && p16(out) && p16(xhat);
 }
 bool dgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* dagg, const float* dxroot) {
   return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fout % 32 == 0 && Fout >= 32 && Fin % 16 == 0 &&
-         Fin >= 16 && Fin <= 128 && p16(dz) && pout(dagg) && pout(dxroot);
+         Fin >= 16 && Fin <= 128 && p16(dz) && p16(dagg) && p16(dxroot);
 }
 
 int64_t project_forward_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64_t)4 * Fin * Fout * 4); }
@@ -726,12 +703,11 @@ k_split_weights_t(const float* __restrict__ W_l, const float* __restrict__ W_r, 
 }
 
 template <int NT, int MODE>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mo0,
-                     const CUtensorMap& mo1, const TcProblem& pb,
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
-  const size_t smem = (size_t)kTcStages * kTcBM * 128 + (size_t)kTcBStages * 2 * pb.Nout * 128 + kTcPatchBytes + 1024;
-  SLDM_OPT_IN_SMEM((k_sage_tc<NT, MODE>), kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcPatchBytes + 1024);
+  const size_t smem = (size_t)kTcStages * kTcBM * 128 + (size_t)kTcBStages * 2 * pb.Nout * 128 + kTcZBytes + 1024;
+  SLDM_OPT_IN_SMEM((k_sage_tc<NT, MODE>), kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcZBytes + 1024);
   const int64_t ntiles = ceil_div<int64_t>(pb.N, kTcBM);
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
   long long* trace = nullptr;
@@ -740,7 +716,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     SLDM_CUDA(cudaMalloc(&trace, sizeof(long long) * kTraceIts * kTraceEv));
     SLDM_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * kTraceIts * kTraceEv, s));
   }
-  k_sage_tc<NT, MODE><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
+  k_sage_tc<NT, MODE><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
   SLDM_LAUNCH_CHECK("k_sage_tc");
   if (trace) {
     static long long h[kTraceIts * kTraceEv];
@@ -750,8 +726,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     FILE* f = fopen(tf, "w");
     if (f) {
       fprintf(f, "# cycles from t0; ev: 0 tma_wait_empty 1 tma_got_empty 2 mma_top 3 mma_accempty 4 mma_conv 5 mma_committed "
-                 "6 conv_full 7 conv_done 8 epi_wait 9 epi_accfull 10 epi_released 11 epi_finalize 14 stats_done 19 act_done "
-                 "20-23 / 24-27 push: waited, filled, fenced, issued\n");
+                 "6 conv_full 7 conv_done 8 drain_wait 9 drain_accfull 10 drain_released 11 drain_tile_done 12 z_empty 13 z_parked "
+                 "16 fin_wait 17 fin_got 18 fin_done (16-18 indexed by hand-off number)\n");
       const long long t0 = h[0];
       for (int i = 0; i < kTraceIts; ++i) {
         fprintf(f, "%d", i);
@@ -765,20 +741,16 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
 }
 
 template <int MODE>
-static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mo0,
-                       const CUtensorMap& mo1, const TcProblem& pb,
+static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
                        const float* b_l, const float* g, const float* b, float eps, float slope,
                        float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   switch (ceil_div(pb.Nout, 32)) {
-    case 1: return launch_tc<1, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 2: return launch_tc<2, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 3: return launch_tc<3, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    default: return launch_tc<4, MODE>(ma, mx, mw, mo0, mo1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 1: return launch_tc<1, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 2: return launch_tc<2, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 3: return launch_tc<3, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    default: return launch_tc<4, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
   }
 }
-
-// swizzle mode of the epilogue store patches: rows of 32*NT bytes (make_tmap_2d_f32: 0 = 128B, 2 = 64B, 4 = 32B, 3 = none)
-static int store_swizzle(int nt) { return nt == 4 ? 0 : (nt == 2 ? 2 : (nt == 1 ? 4 : 3)); }
 
 int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
                               const float* W_l, const float* b_l, const float* W_r,
@@ -795,12 +767,8 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
-  CUtensorMap mo0, mo1;
-  const int nt = ceil_div(Fout, 32);
-  if ((rc = make_tmap_2d_f32(&mo0, out, (uint64_t)N, Fout, Fout, 32, 8 * nt, store_swizzle(nt)))) return rc;
-  if ((rc = make_tmap_2d_f32(&mo1, xhat ? xhat : out, (uint64_t)N, Fout, Fout, 32, 8 * nt, store_swizzle(nt)))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
-  return dispatch_tc<MODE_FWD>(ma, mx, mw, mo0, mo1, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
+  return dispatch_tc<MODE_FWD>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
 }
 
 // dagg[N,Fin] = (dz W_l) / max(deg,1) ; dxroot[N,Fin] = dz W_r          (dz is [N,Fout])
@@ -816,12 +784,8 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
   int rc;
   if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fin, Fout, Fout, Fin, 32))) return rc;
-  CUtensorMap mo0, mo1;
-  const int nt = ceil_div(Fin, 32);
-  if ((rc = make_tmap_2d_f32(&mo0, dagg, (uint64_t)N, Fin, Fin, 32, 8 * nt, store_swizzle(nt)))) return rc;
-  if ((rc = make_tmap_2d_f32(&mo1, dxroot, (uint64_t)N, Fin, Fin, 32, 8 * nt, store_swizzle(nt)))) return rc;
   TcProblem pb{N, Fout / 32, 1, 2, Fin};
-  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, mo0, mo1, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
+  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
 }
 
 bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* agg, const float* x) {

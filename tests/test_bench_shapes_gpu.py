@@ -26,14 +26,14 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _blocks(hdims, dev):
+def _blocks(hdims, dev, slope=bench.SLOPE):
     """The bench's own initialisation (torch.manual_seed(0), then the constructor) for the CUDA block; the fp32 and
     fp64 oracles load its state dict."""
     torch.manual_seed(0)
-    ours = sg.SageBlock(hdims, dropout=None, negative_slope=bench.SLOPE)
-    ref = SageBlockOracle(hdims, dropout=None, negative_slope=bench.SLOPE)
+    ours = sg.SageBlock(hdims, dropout=None, negative_slope=slope)
+    ref = SageBlockOracle(hdims, dropout=None, negative_slope=slope)
     ref.load_state_dict(ours.state_dict(), strict=True)
-    ref64 = SageBlockOracle(hdims, dropout=None, negative_slope=bench.SLOPE).double()
+    ref64 = SageBlockOracle(hdims, dropout=None, negative_slope=slope).double()
     ref64.load_state_dict({k: v.double() for k, v in ours.state_dict().items()})
     return ours.to(dev), ref, ref64
 
@@ -78,6 +78,32 @@ def test_batch_workload_fwd_bwd_and_inference(dev):
     assert torch.equal(yi, yg.detach()), "inference and training forward must agree bit for bit"
 
 
+def test_batch_workload_without_the_activation_kink(dev):
+    """The same batch with negative_slope = 1 (LeakyReLU becomes the identity).  At the fp32 noise floor a handful of
+    the 1e8 pre-activations change sign between two correct fp32 evaluations; with slope 0.1 each such element moves
+    its gradient by a factor 10, which is what the adjudicated counts of the test above are made of (the fp32 oracle
+    misses the bar against fp64 just as often).  Without the kink every kernel of the step -- gather, tcgen05
+    projection, LayerNorm, dgrad, split-K wgrad over 0.82 M rows, transpose gather -- is compared at face value:
+    no tensor may need more than 1e-3 of its elements adjudicated, whatever the fp32 oracle does."""
+    wl = bench.WORKLOADS["batch"]
+    hdims = wl["hdims"]
+    x, ei, N, _, _ = bench.make_inputs(wl, 0)
+    w = torch.randn(N, hdims[-1], generator=torch.Generator().manual_seed(7 + N))
+    ours, ref, ref64 = _blocks(hdims, dev, slope=1.0)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, ei)
+    yr.backward(w)
+    xd = x.double().requires_grad_(True)
+    yd = ref64(xd, ei)
+    yd.backward(w.double())
+    xg = x.to(dev).requires_grad_(True)
+    yg = ours(xg, ei.to(dev))
+    yg.backward(w.to(dev))
+    stats = _compare_all(ours, ref, ref64, (yg, xg.grad), (yr, xr.grad), (yd.detach(), xd.grad))
+    for k, (adj, total) in stats.items():
+        assert adj <= max(2, 1e-3 * total), f"{k}: {adj}/{total} elements outside rtol 1e-5 / atol 1e-6 (scaled)"
+
+
 def test_c4_full_backward_parity(dev):
     import psutil
     if psutil.virtual_memory().available < 40 * 2 ** 30:
@@ -92,9 +118,10 @@ def test_c4_full_backward_parity(dev):
     xr = x.clone().requires_grad_(True)
     yr = ref(xr, ei)                      # the oracle proper: index_select + scatter_add_ over all 10 M edges
     yr.backward(w)
-    yd, dxd, gd = _big_graph_oracle(x, ei, ours.state_dict(), hdims, bench.SLOPE, w, torch.float64)
+    state = {k: v.detach().cpu() for k, v in ours.state_dict().items()}
+    yd, dxd, gd = _big_graph_oracle(x, ei, state, hdims, bench.SLOPE, w, torch.float64)
     # the chunked restatement is the same arithmetic: in fp32 it must reproduce the oracle (checks the adjudicator)
-    y32, dx32, _ = _big_graph_oracle(x, ei, ours.state_dict(), hdims, bench.SLOPE, w, torch.float32)
+    y32, dx32, _ = _big_graph_oracle(x, ei, state, hdims, bench.SLOPE, w, torch.float32)
     assert torch.allclose(y32, yr.detach(), rtol=1e-5, atol=1e-5) and torch.allclose(dx32, xr.grad, rtol=1e-4, atol=1e-4)
 
     eid = ei.to(dev)
