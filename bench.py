@@ -305,7 +305,7 @@ def workload_config(name, wl, N, E, graphs):
          "l2": "inputs and saved tensors exceed the 126 MB L2 (x alone is N*F*4 B); two input batches alternate"}
     if N is not None:
         c.update(nodes_per_gpu=N, edges_per_gpu=E, graphs_per_gpu=graphs)
-    c["parallelism"] = "graph-sharded data parallel, one flat-bucket NCCL all-reduce" if name != "c4" else "replicas only"
+    c["parallelism"] = "graph-sharded data parallel, per-layer gradient buckets all-reduced (NCCL) under the rest of backward" if name != "c4" else "replicas only"
     return c
 
 
@@ -491,6 +491,8 @@ def main_ours(args, wl):
                 return blk(x.detach(), ei)
         ddp.zero_grad()
         x.grad = None
+        if world > 1:
+            ddp.expect_sync(local_weight=b["graphs"])   # buckets leave for the all-reduce as backward finishes them
         y = ddp(x, ei)
         y.backward(b["w"])
         if world > 1:

@@ -47,8 +47,14 @@ using namespace tc;
 
 constexpr int kTcThreads = 896;   // 7 warpgroups: {TMA, MMA, alloc+TMA B, MMA} {converter x4} {drain x4} x 4 {finisher x4}
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
-constexpr int kTcStages = 5;        // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
-constexpr int kTcBStages = 2;       // B ring: weight chunks B_hi | B_lo (L2 resident, short latency)
+#ifndef SLDM_TC_STAGES
+#define SLDM_TC_STAGES 5
+#endif
+#ifndef SLDM_TC_BSTAGES
+#define SLDM_TC_BSTAGES 2
+#endif
+constexpr int kTcStages = SLDM_TC_STAGES;     // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
+constexpr int kTcBStages = SLDM_TC_BSTAGES;   // B ring: weight chunks B_hi | B_lo (32 KB each at Fout = 128; L2 resident)
 constexpr int kTcBM = 128;
 constexpr int kTcAcc = 3;          // TMEM accumulator ring (one K chunk each), columns [0, 3*32*NT): look-ahead of the MMA stream
 constexpr int kTcASlots = 2;       // TMEM A slots (own ring, own "free" barriers: shorter than the smem stage ring)
@@ -108,13 +114,17 @@ __device__ __forceinline__ uint32_t z_chunk_addr(uint32_t zbase, int r, int j) {
 }
 
 struct DrainArgs {
-  int64_t ntiles; int nchunks; int ngroups; uint32_t tmem_base; uint32_t zbase;
+  int64_t N; int Fout; int64_t ntiles; int nchunks; int ngroups; float eps; uint32_t tmem_base; uint32_t zbase;
+  float* rstd; const int32_t* rowptr; const float* s_bias; float* s_sum; float* s_var;
   uint64_t* bar_acc_full; uint64_t* bar_acc_empty; uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
 };
 
 // Drain role: 16 warps (512 threads).  Thread (quadrant q, lane, column quarter CQ) owns tile row q*32+lane and the
-// columns [CQ*8*NT, (CQ+1)*8*NT): one tcgen05.ld round trip per K chunk, fp32 register accumulation.
-template <int NT>
+// columns [CQ*8*NT, (CQ+1)*8*NT): one tcgen05.ld round trip per K chunk, fp32 register accumulation.  After the last
+// chunk: FWD + bias and the LayerNorm statistics (thread per row x quarter: every warp instruction serves 32 rows --
+// a lane-per-column finisher spent 2.9k cycles per 4 rows on the divisions and shuffles of the statistics alone),
+// DGRAD the division by the in-degree; the normalised row is parked for the finisher.  FULL = (Fout == 32*NT).
+template <int NT, bool FULL, int MODE>
 __device__ __forceinline__ void drain_role(const DrainArgs a) {
   constexpr int HC = 8 * NT;               // columns per thread
   constexpr int ACC_COLS = 32 * NT;
@@ -123,7 +133,11 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
   const int q = warp & 3;                  // TMEM lane quadrant of this warp
   const int rloc = q * 32 + lane;
   const int cq = (warp - 8) >> 2;          // column quarter
-  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + cq * HC;
+  const int c_lo = cq * HC;
+  const uint32_t tq = a.tmem_base + ((uint32_t)(q * 32) << 16) + c_lo;
+  const float fF = (float)a.Fout;
+  const int Fout = a.Fout;
+  const float* const bias = a.s_bias + c_lo;
   uint32_t it = 0, hand = 0;
   for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     for (int grp = 0; grp < a.ngroups; ++grp, ++hand) {
@@ -154,8 +168,71 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
             for (int j = 0; j < 8; ++j) z[g0 * 8 + j] += __uint_as_float(rr[g0][j]);
         }
       }
-      // ---- park the finished sums for the finisher warp of this quadrant and move on
       if (tid == 256) TC_TRACE(11, it - 1);
+      const int64_t row = tile * kTcBM + rloc;
+      if constexpr (MODE == MODE_FWD) {
+        // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q.
+        //      Each quarter computes its own (sum, M2 about its own mean); ONE exchange through smem on a 128-thread
+        //      named barrier and Chan's merge give the row mean and variance:
+        //         M2 = sum_q M2_q + sum_q n_q (m_q - mean)^2        (two-pass accuracy, one barrier instead of two)
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j4 = 0; j4 < HC / 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * j4 + e;
+            z[j] += bb[e];
+            ps[e] += (FULL || c_lo + j < Fout) ? z[j] : 0.f;
+          }
+        }
+        const int nq_i = FULL ? HC : max(0, min(HC, Fout - c_lo));     // valid columns of this quarter
+        const float nq = (float)nq_i;
+        const float sq = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        const float mq = nq_i > 0 ? __fdiv_rn(sq, nq) : 0.f;
+        float pv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          const float d = z[j] - mq;
+          pv[j & 3] += (FULL || c_lo + j < Fout) ? d * d : 0.f;
+        }
+        // buffers alternate per tile: a warp can only be one barrier ahead of its three partners, so the values of
+        // tile t are never overwritten (by tile t+2) before everybody has read them
+        float* const sS = a.s_sum + (hand & 1) * 512;
+        float* const sV = a.s_var + (hand & 1) * 512;
+        sS[cq * 128 + rloc] = sq;
+        sV[cq * 128 + rloc] = (pv[0] + pv[1]) + (pv[2] + pv[3]);
+        named_bar_sync(2 + q, 128);
+        float s4[4], m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = sS[k * 128 + rloc];
+        const float mean = __fdiv_rn((s4[0] + s4[1]) + (s4[2] + s4[3]), fF);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int nk_i = FULL ? HC : max(0, min(HC, Fout - k * HC));
+          const float nk = (float)nk_i;
+          const float dm = (nk_i > 0 ? __fdiv_rn(s4[k], nk) : mean) - mean;
+          m2 += sV[k * 128 + rloc] + nk * dm * dm;
+        }
+        const float rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(m2, fF) + a.eps));
+#pragma unroll
+        for (int j = 0; j < HC; ++j) z[j] = (z[j] - mean) * rs;      // z now holds xhat
+        if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
+        if (tid == 256) TC_TRACE(14, it - 1);
+      } else {
+        if (grp == 0) {
+          float cnt = 1.f;
+          if (row < a.N) {
+            int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+            deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
+            cnt = (float)deg;
+          }
+#pragma unroll
+          for (int j = 0; j < HC; ++j) z[j] = __fdiv_rn(z[j], cnt);
+        }
+      }
+      // ---- park the finished row for the finisher warp of this quadrant and move on
       mbar_wait(&a.bar_z_empty[q], (hand & 1) ^ 1);      // the previous tile of this quadrant has been read
       if (tid == 256) TC_TRACE(12, it - 1);
 #pragma unroll
@@ -169,20 +246,21 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
 }
 
 struct FinArgs {
-  int64_t N; int Fout; int64_t ntiles; int ngroups; float eps, slope;
-  float* out; float* xhat; float* rstd; const int32_t* rowptr; uint32_t zbase;
-  const float* bias; const float* gamma; const float* beta;       // global pointers (FWD)
+  int64_t N; int Fout; int64_t ntiles; int ngroups; float slope;
+  float* out; float* xhat; uint32_t zbase;
+  const float* gamma; const float* beta;       // global pointers (FWD)
   uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
 };
 
 // Finisher role: 4 warps, warp q owns rows [32q, 32q+32) of the parked tile.  A row is spread over LPRW = 8*NT lanes
 // (lane = 4 consecutive columns), RPI = 32 / LPRW rows per instruction (NT = 3: 24 of 32 lanes active), U of them in
-// flight so that the shuffle chains of the LayerNorm overlap.
+// flight.  FWD: the parked values are xhat: store it (training), then the affine + (Leaky)ReLU and the output store.
+// DGRAD: plain copy to dagg | dxroot.  Every store instruction writes whole rows (512 B at Fout = 128).
 template <int NT, int MODE>
 __device__ __forceinline__ void finisher_role(const FinArgs a) {
   constexpr int LPRW = (NT == 1) ? 8 : (NT == 2) ? 16 : 32;
   constexpr int RPI = 32 / LPRW;
-  constexpr int U = 4;
+  constexpr int U = 2;                      // rows in flight per warp (40-register budget)
   long long* trace = a.trace;
   const int tid = threadIdx.x, lane = tid & 31;
   const int q = (tid >> 5) & 3;
@@ -190,10 +268,8 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
   const int Fout = a.Fout;
   const int c0 = 4 * lig;
   const bool cvalid = c0 < Fout;                      // Fout % 4 == 0: a lane's four columns are valid together
-  const float fF = (float)Fout;
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gam4 = bias4, bet4 = bias4;
+  float4 gam4 = make_float4(0.f, 0.f, 0.f, 0.f), bet4 = gam4;
   if (MODE == MODE_FWD && cvalid) {
-    bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0));
     gam4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
     bet4 = __ldg(reinterpret_cast<const float4*>(a.beta + c0));
   }
@@ -222,55 +298,19 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&a.bar_z_empty[q]);
         }
-        if constexpr (MODE == MODE_FWD) {
-          float s[U], m2[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            v[u].x += bias4.x; v[u].y += bias4.y; v[u].z += bias4.z; v[u].w += bias4.w;
-            s[u] = cvalid ? (v[u].x + v[u].y) + (v[u].z + v[u].w) : 0.f;
-          }
-#pragma unroll
-          for (int o = LPRW / 2; o >= 1; o >>= 1)
-#pragma unroll
-            for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float mean = __fdiv_rn(s[u], fF);
-            v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
-            m2[u] = cvalid ? (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w) : 0.f;
-          }
-#pragma unroll
-          for (int o = LPRW / 2; o >= 1; o >>= 1)
-#pragma unroll
-            for (int u = 0; u < U; ++u) m2[u] += __shfl_xor_sync(0xffffffffu, m2[u], o);
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(m2[u], fF) + a.eps));
-            const int64_t row = tile * kTcBM + rl[u];
-            if (row < a.N && cvalid) {
-              float4 xh = make_float4(v[u].x * rs, v[u].y * rs, v[u].z * rs, v[u].w * rs);
-              if (a.xhat != nullptr) *reinterpret_cast<float4*>(a.xhat + row * Fout + c0) = xh;
-              if (a.rstd != nullptr && lig == 0) a.rstd[row] = rs;
+        for (int u = 0; u < U; ++u) {
+          const int64_t row = tile * kTcBM + rl[u];
+          if (row < a.N && cvalid) {
+            if constexpr (MODE == MODE_FWD) {
+              if (a.xhat != nullptr) *reinterpret_cast<float4*>(a.xhat + row * Fout + c0) = v[u];
               float4 y;
-              y.x = fmaf(xh.x, gam4.x, bet4.x); y.y = fmaf(xh.y, gam4.y, bet4.y);
-              y.z = fmaf(xh.z, gam4.z, bet4.z); y.w = fmaf(xh.w, gam4.w, bet4.w);
+              y.x = fmaf(v[u].x, gam4.x, bet4.x); y.y = fmaf(v[u].y, gam4.y, bet4.y);
+              y.z = fmaf(v[u].z, gam4.z, bet4.z); y.w = fmaf(v[u].w, gam4.w, bet4.w);
               y.x = y.x > 0.f ? y.x : a.slope * y.x; y.y = y.y > 0.f ? y.y : a.slope * y.y;
               y.z = y.z > 0.f ? y.z : a.slope * y.z; y.w = y.w > 0.f ? y.w : a.slope * y.w;
               *reinterpret_cast<float4*>(o_main + row * Fout + c0) = y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int64_t row = tile * kTcBM + rl[u];
-            if (row < a.N && cvalid) {
-              if (grp == 0) {
-                int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
-                deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
-                const float cnt = (float)deg;
-                v[u].x = __fdiv_rn(v[u].x, cnt); v[u].y = __fdiv_rn(v[u].y, cnt);
-                v[u].z = __fdiv_rn(v[u].z, cnt); v[u].w = __fdiv_rn(v[u].w, cnt);
-              }
+            } else {
               *reinterpret_cast<float4*>(o_main + row * Fout + c0) = v[u];
             }
           }
@@ -299,6 +339,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   __shared__ uint64_t bar_acc_full[kTcAcc], bar_acc_empty[kTcAcc];
   __shared__ uint64_t bar_z_full[4], bar_z_empty[4];                   // hand-off tile, per 32-row quadrant: drain -> finisher -> drain
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ float s_sum[2][4][128], s_var[2][4][128];   // double buffered by tile parity (one barrier per tile)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = kTcBM * 128;
@@ -315,6 +357,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   const int ngroups = pb.ngroups;
   const int64_t ntiles = (N + kTcBM - 1) / kTcBM;
 
+  if (MODE == MODE_FWD && tid < 128) s_bias[tid] = tid < Fout ? b_l[tid] : 0.f;
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -351,20 +394,24 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
    if (warp == 0) {
     // ---------------------------------------------------------- TMA producer: A --
     // raw activation chunks, kTcStages deep: this is the HBM stream, it keeps running while the epilogue finishes a tile
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (operands stay on the uniform datapath)
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = (int)(tile * kTcBM);
         for (int g = 0; g < ngroups; ++g) {
           for (int c = 0; c < nchunks; ++c, ++it) {
             const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
-            TC_TRACE(0, it);
+            if (lane == 0) TC_TRACE(0, it);
             mbar_wait(&bar_empty[s], ph ^ 1);
-            TC_TRACE(1, it);
-            mbar_expect_tx(&bar_full[s], a_bytes);
+            if (lane == 0) TC_TRACE(1, it);
             const int src = c / half;
             const int k0 = (c - src * half) * 32;
-            tma_load_2d(smem + (size_t)s * a_bytes, src == 0 ? &tm_agg : &tm_x, k0, row0, &bar_full[s]);
+            if (elect_one()) {
+              mbar_expect_tx(&bar_full[s], a_bytes);
+              tma_load_2d_u32(smem_u + s * a_bytes, src == 0 ? &tm_agg : &tm_x, k0, row0, &bar_full[s]);
+            }
+            __syncwarp();
           }
         }
       }
@@ -373,32 +420,45 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     // ---------------------------------------------------------- TMA producer: B --
     // pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk (L2 resident; re-streaming them is not a limiter:
     // skipping these loads changed the kernel time by < 5% on B200)
-    if (lane == 0) {
+    {
+      const uint32_t smem_b_u = __shfl_sync(0xffffffffu, smem_u32(smem_b), 0);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int g = 0; g < ngroups; ++g) {
           for (int c = 0; c < nchunks; ++c, ++it) {
             const uint32_t s = it % kTcBStages, ph = (it / kTcBStages) & 1;
+            if (lane == 0) TC_TRACE(29, it);
             mbar_wait(&bar_bempty[s], ph ^ 1);
-            uint8_t* st = smem_b + (size_t)s * 2 * b_bytes;
-            mbar_expect_tx(&bar_bfull[s], 2 * b_bytes);
+            if (lane == 0) TC_TRACE(30, it);
+            const uint32_t st = smem_b_u + s * 2u * b_bytes;
             const int src = c / half;
             const int k0 = (c - src * half) * 32;
             const int wrow = 2 * (g * pb.nsrc + src) * Fout;
-            tma_load_2d(st, &tm_w, k0, wrow, &bar_bfull[s]);
-            tma_load_2d(st + b_bytes, &tm_w, k0, wrow + Fout, &bar_bfull[s]);
+            if (elect_one()) {
+              mbar_expect_tx(&bar_bfull[s], 2 * b_bytes);
+              tma_load_2d_u32(st, &tm_w, k0, wrow, &bar_bfull[s]);
+              tma_load_2d_u32(st + b_bytes, &tm_w, k0, wrow + Fout, &bar_bfull[s]);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1 || warp == 3) {
     // ------------------------------------------------------------- MMA issuers --
-    // Two issuing threads alternate K chunks (warp 1: even, warp 3: odd).  A chunk has its own accumulator, smem stage
-    // and TMEM A slot, so the two streams are independent; while one thread sits in the barrier waits of its next
-    // chunk the tensor pipe is fed by the other (one issuer left ~35% bubbles: profiles/r01c trace).
-    if (lane == 0) {
+    // Two issuing warps alternate K chunks (warp 1: even, warp 3: odd).  A chunk has its own accumulator, smem stage
+    // and TMEM A slot, so the two streams are independent; while one sits in the barrier waits of its next chunk the
+    // tensor pipe is fed by the other (one issuer left ~35% bubbles: profiles/r01c trace).
+    // The WHOLE warp runs this loop in uniform control flow and one elected lane issues.  Round 1 ran it under
+    // `if (lane == 0)`: every operand then lives in a per-thread register and ptxas wraps each tcgen05.mma in an
+    // ELECT / 4x R2UR / BRA.U.ANY broadcast loop (15 SASS instructions per MMA; measured 150 cycles per MMA against
+    // the 64-cycle tensor-pipe floor -- the kernel was bound by MMA ISSUE, profiles/r02 trace).  With warp-uniform
+    // operands (tmem base through a lane-0 shuffle) they are computed on the uniform datapath.
+    {
       const uint32_t my_parity = (warp == 3) ? 1u : 0u;
       const uint32_t idesc = make_idesc_tf32(kTcBM, Fout, 0, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_b_u = __shfl_sync(0xffffffffu, smem_u32(smem_b), 0);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < ngroups * nchunks; ++c, ++it) {
@@ -406,31 +466,35 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           const uint32_t asl = it % kTcASlots, aslph = (it / kTcASlots) & 1;
           const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
           if ((it & 1u) != my_parity) continue;
-          TC_TRACE(2, it);
+          if (lane == 0) TC_TRACE(2, it);
           mbar_wait(&bar_acc_empty[ab], aph ^ 1);   // epilogue drained this accumulator (three chunks ago)
-          TC_TRACE(3, it);
+          if (lane == 0) TC_TRACE(3, it);
           mbar_wait(&bar_conv[asl], aslph);         // a_hi | a_lo of this chunk are in the TMEM slot
+          if (lane == 0) TC_TRACE(28, it);
           mbar_wait(&bar_bfull[sb], bph);           // weight tiles of this chunk have landed
-          TC_TRACE(4, it);
+          if (lane == 0) TC_TRACE(4, it);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_b + (size_t)sb * 2 * b_bytes);
+          const uint32_t sa = smem_b_u + sb * 2u * b_bytes;
           // B descriptors differ only in the 14-bit start-address field (bytes >> 4); A comes from tensor memory
           const uint64_t d_b_hi = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t d_b_lo = d_b_hi + (b_bytes >> 4);
-          const uint32_t a_hi = tmem_base + kTcACol0 + asl * 64;
+          const uint32_t a_hi = tmem_u + kTcACol0 + asl * 64;
           const uint32_t a_lo = a_hi + 32;
-          const uint32_t d = tmem_base + ab * ACC_COLS;
-          // small products first: the accumulator rounds toward zero
+          const uint32_t d = tmem_u + ab * ACC_COLS;
+          if (elect_one()) {
+            // small products first: the accumulator rounds toward zero
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_lo + 8 * ks, d_b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_lo + 8 * ks, d_b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_lo + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_lo + 2 * ks, idesc, 1u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_hi + 2 * ks, idesc, 1u);
-          mma_commit(&bar_bempty[sb]);     // weight stage reusable once these MMAs have read it
-          mma_commit(&bar_afree[asl]);     // ... and the TMEM A slot
-          mma_commit(&bar_acc_full[ab]);   // chunk accumulator complete
-          TC_TRACE(5, it);
+            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 8 * ks, d_b_hi + 2 * ks, idesc, 1u);
+            mma_commit(&bar_bempty[sb]);     // weight stage reusable once these MMAs have read it
+            mma_commit(&bar_afree[asl]);     // ... and the TMEM A slot
+            mma_commit(&bar_acc_full[ab]);   // chunk accumulator complete
+          }
+          __syncwarp();
+          if (lane == 0) TC_TRACE(5, it);
         }
       }
     }
@@ -489,16 +553,15 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       }
     }
   } else if (warp < 24) {
-    reg_inc<80>();
+    reg_inc<88>();
     // ------------------------------------------------------------------- drain --
-    DrainArgs da{ntiles, nchunks, ngroups, tmem_base, smem_u32(smem_z), bar_acc_full, bar_acc_empty, bar_z_full,
-                 bar_z_empty, trace};
-    drain_role<NT>(da);
+    DrainArgs da{N, Fout, ntiles, nchunks, ngroups, eps, tmem_base, smem_u32(smem_z), rstd, rowptr, s_bias,
+                 &s_sum[0][0][0], &s_var[0][0][0], bar_acc_full, bar_acc_empty, bar_z_full, bar_z_empty, trace};
+    if (Fout == 32 * NT) drain_role<NT, true, MODE>(da); else drain_role<NT, false, MODE>(da);
   } else {
-    reg_dec<64>();
+    reg_dec<40>();
     // ---------------------------------------------------------------- finisher --
-    FinArgs fa{N, Fout, ntiles, ngroups, eps, slope, out, xhat, rstd, rowptr, smem_u32(smem_z), b_l, gamma, beta,
-               bar_z_full, bar_z_empty, trace};
+    FinArgs fa{N, Fout, ntiles, ngroups, slope, out, xhat, smem_u32(smem_z), gamma, beta, bar_z_full, bar_z_empty, trace};
     finisher_role<NT, MODE>(fa);
   }
   tc_fence_before();
@@ -559,24 +622,33 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
 
   if (warp < 4) {
     reg_dec<72>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer --
+      // (whole warp, uniform control flow, one elected lane issues: operands stay on the uniform datapath)
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       for (int it = 0; it < nch; ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
         mbar_wait(&bar_empty[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        mbar_expect_tx(&bar_full[s], RAW_BYTES);
+        const uint32_t st = smem_u + s * STAGE_BYTES;
         const int r0 = (int)((c_beg + it) * kWgRows);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_full[s], RAW_BYTES);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(st + b * kWgBlk, &tm_dz, b * 32, r0, &bar_full[s]);
+          for (int b = 0; b < 4; ++b) tma_load_2d_u32(st + b * kWgBlk, &tm_dz, b * 32, r0, &bar_full[s]);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + b * kWgBlk, &tm_agg, b * 32, r0, &bar_full[s]);
+          for (int b = 0; b < NB; ++b) tma_load_2d_u32(st + A_BYTES + b * kWgBlk, &tm_agg, b * 32, r0, &bar_full[s]);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) tma_load_2d(st + A_BYTES + (NB + b) * kWgBlk, &tm_x, b * 32, r0, &bar_full[s]);
+          for (int b = 0; b < NB; ++b) tma_load_2d_u32(st + A_BYTES + (NB + b) * kWgBlk, &tm_x, b * 32, r0, &bar_full[s]);
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ------------------------------------------------------------------ MMA issuer --
+      // whole warp in uniform control flow, one elected lane issues (see k_sage_tc: under `if (lane == 0)` ptxas wraps
+      // every tcgen05.mma in a 15-instruction broadcast loop and the issue rate, not the tensor pipe, sets the pace)
       const uint32_t idesc = make_idesc_tf32(128, NCOLS, 1, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       for (int it = 0; it < nch; ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
         const uint32_t fl = it / kWgFlush, ab = fl & 1, aph = (fl >> 1) & 1;
@@ -584,20 +656,23 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
         if (first) mbar_wait(&bar_acc_empty[ab], aph ^ 1);
         mbar_wait(&bar_conv[s], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sa = smem_u + s * STAGE_BYTES;
         const uint64_t d_a_hi = make_smem_desc(sa, kWgBlk, 512, 1);
         const uint64_t d_b_hi = d_a_hi + (A_BYTES >> 4);
         const uint64_t d_a_lo = d_a_hi + (RAW_BYTES >> 4);
         const uint64_t d_b_lo = d_b_hi + (RAW_BYTES >> 4);
-        const uint32_t d = tmem_base + ab * NCOLS;
+        const uint32_t d = tmem_u + ab * NCOLS;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_lo + 64 * ks, d_b_hi + 64 * ks, idesc, (first && ks == 0) ? 0u : 1u);
+          for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_lo + 64 * ks, d_b_hi + 64 * ks, idesc, (first && ks == 0) ? 0u : 1u);
 #pragma unroll
-        for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
+          for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
 #pragma unroll
-        for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_hi + 64 * ks, idesc, 1u);
-        mma_commit(&bar_empty[s]);
-        if ((it % kWgFlush) == kWgFlush - 1 || it == nch - 1) mma_commit(&bar_acc_full[ab]);
+          for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_hi + 64 * ks, idesc, 1u);
+          mma_commit(&bar_empty[s]);
+          if ((it % kWgFlush) == kWgFlush - 1 || it == nch - 1) mma_commit(&bar_acc_full[ab]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp < 8) {
@@ -727,7 +802,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     if (f) {
       fprintf(f, "# cycles from t0; ev: 0 tma_wait_empty 1 tma_got_empty 2 mma_top 3 mma_accempty 4 mma_conv 5 mma_committed "
                  "6 conv_full 7 conv_done 8 drain_wait 9 drain_accfull 10 drain_released 11 drain_tile_done 12 z_empty 13 z_parked "
-                 "16 fin_wait 17 fin_got 18 fin_done (16-18 indexed by hand-off number)\n");
+                 "16 fin_wait 17 fin_got 18 fin_done (16-18 indexed by hand-off number) 28 mma_conv_only 29 tmaB_wait_empty 30 tmaB_got_empty\n");
       const long long t0 = h[0];
       for (int i = 0; i < kTraceIts; ++i) {
         fprintf(f, "%d", i);

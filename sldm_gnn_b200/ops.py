@@ -215,6 +215,17 @@ def layer_forward(x, csr: Csr, W_l, b_l, W_r, ln_w, ln_b, eps: float, slope: flo
     return out, agg, xhat, rstd
 
 
+# ---- "parameter gradients of the last layer_backward are complete" event (consumed by parallel.GraphDataParallel) ----
+_param_grad_events: dict = {}
+
+
+def take_param_grad_event(dev):
+    """The event layer_backward recorded after its weight-gradient reduction and BEFORE launching the dx gather, or
+    None.  One-shot: a data-parallel wrapper waits on it from its side stream so that the gradient exchange of the
+    layer overlaps the gather."""
+    return _param_grad_events.pop(torch.device(dev), None)
+
+
 def backward_buffers(N: int, Fin: int, Fout: int, E: int, dev, need_dx: bool) -> dict:
     """Outputs, scratch and workspace of one layer_backward call."""
     with torch.cuda.device(dev):
@@ -232,7 +243,7 @@ def backward_buffers(N: int, Fin: int, Fout: int, E: int, dev, need_dx: bool) ->
 
 
 def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slope: float, need_dx: bool,
-                   stages: int = _lib.BWD_STAGE_ALL, bufs: dict | None = None):
+                   stages: int = _lib.BWD_STAGE_ALL, bufs: dict | None = None, record_event: bool = False):
     """Returns (dx | None, dW_l, db_l, dW_r, dln_w, dln_b).
 
     `stages` / `bufs` are for profiling (bench.py): launch only the masked kernels on the buffers of an earlier
@@ -242,11 +253,23 @@ def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slo
     dev = x.device
     dout = dout.contiguous()
     b = bufs if bufs is not None else backward_buffers(N, Fin, Fout, csr.E, dev, need_dx)
-    with torch.cuda.device(dev):
+
+    def launch(mask):
         check(lib.sldm_sage_layer_backward_stages(
             dout.data_ptr(), x.data_ptr(), agg.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), N, Fin, Fout,
             csr.buf.data_ptr(), csr.E, W_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), float(slope),
             _ptr(b["dx"]), b["dW_l"].data_ptr(), b["db_l"].data_ptr(), b["dW_r"].data_ptr(), b["dln_w"].data_ptr(),
             b["dln_b"].data_ptr(), b["dz"].data_ptr(), _ptr(b["dagg"]), _ptr(b["dxroot"]), b["ws"].data_ptr(), b["wsb"],
-            _stream(dev), int(stages)))
+            _stream(dev), int(mask)))
+
+    with torch.cuda.device(dev):
+        if record_event and need_dx and stages == _lib.BWD_STAGE_ALL and N > 0:
+            # the parameter gradients are final before the dx gather starts: mark that point on the stream
+            launch(_lib.BWD_STAGE_ALL & ~_lib.BWD_STAGE_GATHER)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            _param_grad_events[torch.device(dev)] = ev
+            launch(_lib.BWD_STAGE_GATHER)
+        else:
+            launch(stages)
     return b["dx"], b["dW_l"], b["db_l"], b["dW_r"], b["dln_w"], b["dln_b"]

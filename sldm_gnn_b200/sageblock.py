@@ -67,24 +67,60 @@ class SageConvParams(nn.Module):
         return f"{self.in_channels}, {self.out_channels}, aggr=mean"
 
 
-class _SageLayerFn(torch.autograd.Function):
+class _SageBlockFn(torch.autograd.Function):
+    """The whole block as ONE autograd node: L x (CSR segment mean -> fused projection + LayerNorm + activation ->
+    dropout).  Gradients between the layers never pass through the autograd engine (no per-layer node, no dtype
+    casts in the bf16 feature mode), the host issues two C calls per layer and direction.
+
+    Dropout (posts[i][2] of the reference, src/models/blocks/sageblock.py:13) is torch's own fused kernel,
+    torch.native_dropout -- the one nn.Dropout dispatches to on CUDA -- so the global Philox stream is consumed
+    exactly as by the reference; its mask is kept for the backward.
+    """
+
     @staticmethod
-    def forward(ctx, x, W_l, b_l, W_r, ln_w, ln_b, csr, eps, slope):
-        save = any(ctx.needs_input_grad[:6])
-        out, agg, xhat, rstd = ops.layer_forward(x, csr, W_l, b_l, W_r, ln_w, ln_b, eps, slope, save)
+    def forward(ctx, x, csr, eps, slopes, drops, *params):
+        L = len(params) // 5
+        save = any(ctx.needs_input_grad)
+        h, keep = x, []
+        for l in range(L):
+            W_l, b_l, W_r, ln_w, ln_b = params[5 * l:5 * l + 5]
+            out, agg, xhat, rstd = ops.layer_forward(h, csr, W_l, b_l, W_r, ln_w, ln_b, eps[l], slopes[l], save)
+            mask = None
+            if drops[l] is not None:                       # training mode and 0 < p < 1
+                out, mask = torch.native_dropout(out, drops[l], True)
+            if save:
+                keep += [h, agg, xhat, rstd, mask]
+            h = out
         if save:
-            ctx.save_for_backward(x, agg, xhat, rstd, W_l, W_r, ln_w, ln_b)
-            ctx.csr, ctx.slope = csr, slope
-        return out
+            tensors = [t for t in keep if t is not None]
+            ctx.layout = [t is not None for t in keep]
+            ctx.save_for_backward(*tensors, *params)
+            ctx.csr, ctx.slopes, ctx.drops, ctx.L = csr, slopes, drops, L
+        return h
 
     @staticmethod
     @once_differentiable   # hand-written first-order gradients: a double backward raises instead of returning garbage
     def backward(ctx, dout):
-        x, agg, xhat, rstd, W_l, W_r, ln_w, ln_b = ctx.saved_tensors
-        need_dx = ctx.needs_input_grad[0]
-        dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
-            dout, x, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slope, need_dx)
-        return dx, dW_l, db_l, dW_r, dln_w, dln_b, None, None, None
+        L = ctx.L
+        saved = list(ctx.saved_tensors)
+        params = saved[len(saved) - 5 * L:]
+        it = iter(saved[:len(saved) - 5 * L])
+        keep = [next(it) if present else None for present in ctx.layout]
+        ddp = torch.distributed.is_available() and torch.distributed.is_initialized()
+        grads = [None] * (5 * L)
+        g = dout
+        for l in range(L - 1, -1, -1):
+            h, agg, xhat, rstd, mask = keep[5 * l:5 * l + 5]
+            W_l, _, W_r, ln_w, ln_b = params[5 * l:5 * l + 5]
+            if mask is not None:
+                g = torch.ops.aten.native_dropout_backward(g, mask, 1.0 / (1.0 - ctx.drops[l]))
+            need_dx = l > 0 or ctx.needs_input_grad[0]
+            dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
+                g, h, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slopes[l], need_dx,
+                record_event=ddp and l == 0)    # layer 0: the exchange of its gradients overlaps its own dx gather
+            grads[5 * l:5 * l + 5] = [dW_l, db_l, dW_r, dln_w, dln_b]
+            g = dx
+        return (g, None, None, None, None, *grads)
 
 
 class SageBlock(nn.Module):
@@ -138,6 +174,7 @@ class SageBlock(nn.Module):
         x = x.contiguous()
         ops.index_checks.poll()            # a deferred out-of-range report of an earlier edge_index raises here
         csr = self._get_csr(edge_index, x.size(0))
+        eps, slopes, drops, params = [], [], [], []
         for conv, post in zip(self.convs, self.posts):
             ln, act, drop = post[0], post[1], post[2]
             slope = float(act.negative_slope) if isinstance(act, nn.LeakyReLU) else 0.0
@@ -151,7 +188,10 @@ class SageBlock(nn.Module):
                                        "(mat1 and mat2 must have the same dtype)")
                 if not t.is_contiguous():
                     raise RuntimeError(f"SageBlock: parameter {name} is not contiguous")
-            x = _SageLayerFn.apply(x, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight,
-                                   ln.weight, ln.bias, csr, float(ln.eps), slope)
-            x = drop(x)
-        return x
+            p = float(drop.p) if isinstance(drop, nn.Dropout) else 0.0
+            if p >= 1.0 and self.training:
+                raise NotImplementedError("SageBlock: dropout p = 1 is not supported by the fused block")
+            eps.append(float(ln.eps)); slopes.append(slope)
+            drops.append(p if (self.training and p > 0.0) else None)
+            params += [conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, ln.weight, ln.bias]
+        return _SageBlockFn.apply(x, csr, eps, slopes, drops, *params)

@@ -45,6 +45,9 @@ def _worker(rank, world, port, num_graphs, out):
         torch.manual_seed(100 + rank)            # replicas start DIFFERENT: broadcast must fix it
         model = SageBlockOracle([6, 8, 4], negative_slope=0.1)
         ddp = GraphDataParallel(model)
+        assert ddp.num_buckets == 2              # one bucket per SageBlock layer, last layer first (backward order)
+        assert [len(b["params"]) for b in ddp._buckets] == [5, 5]
+        assert ddp._buckets[0]["params"][0] is model.convs[1].lin_l.weight
         # after the broadcast every rank holds rank 0's parameters
         flat = ddp._flat.clone()
         ref = flat.clone(); dist.broadcast(ref, 0)
@@ -79,6 +82,16 @@ def test_graph_data_parallel_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), num_graphs, out), nprocs=world, join=True)
     assert dict(out) == {0: "ok", 1: "ok"}
+
+
+def test_bucket_keys_follow_backward_order():
+    from sldm_gnn_b200.parallel import default_bucket_key as key
+    names = ["sage.convs.0.lin_l.weight", "sage.posts.0.0.bias", "sage.convs.1.lin_r.weight", "sage.posts.1.0.weight",
+             "fc1.0.weight", "map_encoder.sage.convs.0.lin_l.bias"]
+    assert key(names[0]) == key(names[1]) != key(names[2]) == key(names[3])
+    assert key(names[4]) == ("", -1) and key(names[5]) == ("map_encoder.sage.", 0)
+    order = sorted({key(n) for n in names}, reverse=True)
+    assert order.index(key(names[2])) < order.index(key(names[0]))     # layer 1 is exchanged before layer 0
 
 
 def test_shard_graphs_partition():
