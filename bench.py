@@ -355,7 +355,7 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
     conv, ln = blk.convs[0], blk.posts[0][0]
     p = (conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, ln.weight, ln.bias)
     csr = sg.build_csr(ei, N)
-    out, agg, xhat, rstd = ops.layer_forward(x, csr, *p, ln.eps, SLOPE, True)
+    _, out, agg, xhat, rstd = ops.layer_forward(x, csr, *p, ln.eps, SLOPE, True)
     dout = torch.randn_like(out)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=x.device)
 

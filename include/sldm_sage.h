@@ -191,6 +191,40 @@ int     sldm_sage_layer_backward_stages(const float* dout, const float* x, const
                                         void* workspace, int64_t workspace_bytes,
                                         sldm_stream_t stream, int32_t stages);
 
+/* ---- bf16 feature storage (BASELINE.json configs[4]: "fp32 vs bf16 features") ------------------------------------
+ * The reference has no reduced-precision mode (no autocast / bfloat16 anywhere: main.py:58, src/utils.py:176-236);
+ * this is an addition of this library with its own tolerance, the fp32 entry points above stay the parity path.
+ * What is stored as bf16 (2 bytes per feature in HBM): the layer input x, the aggregated rows agg and the layer
+ * output out -- i.e. every [N, F] feature matrix the forward moves.  What stays fp32: all parameters, every
+ * accumulation (segment sums, the tcgen05 products, LayerNorm statistics), the saved xhat / rstd, and the whole
+ * backward data path (dout, dz, dagg, dxroot, dx and the parameter gradients); only the weight-gradient kernel
+ * reads the bf16 x / agg.  Rounding happens once per stored value (round-to-nearest-even).
+ *   sldm_segment_mean_bf16        src, out: bf16 [N,F]; F % 8 == 0, F <= 256
+ *   sldm_sage_layer_forward_bf16  x bf16 [N,Fin]; out bf16 [N,Fout]; agg bf16 [N,Fin]; xhat fp32, rstd fp32 (or NULL)
+ *   sldm_sage_layer_backward_bf16 x, agg bf16; everything else as sldm_sage_layer_backward_stages (fp32)
+ * Shapes: Fin in {64, 128}, Fout % 32 == 0, 32 <= Fout <= 128 (sldm_sage_bf16_supported); otherwise
+ * SLDM_EUNSUPPORTED and the caller converts to fp32.  Workspace sizes are those of the fp32 entry points. */
+int sldm_sage_bf16_supported(int32_t Fin, int32_t Fout);
+int sldm_segment_mean_bf16(const void* src, int64_t N, int32_t F, const int32_t* csr, int64_t E, void* out,
+                           void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
+int sldm_sage_layer_forward_bf16(const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                                 const int32_t* csr, int64_t E,
+                                 const float* W_l, const float* b_l, const float* W_r,
+                                 const float* ln_w, const float* ln_b, float eps, float slope,
+                                 void* out, void* agg, float* xhat_out, float* rstd_out,
+                                 void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
+int sldm_sage_layer_backward_bf16(const float* dout, const void* x, const void* agg,
+                                  const float* xhat, const float* rstd,
+                                  int64_t N, int32_t Fin, int32_t Fout,
+                                  const int32_t* csr, int64_t E,
+                                  const float* W_l, const float* W_r,
+                                  const float* ln_w, const float* ln_b, float slope,
+                                  float* dx, float* dW_l, float* db_l, float* dW_r,
+                                  float* dln_w, float* dln_b,
+                                  float* dz, float* dagg, float* dxroot,
+                                  void* workspace, int64_t workspace_bytes,
+                                  sldm_stream_t stream, int32_t stages);
+
 /* ---- graph readout (the consumer of the SageBlock output) -----------------
  * Replaces global_mean_pool / global_max_pool of PyG 2.7.0 (nn/pool/glob.py -> utils/_scatter.py::scatter with
  * reduce='mean' / 'max') as used at src/models/grusage.py:113-120 (choice) and :185 (x = self.global_pool(x, batch)):

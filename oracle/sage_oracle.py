@@ -137,6 +137,35 @@ class SageBlockOracle(nn.Module):
         return x
 
 
+# ---- bf16 feature storage (an addition of the product, BASELINE configs[4]; the reference has no such mode) --------
+class _RoundBf16(torch.autograd.Function):
+    """Round to bfloat16 (nearest even) and back; the gradient passes straight through -- the product's backward
+    works in fp32 on the stored (rounded) values and never differentiates the rounding."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class SageBlockBf16Oracle(SageBlockOracle):
+    """SageBlockOracle with the three stored feature matrices of every layer rounded to bf16 where the bf16 kernels
+    round them: the layer input x (given already rounded), the aggregated rows, the layer output.  All arithmetic
+    in between is the oracle's fp32 (or fp64) arithmetic."""
+
+    def forward(self, x, edge_index):
+        rnd = _RoundBf16.apply
+        x = rnd(x)
+        for conv, post in zip(self.convs, self.posts):
+            check_edge_index(edge_index)
+            agg = rnd(conv.aggregate(x, edge_index))
+            x = rnd(post(conv.lin_l(agg) + conv.lin_r(x)))
+        return x
+
+
 # ---- one layer, forward + backward, for graphs too large to materialise [E, F] -----
 def layer_fwd_bwd_chunked(x, ei, state, hdims, slope, w, dtype, chunk=1_000_000):
     """One SageBlock layer fwd+bwd on a graph too large to materialise [E, F] in fp64: the aggregation (a3/a4 of SURVEY

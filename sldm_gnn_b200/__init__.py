@@ -9,7 +9,7 @@ fallback.
 from . import _lib  # noqa: F401  (raises ImportError if the CUDA library is missing)
 from . import ops
 from .ops import Csr, build_csr, segment_reduce
-from .sageblock import SageBlock, SageConvParams
+from .sageblock import SageBlock, SageConvParams, GraphedSageBlock
 from .shim import install_reference_shim
 from .readout import global_mean_pool, global_max_pool, global_mean_max_pool
 from .collate import GraphData, GraphBatch, collate
@@ -17,6 +17,6 @@ from .map_attention import MapSpatialAttention
 from .edges import build_proximity_edges
 from .grusage import GruSage, MapEncoder, MapZscoreNorm
 
-__all__ = ["SageBlock", "SageConvParams", "Csr", "build_csr", "segment_reduce", "ops", "install_reference_shim",
+__all__ = ["SageBlock", "SageConvParams", "GraphedSageBlock", "Csr", "build_csr", "segment_reduce", "ops", "install_reference_shim",
            "global_mean_pool", "global_max_pool", "global_mean_max_pool", "GraphData", "GraphBatch", "collate",
            "MapSpatialAttention", "build_proximity_edges", "GruSage", "MapEncoder", "MapZscoreNorm"]

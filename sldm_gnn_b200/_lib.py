@@ -53,6 +53,12 @@ _PROTOS = {
                                            _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "sldm_sage_layer_backward_stages": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _f,
                                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i32]),
+    "sldm_sage_bf16_supported": (C.c_int, [_i32, _i32]),
+    "sldm_segment_mean_bf16": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p]),
+    "sldm_sage_layer_forward_bf16": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _p, _f, _f,
+                                               _p, _p, _p, _p, _p, _i64, _p]),
+    "sldm_sage_layer_backward_bf16": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _f,
+                                                _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i32]),
     "sldm_readout_workspace_bytes": (_i64, [_i64, _i32]),
     "sldm_readout_forward": (C.c_int, [_p, _i64, _i32, _p, _i64, _i64, _p, _p, _i64, _p]),
     "sldm_readout_backward": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _p, _p, _i64, _p]),

@@ -108,17 +108,17 @@ extern "C" int sldm_sage_layer_backward(const float* dout, const float* x, const
                                          workspace_bytes, stream, SLDM_BWD_STAGE_ALL);
 }
 
-extern "C" int sldm_sage_layer_backward_stages(const float* dout, const float* x, const float* agg,
-                                               const float* xhat, const float* rstd,
-                                               int64_t N, int32_t Fin, int32_t Fout,
-                                               const int32_t* csr, int64_t E,
-                                               const float* W_l, const float* W_r,
-                                               const float* ln_w, const float* ln_b, float slope,
-                                               float* dx, float* dW_l, float* db_l, float* dW_r,
-                                               float* dln_w, float* dln_b,
-                                               float* dz, float* dagg, float* dxroot,
-                                               void* workspace, int64_t workspace_bytes,
-                                               sldm_stream_t stream, int32_t stages) {
+static int layer_backward_impl(const float* dout, const float* x, const float* agg,
+                               const float* xhat, const float* rstd,
+                               int64_t N, int32_t Fin, int32_t Fout,
+                               const int32_t* csr, int64_t E,
+                               const float* W_l, const float* W_r,
+                               const float* ln_w, const float* ln_b, float slope,
+                               float* dx, float* dW_l, float* db_l, float* dW_r,
+                               float* dln_w, float* dln_b,
+                               float* dz, float* dagg, float* dxroot,
+                               void* workspace, int64_t workspace_bytes,
+                               sldm_stream_t stream, int32_t stages, bool bf16_feats) {
   SLDM_REQUIRE(N >= 0 && E >= 0, SLDM_EINVAL, "sldm_sage_layer_backward: negative N or E");
   SLDM_REQUIRE(Fin >= 1 && Fout >= 1, SLDM_ESHAPE, "sldm_sage_layer_backward: Fin=%d Fout=%d", Fin, Fout);
   SLDM_REQUIRE(dW_l && db_l && dW_r && dln_w && dln_b, SLDM_EINVAL, "sldm_sage_layer_backward: NULL gradient output");
@@ -137,11 +137,74 @@ extern "C" int sldm_sage_layer_backward_stages(const float* dout, const float* x
   if (N > 0) rowptr_dst = csr + csr_layout(N, E).off[SLDM_CSR_ROWPTR_DST];
   int rc = layer_backward_launch(dout, x, agg, xhat, rstd, N, Fin, Fout, rowptr_dst, W_l, W_r, ln_w, ln_b, slope,
                                  need_dx, dW_l, db_l, dW_r, dln_w, dln_b, dz, dagg, dxroot,
-                                 static_cast<char*>(workspace) + seg_ws, workspace_bytes - seg_ws, s, stages);
+                                 static_cast<char*>(workspace) + seg_ws, workspace_bytes - seg_ws, s, stages, bf16_feats);
   if (rc || !need_dx || N == 0 || !(stages & SLDM_BWD_STAGE_GATHER)) return rc;
   // dx[j] = dxroot[j] + sum_{e: src[e]=j} dagg[dst[e]]   (dagg already divided by the count)
   return sldm_segment_reduce(dagg, N, Fin, csr, E, /*transpose=*/1, /*mean=*/0, dxroot, dx,
                              workspace, seg_ws, stream);
+}
+
+extern "C" int sldm_sage_layer_backward_stages(const float* dout, const float* x, const float* agg,
+                                               const float* xhat, const float* rstd,
+                                               int64_t N, int32_t Fin, int32_t Fout,
+                                               const int32_t* csr, int64_t E,
+                                               const float* W_l, const float* W_r,
+                                               const float* ln_w, const float* ln_b, float slope,
+                                               float* dx, float* dW_l, float* db_l, float* dW_r,
+                                               float* dln_w, float* dln_b,
+                                               float* dz, float* dagg, float* dxroot,
+                                               void* workspace, int64_t workspace_bytes,
+                                               sldm_stream_t stream, int32_t stages) {
+  return layer_backward_impl(dout, x, agg, xhat, rstd, N, Fin, Fout, csr, E, W_l, W_r, ln_w, ln_b, slope, dx, dW_l, db_l,
+                             dW_r, dln_w, dln_b, dz, dagg, dxroot, workspace, workspace_bytes, stream, stages, false);
+}
+
+// ------------------------------------------------------ bf16 feature storage --
+extern "C" int sldm_sage_bf16_supported(int32_t Fin, int32_t Fout) {
+  return (Fin % 64 == 0 && Fin >= 64 && Fin <= 128 && Fout % 32 == 0 && Fout >= 32 && Fout <= 128) ? 1 : 0;
+}
+
+extern "C" int sldm_sage_layer_forward_bf16(const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                                            const int32_t* csr, int64_t E,
+                                            const float* W_l, const float* b_l, const float* W_r,
+                                            const float* ln_w, const float* ln_b, float eps, float slope,
+                                            void* out, void* agg, float* xhat_out, float* rstd_out,
+                                            void* workspace, int64_t workspace_bytes, sldm_stream_t stream) {
+  SLDM_REQUIRE(N >= 0 && E >= 0, SLDM_EINVAL, "sldm_sage_layer_forward_bf16: negative N or E");
+  SLDM_REQUIRE(sldm_sage_bf16_supported(Fin, Fout), SLDM_EUNSUPPORTED,
+               "sldm_sage_layer_forward_bf16: Fin=%d Fout=%d (needs Fin in {64,128}, Fout %% 32 == 0, Fout <= 128)", Fin, Fout);
+  if (N == 0) return SLDM_OK;
+  SLDM_REQUIRE(x && csr && W_l && b_l && W_r && ln_w && ln_b && out && agg, SLDM_EINVAL,
+               "sldm_sage_layer_forward_bf16: NULL pointer");
+  SLDM_REQUIRE(project_forward_bf16_eligible(N, Fin, Fout, agg, x, out, xhat_out), SLDM_EUNSUPPORTED,
+               "sldm_sage_layer_forward_bf16: buffers must be 16-byte aligned (and SLDM_DISABLE_TC unset)");
+  const int64_t seg_ws = sldm_segment_workspace_bytes(N, E, Fin);
+  const int64_t need = seg_ws + project_forward_ws_bytes(N, Fin, Fout);
+  SLDM_REQUIRE(workspace != nullptr && workspace_bytes >= need, SLDM_EWORKSPACE,
+               "sldm_sage_layer_forward_bf16: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+  int rc = sldm_segment_mean_bf16(x, N, Fin, csr, E, agg, workspace, seg_ws, stream);
+  if (rc) return rc;
+  return project_forward_bf16_launch(agg, x, N, Fin, Fout, W_l, b_l, W_r, ln_w, ln_b, eps, slope, out, xhat_out,
+                                     rstd_out, static_cast<char*>(workspace) + seg_ws, workspace_bytes - seg_ws,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sldm_sage_layer_backward_bf16(const float* dout, const void* x, const void* agg,
+                                             const float* xhat, const float* rstd,
+                                             int64_t N, int32_t Fin, int32_t Fout,
+                                             const int32_t* csr, int64_t E,
+                                             const float* W_l, const float* W_r,
+                                             const float* ln_w, const float* ln_b, float slope,
+                                             float* dx, float* dW_l, float* db_l, float* dW_r,
+                                             float* dln_w, float* dln_b,
+                                             float* dz, float* dagg, float* dxroot,
+                                             void* workspace, int64_t workspace_bytes,
+                                             sldm_stream_t stream, int32_t stages) {
+  SLDM_REQUIRE(sldm_sage_bf16_supported(Fin, Fout), SLDM_EUNSUPPORTED,
+               "sldm_sage_layer_backward_bf16: Fin=%d Fout=%d (needs Fin in {64,128}, Fout %% 32 == 0, Fout <= 128)", Fin, Fout);
+  return layer_backward_impl(dout, static_cast<const float*>(x), static_cast<const float*>(agg), xhat, rstd, N, Fin,
+                             Fout, csr, E, W_l, W_r, ln_w, ln_b, slope, dx, dW_l, db_l, dW_r, dln_w, dln_b, dz, dagg,
+                             dxroot, workspace, workspace_bytes, stream, stages, true);
 }
 
 // -------------------------------------------------- host buffers in and out --

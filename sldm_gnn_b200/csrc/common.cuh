@@ -108,7 +108,8 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
                           bool need_dx,
                           float* dW_l, float* db_l, float* dW_r, float* dln_w, float* dln_b,
                           float* dz, float* dagg, float* dxroot,
-                          void* ws, int64_t ws_bytes, cudaStream_t s, int stages = SLDM_BWD_STAGE_ALL);
+                          void* ws, int64_t ws_bytes, cudaStream_t s, int stages = SLDM_BWD_STAGE_ALL,
+                          bool bf16_feats = false);   // bf16_feats: x and agg point at bf16 rows
 int64_t layer_backward_ws_bytes(int64_t N, int32_t Fin, int32_t Fout);
 
 bool dgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* dagg, const float* dxroot);
@@ -119,8 +120,16 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
 
 bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* agg, const float* x);
 int64_t wgrad_tc_ws_bytes(int32_t Fin, int32_t Fout);
-int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
-                    float* part, int* nparts, cudaStream_t s);
+int wgrad_tc_launch(const float* dz, const void* agg, const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                    float* part, int* nparts, cudaStream_t s, bool bf16_ops = false);
+bool wgrad_bf16_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const void* agg, const void* x);
+// bf16 feature storage (sage_tc.cu): agg / x / out bf16, everything else fp32
+bool project_forward_bf16_eligible(int64_t N, int32_t Fin, int32_t Fout, const void* agg, const void* x,
+                                   const void* out, const float* xhat);
+int project_forward_bf16_launch(const void* agg, const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                                const float* W_l, const float* b_l, const float* W_r,
+                                const float* ln_w, const float* ln_b, float eps, float slope,
+                                void* out, float* xhat, float* rstd, void* ws, int64_t ws_bytes, cudaStream_t s);
 
 // ---- device helpers -----------------------------------------------------------
 // exclusive scan of one int per thread across a 256-thread CTA; returns this thread's prefix, `total` to every thread.
@@ -152,6 +161,14 @@ __device__ __forceinline__ int block_exclusive_scan_256(int v, int& total, int* 
   __syncthreads();
   return prefix;
 }
+
+// round-to-nearest-even fp32 -> bf16 bits (NaN stays NaN through the quiet bit)
+__device__ __forceinline__ uint32_t bf16_rn(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u);
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) { return bf16_rn(lo) | (bf16_rn(hi) << 16); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -544,8 +544,12 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
                           bool need_dx,
                           float* dW_l, float* db_l, float* dW_r, float* dln_w, float* dln_b,
                           float* dz, float* dagg, float* dxroot,
-                          void* ws, int64_t ws_bytes, cudaStream_t s, int stages) {
+                          void* ws, int64_t ws_bytes, cudaStream_t s, int stages, bool bf16_feats) {
   SLDM_REQUIRE(Fin >= 1 && Fout >= 1, SLDM_ESHAPE, "backward: Fin=%d Fout=%d must be >= 1", Fin, Fout);
+  // bf16 feature storage: x and agg are bf16 rows (only the weight gradient reads them); needs the tensor path
+  SLDM_REQUIRE(!bf16_feats || N == 0 || (wgrad_bf16_eligible(N, Fin, Fout, dz, agg, x) &&
+                                         (!need_dx || dgrad_tc_eligible(N, Fin, Fout, dz, dagg, dxroot))),
+               SLDM_EUNSUPPORTED, "backward (bf16 features): needs Fin %% 64 == 0, Fin <= 128, Fout %% 32 == 0, Fout <= 128");
   SLDM_REQUIRE(Fout <= 256, SLDM_EUNSUPPORTED, "backward: Fout=%d > 256 is not covered by the kernels", Fout);
   const int64_t wcount = (int64_t)Fout * Fin;
   if (N == 0) {  // empty batch: all parameter gradients are zero
@@ -607,9 +611,9 @@ int layer_backward_launch(const float* dout, const float* x, const float* agg,
 
   if (!(stages & SLDM_BWD_STAGE_WGRAD)) return SLDM_OK;
   int nparts = p.S;
-  if (wgrad_tc_eligible(N, Fin, Fout, dz, agg, x)) {
+  if (bf16_feats || wgrad_tc_eligible(N, Fin, Fout, dz, agg, x)) {
     part = reinterpret_cast<float*>(static_cast<char*>(ws) + p.wg_off);
-    if ((rc = wgrad_tc_launch(dz, agg, x, N, Fin, Fout, part, &nparts, s))) return rc;
+    if ((rc = wgrad_tc_launch(dz, agg, x, N, Fin, Fout, part, &nparts, s, bf16_feats))) return rc;
   } else {
     dim3 grid(p.S, 2 * p.MB * p.NB);
     const int vec_m = (Fout % 4 == 0) && b16(dz);

@@ -13,7 +13,7 @@
 // fp64 (tools/tc_probe2.cu, K=128): max 3.2e-7 / rms 7.3e-8 versus 7.8e-7 / 1.1e-7 for a
 // sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
 //
-// Pipeline (one persistent CTA per SM, 896 threads = 7 warpgroups, 128 rows x Fout per tile; setmaxnreg 40 / 72 / 80 / 64):
+// Pipeline (one persistent CTA per SM, 896 threads = 7 warpgroups, 128 rows x Fout per tile; setmaxnreg 56 / 72 / 80 / 56 of the 72 x 896 pool):
 //   warp 0        TMA producer A: raw activation chunks [128 x 32] (agg, then x) into a 5-deep ring -- the HBM stream;
 //                                a stage is handed back by the CONVERTER as soon as the tile is in registers
 //   warp 2        TMA producer B: pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk into a 2-deep ring (L2 hits)
@@ -256,7 +256,7 @@ struct FinArgs {
 // (lane = 4 consecutive columns), RPI = 32 / LPRW rows per instruction (NT = 3: 24 of 32 lanes active), U of them in
 // flight.  FWD: the parked values are xhat: store it (training), then the affine + (Leaky)ReLU and the output store.
 // DGRAD: plain copy to dagg | dxroot.  Every store instruction writes whole rows (512 B at Fout = 128).
-template <int NT, int MODE>
+template <int NT, int MODE, bool ABF>
 __device__ __forceinline__ void finisher_role(const FinArgs a) {
   constexpr int LPRW = (NT == 1) ? 8 : (NT == 2) ? 16 : 32;
   constexpr int RPI = 32 / LPRW;
@@ -309,7 +309,12 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
               y.z = fmaf(v[u].z, gam4.z, bet4.z); y.w = fmaf(v[u].w, gam4.w, bet4.w);
               y.x = y.x > 0.f ? y.x : a.slope * y.x; y.y = y.y > 0.f ? y.y : a.slope * y.y;
               y.z = y.z > 0.f ? y.z : a.slope * y.z; y.w = y.w > 0.f ? y.w : a.slope * y.w;
-              *reinterpret_cast<float4*>(o_main + row * Fout + c0) = y;
+              if constexpr (ABF) {     // bf16 feature storage: the layer output is rounded once, here
+                uint16_t* const ob = reinterpret_cast<uint16_t*>(o_main);
+                *reinterpret_cast<uint2*>(ob + row * Fout + c0) = make_uint2(pack2_bf16(y.x, y.y), pack2_bf16(y.z, y.w));
+              } else {
+                *reinterpret_cast<float4*>(o_main + row * Fout + c0) = y;
+              }
             } else {
               *reinterpret_cast<float4*>(o_main + row * Fout + c0) = v[u];
             }
@@ -321,7 +326,11 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
   }
 }
 
-template <int NT, int MODE>  // NT = ceil(Nout / 32) in 1..4
+// ABF (forward only): the A sources (agg, x) are bf16 rows.  TMA moves them as 32-bit words (a raw chunk [128 x 32
+// words] carries 64 K values), the converter unpacks a word into its two bf16 values -- both EXACT in tf32, so there
+// is no a_lo: a TMEM slot holds the 64 K values of the chunk and every k-step costs two MMAs (a*b_lo, a*b_hi)
+// instead of three; the weight tiles stay 32-K stages, two per raw chunk.  The output is stored as bf16.
+template <int NT, int MODE, bool ABF>  // NT = ceil(Nout / 32) in 1..4
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CUtensorMap tm_x,
           const __grid_constant__ CUtensorMap tm_w, const TcProblem pb,
@@ -390,7 +399,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
 
   // warpgroups 0 and 1 hand registers to the two epilogue warpgroups (setmaxnreg is per warpgroup)
   if (warp < 4) {
-   reg_dec<40>();
+   reg_dec<56>();
    if (warp == 0) {
     // ---------------------------------------------------------- TMA producer: A --
     // raw activation chunks, kTcStages deep: this is the HBM stream, it keeps running while the epilogue finishes a tile
@@ -425,14 +434,15 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int g = 0; g < ngroups; ++g) {
-          for (int c = 0; c < nchunks; ++c, ++it) {
+          for (int c = 0; c < nchunks * (ABF ? 2 : 1); ++c, ++it) {    // ABF: two 32-K weight stages per raw chunk
             const uint32_t s = it % kTcBStages, ph = (it / kTcBStages) & 1;
             if (lane == 0) TC_TRACE(29, it);
             mbar_wait(&bar_bempty[s], ph ^ 1);
             if (lane == 0) TC_TRACE(30, it);
             const uint32_t st = smem_b_u + s * 2u * b_bytes;
-            const int src = c / half;
-            const int k0 = (c - src * half) * 32;
+            const int cc = ABF ? (c >> 1) : c;
+            const int src = cc / half;
+            const int k0 = ABF ? ((cc - src * half) * 64 + 32 * (c & 1)) : ((cc - src * half) * 32);
             const int wrow = 2 * (g * pb.nsrc + src) * Fout;
             if (elect_one()) {
               mbar_expect_tx(&bar_bfull[s], 2 * b_bytes);
@@ -471,6 +481,34 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           if (lane == 0) TC_TRACE(3, it);
           mbar_wait(&bar_conv[asl], aslph);         // a_hi | a_lo of this chunk are in the TMEM slot
           if (lane == 0) TC_TRACE(28, it);
+          const uint32_t a_hi = tmem_u + kTcACol0 + asl * 64;
+          const uint32_t a_lo = a_hi + 32;
+          const uint32_t d = tmem_u + ab * ACC_COLS;
+          if constexpr (ABF) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t itb = 2u * it + h;
+              const uint32_t sbh = itb % kTcBStages, bphh = (itb / kTcBStages) & 1;
+              mbar_wait(&bar_bfull[sbh], bphh);
+              tc_fence_after();
+              const uint64_t db_hi = make_smem_desc_sw128(smem_b_u + sbh * 2u * b_bytes, 16, 1024);
+              const uint64_t db_lo = db_hi + (b_bytes >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 32 * h + 8 * ks, db_lo + 2 * ks, idesc, (h | ks) ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(d, a_hi + 32 * h + 8 * ks, db_hi + 2 * ks, idesc, 1u);
+                mma_commit(&bar_bempty[sbh]);
+                if (h == 1) {
+                  mma_commit(&bar_afree[asl]);
+                  mma_commit(&bar_acc_full[ab]);
+                }
+              }
+              __syncwarp();
+            }
+            if (lane == 0) TC_TRACE(5, it);
+            continue;
+          }
           mbar_wait(&bar_bfull[sb], bph);           // weight tiles of this chunk have landed
           if (lane == 0) TC_TRACE(4, it);
           tc_fence_after();
@@ -478,9 +516,6 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           // B descriptors differ only in the 14-bit start-address field (bytes >> 4); A comes from tensor memory
           const uint64_t d_b_hi = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t d_b_lo = d_b_hi + (b_bytes >> 4);
-          const uint32_t a_hi = tmem_u + kTcACol0 + asl * 64;
-          const uint32_t a_lo = a_hi + 32;
-          const uint32_t d = tmem_u + ab * ACC_COLS;
           if (elect_one()) {
             // small products first: the accumulator rounds toward zero
 #pragma unroll
@@ -532,8 +567,17 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
             const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              hi[4 * j + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
-              lo[4 * j + e] = __float_as_uint(tf32_lo(f[e]));
+              if constexpr (ABF) {
+                // a 32-bit word = two bf16 values (low half = even K index); hi[] takes K values 16h .. 16h+15 of
+                // this half's 32, lo[] the next 16 -- both exact, no remainder term
+                const uint32_t w = __float_as_uint(f[e]);
+                uint32_t* const dst = (j < 2) ? hi : lo;
+                dst[8 * (j & 1) + 2 * e] = w << 16;
+                dst[8 * (j & 1) + 2 * e + 1] = w & 0xFFFF0000u;
+              } else {
+                hi[4 * j + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
+                lo[4 * j + e] = __float_as_uint(tf32_lo(f[e]));
+              }
             }
           }
           if (h == 0) {
@@ -542,8 +586,13 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
             mbar_wait(&bar_afree[asl], aslph ^ 1);
             tc_fence_after();
           }
-          tmem_st_32x16(t_hi + 16 * h, hi);
-          tmem_st_32x16(t_hi + 32 + 16 * h, lo);
+          if constexpr (ABF) {           // K values 32h .. 32h+31 of the chunk's 64
+            tmem_st_32x16(t_hi + 32 * h, hi);
+            tmem_st_32x16(t_hi + 32 * h + 16, lo);
+          } else {
+            tmem_st_32x16(t_hi + 16 * h, hi);
+            tmem_st_32x16(t_hi + 32 + 16 * h, lo);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -553,16 +602,16 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       }
     }
   } else if (warp < 24) {
-    reg_inc<88>();
+    reg_inc<80>();
     // ------------------------------------------------------------------- drain --
     DrainArgs da{N, Fout, ntiles, nchunks, ngroups, eps, tmem_base, smem_u32(smem_z), rstd, rowptr, s_bias,
                  &s_sum[0][0][0], &s_var[0][0][0], bar_acc_full, bar_acc_empty, bar_z_full, bar_z_empty, trace};
     if (Fout == 32 * NT) drain_role<NT, true, MODE>(da); else drain_role<NT, false, MODE>(da);
   } else {
-    reg_dec<40>();
+    reg_dec<56>();
     // ---------------------------------------------------------------- finisher --
     FinArgs fa{N, Fout, ntiles, ngroups, slope, out, xhat, smem_u32(smem_z), gamma, beta, bar_z_full, bar_z_empty, trace};
-    finisher_role<NT, MODE>(fa);
+    finisher_role<NT, MODE, ABF>(fa);
   }
   tc_fence_before();
   __syncthreads();
@@ -584,7 +633,13 @@ constexpr int kWgStages = 4;                // 4 x 48 KB: the fixed TMA latency 
 constexpr int kWgFlush = 128 / kWgRows;     // chunks per TMEM accumulator (128 rows)
 constexpr uint32_t kWgBlk = kWgRows * 128;  // bytes of one [kWgRows x 32 floats] operand block
 
-template <int NB>   // NB = ceil(Fin / 32) in 1..4
+// BBF: agg and x are bf16 rows.  TMA moves them as 32-bit words ([kWgRows x 32 words] blocks, NB/2 per source); the
+// converter splits every word IN PLACE into its odd-column value (w & 0xFFFF0000) and writes the even-column value
+// (w << 16) NB blocks further on -- both exact in tf32, so the operand needs no lo part and a k-step costs two MMAs.
+// The accumulator columns then come out as [odd(agg) | odd(x) | even(agg) | even(x)]; the epilogue undoes that
+// permutation when it writes the partial.  (No knowledge of the swizzle pattern is needed: a word stays where TMA
+// put it.)  Needs Fin % 64 == 0.
+template <int NB, bool BBF>   // NB = ceil(Fin / 32) in 1..4
 __global__ void __launch_bounds__(kWgThreads, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_agg,
            const __grid_constant__ CUtensorMap tm_x, int64_t N, int Fin, int Fout, int chunks_per_cta,
@@ -632,13 +687,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
         const uint32_t st = smem_u + s * STAGE_BYTES;
         const int r0 = (int)((c_beg + it) * kWgRows);
         if (elect_one()) {
-          mbar_expect_tx(&bar_full[s], RAW_BYTES);
+          constexpr int NBS = BBF ? NB / 2 : NB;         // TMA blocks per source (bf16 rows are half as many words)
+          mbar_expect_tx(&bar_full[s], A_BYTES + 2 * NBS * kWgBlk);
 #pragma unroll
           for (int b = 0; b < 4; ++b) tma_load_2d_u32(st + b * kWgBlk, &tm_dz, b * 32, r0, &bar_full[s]);
 #pragma unroll
-          for (int b = 0; b < NB; ++b) tma_load_2d_u32(st + A_BYTES + b * kWgBlk, &tm_agg, b * 32, r0, &bar_full[s]);
+          for (int b = 0; b < NBS; ++b) tma_load_2d_u32(st + A_BYTES + b * kWgBlk, &tm_agg, b * 32, r0, &bar_full[s]);
 #pragma unroll
-          for (int b = 0; b < NB; ++b) tma_load_2d_u32(st + A_BYTES + (NB + b) * kWgBlk, &tm_x, b * 32, r0, &bar_full[s]);
+          for (int b = 0; b < NBS; ++b) tma_load_2d_u32(st + A_BYTES + (NBS + b) * kWgBlk, &tm_x, b * 32, r0, &bar_full[s]);
         }
         __syncwarp();
       }
@@ -665,8 +721,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_lo + 64 * ks, d_b_hi + 64 * ks, idesc, (first && ks == 0) ? 0u : 1u);
+          if constexpr (!BBF) {
 #pragma unroll
-          for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
+            for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_lo + 64 * ks, idesc, 1u);
+          }
 #pragma unroll
           for (int ks = 0; ks < kWgRows / 8; ++ks) mma_tf32_ss(d, d_a_hi + 64 * ks, d_b_hi + 64 * ks, idesc, 1u);
           mma_commit(&bar_empty[s]);
@@ -683,6 +741,28 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
       const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
       mbar_wait(&bar_full[s], ph);
       const uint32_t raw = smem_u32(smem + (size_t)s * STAGE_BYTES);
+      if constexpr (BBF) {
+        constexpr int NVA = A_BYTES / 16 / 128;          // dz: lo part as usual
+#pragma unroll
+        for (int i = 0; i < NVA; ++i) {
+          const uint32_t off = (uint32_t)(t + i * 128) * 16;
+          const float4 v = lds128(raw + off);
+          float4 l;
+          l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+          sts128(raw + RAW_BYTES + off, l);
+        }
+        constexpr int NVB = NB * kWgBlk / 16 / 128;      // [agg | x] words: odd values in place, even values NB blocks on
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+          const uint32_t off = A_BYTES + (uint32_t)(t + i * 128) * 16;
+          const float4 v = lds128(raw + off);
+          const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+          sts128(raw + off, make_float4(__uint_as_float(w[0] & 0xFFFF0000u), __uint_as_float(w[1] & 0xFFFF0000u),
+                                        __uint_as_float(w[2] & 0xFFFF0000u), __uint_as_float(w[3] & 0xFFFF0000u)));
+          sts128(raw + off + NB * kWgBlk, make_float4(__uint_as_float(w[0] << 16), __uint_as_float(w[1] << 16),
+                                                      __uint_as_float(w[2] << 16), __uint_as_float(w[3] << 16)));
+        }
+      } else {
       constexpr int NV = RAW_BYTES / 16 / 128;   // float4 per thread
 #pragma unroll 4
       for (int i = 0; i < NV; ++i) {
@@ -691,6 +771,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
         float4 l;
         l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
         sts128(raw + RAW_BYTES + off, l);
+      }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -728,10 +809,20 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CU
     }
     // partial of this CTA: part[cta][hf][m][n], n < Fin
     if (m < Fout) {
-      float* dst = part + (((int64_t)blockIdx.x * 2 + hf) * Fout + m) * Fin;
+      if constexpr (BBF) {
+        // accumulator half hf = odd (0) / even (1) feature columns; inside: [agg blocks (NB/2) | x blocks (NB/2)]
 #pragma unroll
-      for (int j = 0; j < HC; ++j)
-        if (j < Fin) dst[j] = acc[j];
+        for (int j = 0; j < HC; ++j) {
+          const int blk = j >> 5, src = blk / (NB / 2), word = (blk % (NB / 2)) * 32 + (j & 31);
+          const int col = 2 * word + (hf == 0 ? 1 : 0);
+          if (col < Fin) part[(((int64_t)blockIdx.x * 2 + src) * Fout + m) * Fin + col] = acc[j];
+        }
+      } else {
+        float* dst = part + (((int64_t)blockIdx.x * 2 + hf) * Fout + m) * Fin;
+#pragma unroll
+        for (int j = 0; j < HC; ++j)
+          if (j < Fin) dst[j] = acc[j];
+      }
     }
   }
   tc_fence_before();
@@ -777,12 +868,12 @@ k_split_weights_t(const float* __restrict__ W_l, const float* __restrict__ W_r, 
   }
 }
 
-template <int NT, int MODE>
+template <int NT, int MODE, bool ABF = false>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   const size_t smem = (size_t)kTcStages * kTcBM * 128 + (size_t)kTcBStages * 2 * pb.Nout * 128 + kTcZBytes + 1024;
-  SLDM_OPT_IN_SMEM((k_sage_tc<NT, MODE>), kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcZBytes + 1024);
+  SLDM_OPT_IN_SMEM((k_sage_tc<NT, MODE, ABF>), kTcStages * kTcBM * 128 + kTcBStages * 2 * 128 * 128 + kTcZBytes + 1024);
   const int64_t ntiles = ceil_div<int64_t>(pb.N, kTcBM);
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
   long long* trace = nullptr;
@@ -791,7 +882,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     SLDM_CUDA(cudaMalloc(&trace, sizeof(long long) * kTraceIts * kTraceEv));
     SLDM_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * kTraceIts * kTraceEv, s));
   }
-  k_sage_tc<NT, MODE><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
+  k_sage_tc<NT, MODE, ABF><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
   SLDM_LAUNCH_CHECK("k_sage_tc");
   if (trace) {
     static long long h[kTraceIts * kTraceEv];
@@ -815,15 +906,15 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
   return SLDM_OK;
 }
 
-template <int MODE>
+template <int MODE, bool ABF = false>
 static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
                        const float* b_l, const float* g, const float* b, float eps, float slope,
                        float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   switch (ceil_div(pb.Nout, 32)) {
-    case 1: return launch_tc<1, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 2: return launch_tc<2, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 3: return launch_tc<3, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    default: return launch_tc<4, MODE>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 1: return launch_tc<1, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 2: return launch_tc<2, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 3: return launch_tc<3, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    default: return launch_tc<4, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
   }
 }
 
@@ -844,6 +935,33 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
   return dispatch_tc<MODE_FWD>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
+}
+
+// bf16 feature storage: agg, x and out are bf16 rows ([N,Fin] / [N,Fout] uint16), weights / LayerNorm / xhat / rstd fp32
+bool project_forward_bf16_eligible(int64_t N, int32_t Fin, int32_t Fout, const void* agg, const void* x,
+                                   const void* out, const float* xhat) {
+  return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fin % 64 == 0 && Fin >= 64 && Fin <= 256 &&
+         Fout % 16 == 0 && Fout >= 16 && Fout <= 128 && p16(agg) && p16(x) && p16(out) && p16(xhat);
+}
+int project_forward_bf16_launch(const void* agg, const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                                const float* W_l, const float* b_l, const float* W_r,
+                                const float* ln_w, const float* ln_b, float eps, float slope,
+                                void* out, float* xhat, float* rstd, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  SLDM_REQUIRE(ws != nullptr && ws_bytes >= project_forward_tc_ws_bytes(Fin, Fout), SLDM_EWORKSPACE,
+               "projection (bf16 features): workspace too small");
+  float* wsplit = static_cast<float*>(ws);
+  const int count = Fin * Fout;
+  k_split_weights<<<ceil_div(2 * count, 256 * 4), 256, 0, s>>>(W_l, W_r, count, wsplit);
+  SLDM_LAUNCH_CHECK("k_split_weights");
+  CUtensorMap ma, mx, mw;
+  int rc;
+  // the bf16 rows travel as 32-bit words: [N][Fin/2]
+  if ((rc = make_tmap_2d_f32(&ma, static_cast<const float*>(agg), (uint64_t)N, Fin / 2, Fin / 2, kTcBM, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&mx, static_cast<const float*>(x), (uint64_t)N, Fin / 2, Fin / 2, kTcBM, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
+  TcProblem pb{N, Fin / 64, 2, 1, Fout};
+  return dispatch_tc<MODE_FWD, true>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, static_cast<float*>(out), xhat, rstd,
+                                     nullptr, s);
 }
 
 // dagg[N,Fin] = (dz W_l) / max(deg,1) ; dxroot[N,Fin] = dz W_r          (dz is [N,Fout])
@@ -870,24 +988,32 @@ bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, co
 int wgrad_tc_grid() { return num_sms(); }
 int64_t wgrad_tc_ws_bytes(int32_t Fin, int32_t Fout) { return align_bytes((int64_t)wgrad_tc_grid() * 2 * Fin * Fout * 4); }
 
-template <int NB>
+template <int NB, bool BBF = false>
 static int launch_wgrad(const CUtensorMap& mz, const CUtensorMap& ma, const CUtensorMap& mx, int64_t N, int Fin,
                         int Fout, int cpc, int grid, float* part, cudaStream_t s) {
   const size_t smem = (size_t)kWgStages * 2 * (4 + 2 * NB) * kWgBlk + 1024;
-  SLDM_OPT_IN_SMEM(k_wgrad_tc<NB>, smem);
-  k_wgrad_tc<NB><<<grid, kWgThreads, smem, s>>>(mz, ma, mx, N, Fin, Fout, cpc, part);
+  SLDM_OPT_IN_SMEM((k_wgrad_tc<NB, BBF>), smem);
+  k_wgrad_tc<NB, BBF><<<grid, kWgThreads, smem, s>>>(mz, ma, mx, N, Fin, Fout, cpc, part);
   SLDM_LAUNCH_CHECK("k_wgrad_tc");
   return SLDM_OK;
 }
 
-// part[grid][2][Fout][Fin]; returns the number of partials through *nparts
-int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N, int32_t Fin, int32_t Fout,
-                    float* part, int* nparts, cudaStream_t s) {
+bool wgrad_bf16_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const void* agg, const void* x) {
+  return !tc_disabled() && N >= 1 && N < ((int64_t)1 << 31) - 256 && Fin % 64 == 0 && Fout % 4 == 0 && Fin >= 64 &&
+         Fin <= 128 && Fout >= 16 && Fout <= 128 && p16(dz) && p16(agg) && p16(x);
+}
+
+// part[grid][2][Fout][Fin]; returns the number of partials through *nparts.  bf16_ops: agg and x are bf16 rows.
+int wgrad_tc_launch(const float* dz, const void* agg_v, const void* x_v, int64_t N, int32_t Fin, int32_t Fout,
+                    float* part, int* nparts, cudaStream_t s, bool bf16_ops) {
   CUtensorMap mz, ma, mx;
   int rc;
+  const float* agg = static_cast<const float*>(agg_v);
+  const float* x = static_cast<const float*>(x_v);
+  const int Fw = bf16_ops ? Fin / 2 : Fin;          // 32-bit words per operand row
   if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kWgRows, 32, 1))) return rc;
-  if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, kWgRows, 32, 1))) return rc;
-  if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kWgRows, 32, 1))) return rc;
+  if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fw, Fw, kWgRows, 32, 1))) return rc;
+  if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fw, Fw, kWgRows, 32, 1))) return rc;
   const int64_t total_chunks = ceil_div<int64_t>(N, kWgRows);
   int grid = wgrad_tc_grid();
   if (grid > total_chunks) grid = (int)total_chunks;
@@ -895,6 +1021,9 @@ int wgrad_tc_launch(const float* dz, const float* agg, const float* x, int64_t N
   int64_t cpc = round_up<int64_t>(ceil_div<int64_t>(total_chunks, grid), kWgFlush);
   grid = (int)ceil_div<int64_t>(total_chunks, cpc);
   *nparts = grid;
+  if (bf16_ops)
+    return Fin == 64 ? launch_wgrad<2, true>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s)
+                     : launch_wgrad<4, true>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);
   switch (ceil_div(Fin, 32)) {
     case 1: return launch_wgrad<1>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);
     case 2: return launch_wgrad<2>(mz, ma, mx, N, Fin, Fout, (int)cpc, grid, part, s);

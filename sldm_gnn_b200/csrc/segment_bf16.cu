@@ -17,12 +17,6 @@ __device__ __forceinline__ void add8_bf16(float (&acc)[8], const uint4& v) {
   acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xFFFF0000u);
   acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xFFFF0000u);
 }
-// round-to-nearest-even fp32 -> bf16 (finite inputs; NaN stays NaN through the quiet bit)
-__device__ __forceinline__ uint32_t bf16_rn(float f) {
-  uint32_t u = __float_as_uint(f);
-  if ((u & 0x7F800000u) == 0x7F800000u) return (u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u);
-  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
-}
 __device__ __forceinline__ uint4 pack8_bf16(const float (&a)[8]) {
   uint4 r;
   r.x = bf16_rn(a[0]) | (bf16_rn(a[1]) << 16);

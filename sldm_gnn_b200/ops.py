@@ -195,11 +195,37 @@ def project_forward(agg, x, W_l, b_l, W_r, ln_w, ln_b, eps, slope, save: bool):
     return out, xhat, rstd
 
 
+def bf16_supported(Fin: int, Fout: int) -> bool:
+    """Layer shapes the bf16 feature-storage kernels cover (include/sldm_sage.h)."""
+    return bool(lib.sldm_sage_bf16_supported(int(Fin), int(Fout)))
+
+
 def layer_forward(x, csr: Csr, W_l, b_l, W_r, ln_w, ln_b, eps: float, slope: float, save: bool):
-    """One SageBlock layer.  Returns (out, agg, xhat, rstd); xhat/rstd are None unless `save`."""
+    """One SageBlock layer.  Returns (x_used, out, agg, xhat, rstd); xhat/rstd are None unless `save`.
+
+    bf16 feature storage: a bfloat16 `x` runs the bf16 kernels (out and agg come back as bfloat16, xhat / rstd stay
+    float32) when the layer shape is covered; otherwise it is converted to float32 for this layer (x_used is then the
+    float32 copy -- the tensor the backward has to be given) and only `out` is rounded to bfloat16."""
     N, Fin = x.shape
     Fout = W_l.shape[0]
     dev = x.device
+    if x.dtype == torch.bfloat16:
+        if not bf16_supported(Fin, Fout):
+            x32, out, agg, xhat, rstd = layer_forward(x.float(), csr, W_l, b_l, W_r, ln_w, ln_b, eps, slope, save)
+            return x32, out.to(torch.bfloat16), agg, xhat, rstd
+        with torch.cuda.device(dev):
+            out = torch.empty((N, Fout), dtype=torch.bfloat16, device=dev)
+            agg = torch.empty((N, Fin), dtype=torch.bfloat16, device=dev)
+            xhat = torch.empty((N, Fout), dtype=torch.float32, device=dev) if save else None
+            rstd = torch.empty((N,), dtype=torch.float32, device=dev) if save else None
+            wsb = int(lib.sldm_sage_layer_fwd_workspace_bytes(N, csr.E, Fin, Fout))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            check(lib.sldm_sage_layer_forward_bf16(x.data_ptr(), N, Fin, Fout, csr.buf.data_ptr(), csr.E,
+                                                   W_l.data_ptr(), b_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(),
+                                                   ln_b.data_ptr(), float(eps), float(slope),
+                                                   out.data_ptr(), agg.data_ptr(), _ptr(xhat), _ptr(rstd),
+                                                   ws.data_ptr(), wsb, _stream(dev)))
+        return x, out, agg, xhat, rstd
     with torch.cuda.device(dev):
         out = torch.empty((N, Fout), dtype=torch.float32, device=dev)
         agg = torch.empty((N, Fin), dtype=torch.float32, device=dev)
@@ -212,7 +238,7 @@ def layer_forward(x, csr: Csr, W_l, b_l, W_r, ln_w, ln_b, eps: float, slope: flo
                                           ln_b.data_ptr(), float(eps), float(slope),
                                           out.data_ptr(), agg.data_ptr(), _ptr(xhat), _ptr(rstd),
                                           ws.data_ptr(), wsb, _stream(dev)))
-    return out, agg, xhat, rstd
+    return x, out, agg, xhat, rstd
 
 
 # ---- "parameter gradients of the last layer_backward are complete" event (consumed by parallel.GraphDataParallel) ----
@@ -254,8 +280,12 @@ def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slo
     dout = dout.contiguous()
     b = bufs if bufs is not None else backward_buffers(N, Fin, Fout, csr.E, dev, need_dx)
 
+    entry = lib.sldm_sage_layer_backward_bf16 if x.dtype == torch.bfloat16 else lib.sldm_sage_layer_backward_stages
+    if x.dtype != agg.dtype or dout.dtype != torch.float32:
+        raise RuntimeError(f"layer_backward: x is {x.dtype}, agg is {agg.dtype}, dout is {dout.dtype}")
+
     def launch(mask):
-        check(lib.sldm_sage_layer_backward_stages(
+        check(entry(
             dout.data_ptr(), x.data_ptr(), agg.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), N, Fin, Fout,
             csr.buf.data_ptr(), csr.E, W_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), float(slope),
             _ptr(b["dx"]), b["dW_l"].data_ptr(), b["db_l"].data_ptr(), b["dW_r"].data_ptr(), b["dln_w"].data_ptr(),

@@ -84,7 +84,7 @@ class _SageBlockFn(torch.autograd.Function):
         h, keep = x, []
         for l in range(L):
             W_l, b_l, W_r, ln_w, ln_b = params[5 * l:5 * l + 5]
-            out, agg, xhat, rstd = ops.layer_forward(h, csr, W_l, b_l, W_r, ln_w, ln_b, eps[l], slopes[l], save)
+            h, out, agg, xhat, rstd = ops.layer_forward(h, csr, W_l, b_l, W_r, ln_w, ln_b, eps[l], slopes[l], save)
             mask = None
             if drops[l] is not None:                       # training mode and 0 < p < 1
                 out, mask = torch.native_dropout(out, drops[l], True)
@@ -108,12 +108,13 @@ class _SageBlockFn(torch.autograd.Function):
         keep = [next(it) if present else None for present in ctx.layout]
         ddp = torch.distributed.is_available() and torch.distributed.is_initialized()
         grads = [None] * (5 * L)
-        g = dout
+        g = dout if dout.dtype == torch.float32 else dout.float()    # bf16 features: the gradient path stays fp32
         for l in range(L - 1, -1, -1):
             h, agg, xhat, rstd, mask = keep[5 * l:5 * l + 5]
             W_l, _, W_r, ln_w, ln_b = params[5 * l:5 * l + 5]
             if mask is not None:
                 g = torch.ops.aten.native_dropout_backward(g, mask, 1.0 / (1.0 - ctx.drops[l]))
+            g = g.contiguous()
             need_dx = l > 0 or ctx.needs_input_grad[0]
             dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
                 g, h, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slopes[l], need_dx,
@@ -156,6 +157,10 @@ class SageBlock(nn.Module):
     def clear_cache(self) -> None:
         self._csr_key = self._csr = None
 
+    def graphed(self, max_nodes: int, max_edges: int) -> "GraphedSageBlock":
+        """Inference through one captured CUDA graph for inputs of up to max_nodes - 1 nodes / max_edges edges."""
+        return GraphedSageBlock(self, max_nodes, max_edges)
+
     def forward(self, x, edge_index, batch=None):
         if len(self.convs) == 0:
             return x
@@ -166,8 +171,8 @@ class SageBlock(nn.Module):
         ops._require_cuda(edge_index, "edge_index")
         if edge_index.device != x.device:
             raise RuntimeError(f"SageBlock: x is on {x.device} but edge_index is on {edge_index.device}")
-        if x.dtype != torch.float32:
-            raise RuntimeError(f"SageBlock: expected float32 features, got {x.dtype}")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"SageBlock: expected float32 (or bfloat16: bf16 feature storage) features, got {x.dtype}")
         if x.size(1) != self.convs[0].in_channels:
             raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.size(0)}x{x.size(1)} and "
                                f"{self.convs[0].in_channels}x{self.convs[0].out_channels})")
@@ -195,3 +200,70 @@ class SageBlock(nn.Module):
             drops.append(p if (self.training and p > 0.0) else None)
             params += [conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, ln.weight, ln.bias]
         return _SageBlockFn.apply(x, csr, eps, slopes, drops, *params)
+
+
+class GraphedSageBlock:
+    """Inference through ONE captured CUDA graph per size bucket -- the reference's real operating point is
+    launch-bound: eval batches of 64 graphs (test.py:58) and, online, one un-batched graph of tens to ~300 vehicles
+    per call from a worker thread (rcv.py:77-84, :107), where ~20 kernel launches and their Python glue cost more
+    than the kernels.
+
+        g = blk.graphed(max_nodes=512, max_edges=4096)     # captures CSR build + all layers once
+        y = g(x, edge_index)                               # copy-in, one graph launch, copy-out
+
+    The captured step works on static buffers of the bucket's size: x is copied into the first N rows (the rest stay
+    zero), edge_index into the first E columns, the remaining columns point at the last padding node (p, p) -- edges
+    among padding rows never touch a real node, and every kernel is row-wise independent, so rows [0, N) of the
+    result are bit-identical to the un-captured module's.  Requires N < max_nodes (one padding node) and
+    E <= max_edges; inference only (no autograd), eval-mode dropout.  Thread-safe: calls serialise on a lock.
+    """
+
+    def __init__(self, block: "SageBlock", max_nodes: int, max_edges: int, device=None):
+        import threading
+        if len(block.convs) == 0:
+            raise ValueError("GraphedSageBlock: the block has no layers")
+        p0 = block.convs[0].lin_l.weight
+        dev = torch.device(device) if device is not None else p0.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedSageBlock: CUDA only")
+        self.block, self.dev = block, dev
+        self.max_nodes, self.max_edges = int(max_nodes), int(max_edges)
+        self.fin, self.fout = block.convs[0].in_channels, block.convs[-1].out_channels
+        self._lock = threading.Lock()
+        with torch.cuda.device(dev), torch.inference_mode():
+            self._x = torch.zeros((self.max_nodes, self.fin), dtype=torch.float32, device=dev)
+            self._ei = torch.full((2, self.max_edges), self.max_nodes - 1, dtype=torch.long, device=dev)
+            was_training = block.training
+            block.eval()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                  # warm-up outside the capture: opt-in attributes, tensor maps
+                for _ in range(2):
+                    block.clear_cache()
+                    block(self._x, self._ei)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self._graph = torch.cuda.CUDAGraph()
+            block.clear_cache()
+            with torch.cuda.graph(self._graph):
+                self._y = block(self._x, self._ei)
+            block.clear_cache()
+            block.train(was_training)
+
+    def __call__(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        ops.check_edge_index(edge_index)
+        N, E = int(x.size(0)), int(edge_index.size(1))
+        if x.dim() != 2 or x.size(1) != self.fin or x.dtype != torch.float32:
+            raise RuntimeError(f"GraphedSageBlock: expected float32 x of shape [N, {self.fin}]")
+        if N >= self.max_nodes or E > self.max_edges:
+            raise RuntimeError(f"GraphedSageBlock: N = {N}, E = {E} exceed the bucket ({self.max_nodes - 1} nodes, "
+                               f"{self.max_edges} edges)")
+        with self._lock, torch.cuda.device(self.dev), torch.inference_mode():
+            self._x[:N].copy_(x, non_blocking=True)
+            self._ei[:, :E].copy_(edge_index, non_blocking=True)
+            if E < self.max_edges:
+                self._ei[:, E:].fill_(self.max_nodes - 1)
+            # rows beyond N keep whatever an earlier, larger call left there: they are padding rows (no edge from a
+            # real node reaches them), so their values never matter
+            self._graph.replay()
+            return self._y[:N].clone()

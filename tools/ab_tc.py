@@ -26,7 +26,7 @@ blk = sg.SageBlock([F, F], negative_slope=0.1).to(dev)
 conv, ln = blk.convs[0], blk.posts[0][0]
 p = (conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, ln.weight, ln.bias)
 csr = sg.build_csr(ei, N)
-out, agg, xhat, rstd = ops.layer_forward(x, csr, *p, ln.eps, 0.1, True)
+_, out, agg, xhat, rstd = ops.layer_forward(x, csr, *p, ln.eps, 0.1, True)
 dout = torch.randn_like(out)
 bb = ops.backward_buffers(N, F, F, E, dev, True)
 bargs = (dout, x, agg, xhat, rstd, csr, p[0], p[2], p[3], p[4], 0.1, True)
