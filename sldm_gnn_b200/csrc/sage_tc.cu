@@ -13,32 +13,45 @@
 // fp64 (tools/tc_probe2.cu, K=128): max 3.2e-7 / rms 7.3e-8 versus 7.8e-7 / 1.1e-7 for a
 // sequential fp32 FMA chain -- i.e. at least as accurate as the SIMT kernel.
 //
-// Pipeline (one persistent CTA per SM, 896 threads = 7 warpgroups, 128 rows x Fout per tile; setmaxnreg 56 / 72 / 80 / 56 of the 72 x 896 pool):
+// Pipeline (one persistent CTA per SM, 896 threads = 7 warpgroups, 128 rows x Fout per tile; setmaxnreg 56 / 72 / 80 / 56
+// of the 72 x 896 register pool):
 //   warp 0        TMA producer A: raw activation chunks [128 x 32] (agg, then x) into a 5-deep ring -- the HBM stream;
 //                                a stage is handed back by the CONVERTER as soon as the tile is in registers
 //   warp 2        TMA producer B: pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk into a 2-deep ring (L2 hits)
-//   warps 4-7     converter    : reads its row of the raw tile, splits every value into a_hi (what the tensor core
-//                                keeps) and a_lo = rna_tf32(a - a_hi) and parks both in TENSOR MEMORY with tcgen05.st
-//                                (lane = row, column = k; two 64-column slots with their own free barriers) -- the MMAs
-//                                take A from TMEM, so shared memory only carries the raw tile once and the weights
+//   warps 4-7     converter    : reads its row of the raw tile and parks a (the tensor core truncates it to tf32 = a_hi
+//                                itself) and a_lo = rna_tf32(a - a_hi) in TENSOR MEMORY with tcgen05.st (lane = row,
+//                                column = k; two 64-column slots with their own free barriers) -- the MMAs take A from
+//                                TMEM, so shared memory only carries the raw tile once and the weights
 //   warps 1, 3    MMA issuers  : alternate K chunks; 12 x tcgen05.mma.kind::tf32 (M=128, N=Fout, K=8), A from TMEM, B
 //                                from smem descriptors, into one of three TMEM accumulators; tcgen05.commit frees the
-//                                weight stage and the TMEM A slot and signals the drain
+//                                weight stage and the TMEM A slot and signals the drain.  Warp-uniform control flow,
+//                                one elected lane issues (12 back-to-back UTCHMMA, operands on the uniform datapath)
 //   warps 8-23    drain        : tcgen05.ld the chunk accumulator (thread = row x quarter of the columns), add into
-//                                registers (round-to-nearest); after the last chunk of a tile the raw sums are parked in
-//                                a swizzled shared-memory tile [128 x Fout] and the warp goes straight on to the next
-//                                tile's chunks: its tail is ~0.3k cycles, the MMA stream never waits for it
-//   warps 24-27   finisher     : one warp per 32-row quadrant of the parked tile, LANE = 4 CONSECUTIVE COLUMNS: + bias,
-//                                LayerNorm (two-pass mean / variance by warp shuffles), xhat out, (Leaky)ReLU, out --
-//                                every store instruction writes whole 512-byte rows (DGRAD: / max(deg,1), dagg | dxroot)
+//                                registers (round to nearest); after the last chunk: + bias, LayerNorm statistics (thread
+//                                per row x quarter: one warp instruction serves 32 rows; one exchange of per-quarter
+//                                (sum, M2) through smem, Chan's merge) -- DGRAD: / max(deg,1) -- and the normalised row
+//                                is PARKED in a swizzled shared-memory tile [128 x Fout]; on to the next tile's chunks
+//   warps 24-27   finisher     : one warp per 32-row quadrant of the parked tile, LANE = 4 CONSECUTIVE COLUMNS: xhat out
+//                                (training), affine + (Leaky)ReLU, out -- every store instruction writes whole 512-byte
+//                                rows; off the MMA -> drain critical path (DGRAD: plain copy to dagg | dxroot)
 // Tensor memory (512 columns): three accumulators [0, 384), two A slots [384, 512).
-// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  History (profiles/r01c traces): with the epilogue
-// warps doing statistics and stores themselves a tile took 14.7k cycles against an HBM floor of 11.4k: a 6.4k-cycle tail
-// (statistics 1.9k, two TMA-store pushes that queued ~1.0k each behind the operand loads in the TMA engine and waited
-// 0.8k for the patch to be read back) during which the MMA stream could only run three accumulators ahead.  Round 2:
-// (a) 256-bit st.global straight from the accumulator registers (lane = row, 32 B per lane) was SLOWER (0.507 vs
-// 0.398 ms: 32 rows x 32 B per instruction are partial-line writes); (b) the finisher above: the tail leaves the
-// drain warps, stores are full-line and never touch the TMA engine.
+// Bound: HBM at large N (N*4*(2Fin + 2Fout) bytes).  Measured on B200, batch shape (0.82 M rows, 128 -> 128), per
+// 128-row tile in SM cycles (clock64 traces under profiles/r02_trace_*; HBM floor ~8.9k at the ~1.5 GHz the SMs run at):
+//   round 1 (epilogue warps do statistics + two TMA-store pushes)                         14.7k   0.392 ms
+//   + finisher warpgroup (stores leave the drain), still `if (lane == 0)` MMA issue         13.8k   0.380 ms
+//     -> trace: 150 cycles per tcgen05.mma: under a divergent branch ptxas wraps every MMA in an ELECT / 4x R2UR /
+//        BRA.U.ANY broadcast loop (15 SASS instructions each); the kernel was bound by MMA ISSUE
+//   + warp-uniform issue with an elected lane (this file)                                   12.3k   0.355 ms
+//   + four rows in flight per finisher warp                                                         0.349 ms
+// What was tried and lost: 256-bit st.global straight from the accumulator registers (lane = row, 32 B per lane:
+// partial-line writes, 0.507 ms); LayerNorm in a lane-per-column finisher (2.9k cycles per 4 rows of shuffles and
+// divisions: 0.587 ms) and in a thread-per-row finisher over the parked tile (0.470 ms: four warps cannot absorb it);
+// deeper rings (A 3..8, B 2..3: no change).  Timing-only experiments (wrong results, -DSLDM_TC_NOSTORE / weights loaded
+// once): without the 128 KB of stores per tile 0.300 ms (the finisher's 64 STG.128 per warp and tile take ~11k cycles:
+// a warp gets one 512-byte store through every ~190 cycles), without the weight re-streaming 0.339 ms, without both
+// 0.278 ms (then the drain tail -- statistics 2.6k + park 0.8k during which the MMA stream runs out of accumulators --
+// sets the pace).  Three limits sit within 10 % of each other; the next step is a CTA pair sharing the weight stages
+// (cluster multicast) and TMA bulk stores from the parked tile.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -260,7 +273,10 @@ template <int NT, int MODE, bool ABF>
 __device__ __forceinline__ void finisher_role(const FinArgs a) {
   constexpr int LPRW = (NT == 1) ? 8 : (NT == 2) ? 16 : 32;
   constexpr int RPI = 32 / LPRW;
-  constexpr int U = 2;                      // rows in flight per warp (40-register budget)
+  #ifndef SLDM_TC_FIN_U
+#define SLDM_TC_FIN_U 4
+#endif
+  constexpr int U = SLDM_TC_FIN_U;          // row instructions in flight per warp
   long long* trace = a.trace;
   const int tid = threadIdx.x, lane = tid & 31;
   const int q = (tid >> 5) & 3;
@@ -301,7 +317,11 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int64_t row = tile * kTcBM + rl[u];
+#ifdef SLDM_TC_NOSTORE   /* timing experiment only (no results): the finisher issues no global stores */
+          if (row < 0 && cvalid) {
+#else
           if (row < a.N && cvalid) {
+#endif
             if constexpr (MODE == MODE_FWD) {
               if (a.xhat != nullptr) *reinterpret_cast<float4*>(a.xhat + row * Fout + c0) = v[u];
               float4 y;
@@ -475,7 +495,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           const uint32_t sb = it % kTcBStages, bph = (it / kTcBStages) & 1;
           const uint32_t asl = it % kTcASlots, aslph = (it / kTcASlots) & 1;
           const uint32_t ab = it % kTcAcc, aph = (it / kTcAcc) & 1;
-          if ((it & 1u) != my_parity) continue;
+          if (ABF ? (my_parity != 0u) : ((it & 1u) != my_parity)) continue;   // ABF: warp 1 issues every chunk (see below)
           if (lane == 0) TC_TRACE(2, it);
           mbar_wait(&bar_acc_empty[ab], aph ^ 1);   // epilogue drained this accumulator (three chunks ago)
           if (lane == 0) TC_TRACE(3, it);
@@ -485,6 +505,9 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
           const uint32_t a_lo = a_hi + 32;
           const uint32_t d = tmem_u + ab * ACC_COLS;
           if constexpr (ABF) {
+            // One issuer only: a raw chunk consumes BOTH weight stages, and a parity wait is only safe when the waiter
+            // is at most one phase away from the barrier -- two warps alternating chunks would each wait on stages
+            // whose previous phase they never observed (seen on B200: 3 of 9 tiles wrong at Fin = Fout = 128).
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint32_t itb = 2u * it + h;
@@ -575,7 +598,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
                 dst[8 * (j & 1) + 2 * e] = w << 16;
                 dst[8 * (j & 1) + 2 * e + 1] = w & 0xFFFF0000u;
               } else {
-                hi[4 * j + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
+                hi[4 * j + e] = __float_as_uint(f[e]);    // unmasked: the tensor core truncates to tf32 itself
                 lo[4 * j + e] = __float_as_uint(tf32_lo(f[e]));
               }
             }

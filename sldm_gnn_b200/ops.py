@@ -102,7 +102,7 @@ class _IndexChecks:
                              "SLDM_CHECK_INDICES=1 raises at the call that passed it)")
 
     def poll(self, block: bool = False) -> None:
-        if not self.pending:
+        if not self.pending or torch.cuda.is_current_stream_capturing():   # (event queries are illegal during capture)
             return
         with self.lock:
             self._drain(block)

@@ -243,6 +243,7 @@ class GraphedSageBlock:
                     block(self._x, self._ei)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
+            ops.index_checks.poll(block=True)              # nothing may be pending when the capture starts
             self._graph = torch.cuda.CUDAGraph()
             block.clear_cache()
             with torch.cuda.graph(self._graph):

@@ -33,7 +33,7 @@ def _log(rec: dict) -> None:
 def assert_close(got, want, what, scale_atol=False, want64=None, rtol=RTOL, atol=ATOL):
     """|got - want| <= atol + rtol*|want| element-wise against the fp32 oracle; fp64 adjudication as described in the
     module docstring.  Parameter gradients are sums over all N rows: `scale_atol` scales atol by the tensor's own
-    magnitude (the same relative bar).  Returns (adjudicated, total)."""
+    magnitude (the same relative bar).  Returns (adjudicated, total, fp32-oracle misses against fp64 | None)."""
     got, want = got.detach().cpu(), want.detach().cpu()
     assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} != {tuple(want.shape)}"
     total = want.numel()
@@ -45,7 +45,7 @@ def assert_close(got, want, what, scale_atol=False, want64=None, rtol=RTOL, atol
            "atol": a, "rtol": rtol}
     if n_bad == 0:
         _log(rec)
-        return 0, total
+        return 0, total, None
     msg = f"{what}: {n_bad}/{total} outside tolerance, max err {float(err.max()):.3e}"
     assert want64 is not None, msg
     w64 = want64.detach().cpu().double()
@@ -59,4 +59,4 @@ def assert_close(got, want, what, scale_atol=False, want64=None, rtol=RTOL, atol
     assert ok.all(), msg + f"; vs fp64: ours max {float(e_g.max()):.3e}, fp32 oracle max {e_o_max:.3e}"
     assert n_bad <= MAX_ADJUDICATED_FRAC * total or 2 * oracle_misses >= n_bad or n_bad <= 2, \
         msg + f" -- too many adjudicated elements (fp32 oracle misses the bar vs fp64 on {oracle_misses})"
-    return n_bad, total
+    return n_bad, total, oracle_misses
