@@ -138,6 +138,16 @@ def layer_bytes_fwd_bwd_cache_perfect(N, E, Fin, Fout, s=4):
     return 2 * (4 * E + N * Fin * s) + N * s * (6 * Fin + 5 * Fout) + 28 * N
 
 
+def layer_bytes_fwd_bwd_bf16feat(N, E, Fin, Fout):
+    """bf16 FEATURE storage (x, agg, out in 2 bytes; xhat, every gradient and all accumulation in fp32), the tensors
+    the kernels actually move, per layer fwd+bwd: forward gather E(2Fin+4) + 4(N+1) + agg write 2N Fin; projection
+    reads agg, x (2 x 2N Fin), writes out (2N Fout) + xhat (4N Fout) + rstd; backward as fp32 (8d) except that the
+    weight gradient reads the bf16 agg / x."""
+    fwd = E * (2 * Fin + 4) + 4 * (N + 1) + 2 * N * Fin + N * (4 * Fin + 2 * Fout + 4 * Fout) + 4 * N
+    bwd = N * 4 * (3 * Fout) + N * 4 * (Fout + 2 * Fin) + N * (4 * Fout + 4 * Fin) + E * (Fin * 4 + 4) + 4 * (N + 1) + 3 * N * Fin * 4 + 12 * N
+    return fwd + bwd
+
+
 def csr_bytes(N, E):
     return 16 * E + 8 * E + 8 * (N + 1)
 
@@ -356,7 +366,7 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
     p = (conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, ln.weight, ln.bias)
     csr = sg.build_csr(ei, N)
     _, out, agg, xhat, rstd = ops.layer_forward(x, csr, *p, ln.eps, SLOPE, True)
-    dout = torch.randn_like(out)
+    dout = torch.randn(out.shape, dtype=torch.float32, device=out.device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=x.device)
 
     def timed(fn, reps=5):
@@ -370,26 +380,29 @@ def time_kernels(blk, x, ei, N, E, hdims, peak_gbs, batch_vec=None, num_graphs=N
         return ts[len(ts) // 2]
 
     s = 4
+    sf = 2 if x.dtype == torch.bfloat16 else 4      # bytes per stored FEATURE (x, agg, out); gradients / xhat stay fp32
+    seg_fwd = (lambda: ops.segment_mean_bf16(x, csr)) if sf == 2 else (lambda: sg.segment_reduce(x, csr))
     from sldm_gnn_b200 import _lib as L_
     bb = ops.backward_buffers(N, Fin, Fout, E, x.device, True)
     bargs = (dout, x, agg, xhat, rstd, csr, p[0], p[2], p[3], p[4], SLOPE, True)
     ops.layer_backward(*bargs, bufs=bb)          # fills dz / dagg / dxroot / partials for the single-stage launches
     groups = {
         "csr_build": (lambda: sg.build_csr(ei, N), csr_bytes(N, E)),
-        "segment_mean_fwd": (lambda: sg.segment_reduce(x, csr), E * (Fin * s + 4) + 4 * (N + 1) + N * Fin * s),
-        "project_ln_act_fwd": (lambda: ops.project_forward(agg, x, *p, ln.eps, SLOPE, True), N * s * (2 * Fin + 2 * Fout) + 4 * N),
+        "segment_mean_fwd": (seg_fwd, E * (Fin * sf + 4) + 4 * (N + 1) + N * Fin * sf),
+        "project_ln_act_fwd": (lambda: ops.project_forward(agg, x, *p, ln.eps, SLOPE, True),
+                               N * (2 * Fin * sf + Fout * sf + Fout * s) + 4 * N),
         "layer_backward": (lambda: ops.layer_backward(dout, x, agg, xhat, rstd, csr, p[0], p[2], p[3], p[4], SLOPE, True),
-                           N * s * (3 * Fout + 4 * Fin) + 12 * N + E * (Fin * s + 4) + 4 * (N + 1)),
+                           N * (3 * Fout * s + 2 * Fin * sf + 2 * Fin * s) + 12 * N + E * (Fin * s + 4) + 4 * (N + 1)),
         # the kernels of layer_backward one at a time (include/sldm_sage.h SLDM_BWD_STAGE_*), on the buffers of a full call
         "ln_bwd": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_LN, bufs=bb), 3 * N * s * Fout + 4 * N),
         "dgrad": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_DGRAD, bufs=bb), N * s * (Fout + 2 * Fin) + 4 * N),
-        "wgrad": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_WGRAD, bufs=bb), N * s * (Fout + 2 * Fin)),
-        "segment_sum_bwd": (lambda: sg.segment_reduce(agg, csr, transpose=True, mean=False, addend=x),
-                            E * (Fin * s + 4) + 4 * (N + 1) + 2 * N * Fin * s),
+        "wgrad": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_WGRAD, bufs=bb), N * (s * Fout + 2 * Fin * sf)),
+        "segment_sum_bwd": (lambda: ops.layer_backward(*bargs, stages=L_.BWD_STAGE_GATHER, bufs=bb),
+                            E * (Fin * s + 4) + 4 * (N + 1) + 3 * N * Fin * s),
     }
     if batch_vec is not None:
         try:     # the widened components must never take the headline measurement down
-            groups.update(widened_groups(sg, x, out, batch_vec, num_graphs, N, s))
+            groups.update(widened_groups(sg, x, out if out.dtype == torch.float32 else out.float(), batch_vec, num_graphs, N, s))
         except Exception as exc:
             groups["widened_components"] = (lambda: (_ for _ in ()).throw(RuntimeError(repr(exc)[:200])), 0)
     res = {}
@@ -464,6 +477,9 @@ def main_ours(args, wl):
 
     hdims = wl["hdims"]
     L = len(hdims) - 1
+    bf16 = args.dtype == "bf16"
+    if bf16 and not all(sg.ops.bf16_supported(hdims[l], hdims[l + 1]) for l in range(L)):
+        raise SystemExit(f"--dtype bf16: hdims {hdims} are not covered by the bf16 kernels")
     torch.manual_seed(0)
     blk = sg.SageBlock(hdims, dropout=None, negative_slope=SLOPE).to(dev)
     ddp = GraphDataParallel(blk)
@@ -472,12 +488,16 @@ def main_ours(args, wl):
     for j in range(2):
         seed = (rank * 2 + j) if args.workload != "c4" else j
         x_h, ei_h, N, graphs, bv = make_inputs(wl, seed)
+        if bf16:
+            x_h = x_h.to(torch.bfloat16)           # the features are STORED as bf16: half the H2D bytes, half the HBM rows
         batches.append(dict(x_h=x_h.pin_memory(), ei_h=ei_h.pin_memory(), N=N, E=ei_h.size(1), graphs=graphs, bv=bv))
     for b in batches:
         b["x"] = b["x_h"].to(dev).requires_grad_(True)
         b["ei"] = b["ei_h"].to(dev)
         # fixed upstream gradient dL/dout: stands in for whatever follows the block (pooling, head, loss)
         b["w"] = upstream_gradient(b["N"], hdims[-1]).to(dev)
+        if bf16:
+            b["w"] = b["w"].to(torch.bfloat16)     # dL/dout has the dtype of the block's output
     N, E, graphs = batches[0]["N"], batches[0]["E"], batches[0]["graphs"]
 
     fwd_only = bool(wl.get("forward_only"))
@@ -548,7 +568,7 @@ def main_ours(args, wl):
             ev.record(copy_stream)
         return b, xd, eid, ev
 
-    out_h = torch.empty((N, hdims[-1]), dtype=torch.float32).pin_memory() if fwd_only else None
+    out_h = torch.empty((N, hdims[-1]), dtype=torch.bfloat16 if bf16 else torch.float32).pin_memory() if fwd_only else None
 
     def consume(item):
         b, xd, eid, ev = item
@@ -594,6 +614,9 @@ def main_ours(args, wl):
             step_bytes = sum(E * (hdims[l] * 4 + 4) + 4 * (N + 1) + N * 4 * (hdims[l] + hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
             # cache-perfect lower bound: every source row read once (E*Fin*s -> N*Fin*s)
             step_bytes_cp = sum(4 * E + 4 * (N + 1) + N * 4 * (2 * hdims[l] + hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+        elif bf16:
+            step_bytes = sum(layer_bytes_fwd_bwd_bf16feat(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
+            step_bytes_cp = step_bytes - sum((E - N) * (2 * hdims[l] + 4 * hdims[l]) for l in range(L))
         else:
             step_bytes = sum(layer_bytes_fwd_bwd(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
             step_bytes_cp = sum(layer_bytes_fwd_bwd_cache_perfect(N, E, hdims[l], hdims[l + 1]) for l in range(L)) + csr_bytes(N, E)
@@ -609,13 +632,14 @@ def main_ours(args, wl):
         line = {
             "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, wl, N, E, graphs),
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 features (fp32 accumulate, parameters and gradients)" if bf16 else "f32",
+            "data": "synthetic",
+            "config": dict(workload_config(args.workload, wl, N, E, graphs), feature_dtype=args.dtype),
             "graphs_per_sec": graphs_all / (ms_step * 1e-3),
             "clocks": clocks,
             "e2e": {"value": E_all * L / (e2e_ms * 1e-3), "unit": "edges/s",
-                    "h2d_bytes_per_step": batches[0]["x_h"].numel() * 4 + batches[0]["ei_h"].numel() * 8,
-                    "d2h_bytes_per_step": (N * hdims[-1] * 4 if fwd_only else 4), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "h2d_bytes_per_step": batches[0]["x_h"].numel() * batches[0]["x_h"].element_size() + batches[0]["ei_h"].numel() * 8,
+                    "d2h_bytes_per_step": (N * hdims[-1] * (2 if bf16 else 4) if fwd_only else 4), "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "graphs_per_sec": graphs_all / (e2e_ms * 1e-3)},
             "host_numa_bound_cpus": numa,
             "gpu_launches": int(launches),
@@ -636,10 +660,11 @@ def main_ours(args, wl):
                               "frac_measured_dram": None,
                               "frac_measured_dram_note": "needs ncu dram__bytes of every kernel of the step; see profiles/ for the latest capture",
                               "model": ("SURVEY 8d FWD_inf: sum_l [E(Fin*4+4) + 4(N+1) + 4N(Fin+Fout)] + 24E + 8(N+1)" if fwd_only else
+                                        "bf16 features: the tensors actually moved (bench.py layer_bytes_fwd_bwd_bf16feat) + 24E + 8(N+1)" if bf16 else
                                         "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)")},
             "kernels": kern,
         }
-        if world == 1 and args.workload == "batch" and not args.no_c4:
+        if world == 1 and args.workload == "batch" and not args.no_c4 and not bf16:
             for b in batches:                      # release the batch workload's device buffers first
                 b.pop("x", None); b.pop("ei", None); b.pop("w", None)
             try:
@@ -665,6 +690,9 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["c2"], default="batch")
     ap.add_argument("--c2-graphs", type=int, default=1024, help="--workload c2: sequences (vehicle graphs) per GPU and step")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32",
+                    help="f32 (default, the parity path) or bf16 FEATURE storage (x / agg / layer outputs in bf16; parameters, "
+                         "accumulation, LayerNorm statistics and the whole gradient path stay fp32) -- BASELINE configs[4]")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the c4 sub-record of the default line")
     ap.add_argument("--skip-kernel-timing", action="store_true",

@@ -200,6 +200,7 @@ int     sldm_sage_layer_backward_stages(const float* dout, const float* x, const
  * backward data path (dout, dz, dagg, dxroot, dx and the parameter gradients); only the weight-gradient kernel
  * reads the bf16 x / agg.  Rounding happens once per stored value (round-to-nearest-even).
  *   sldm_segment_mean_bf16        src, out: bf16 [N,F]; F % 8 == 0, F <= 256
+ *   sldm_sage_project_forward_bf16  agg, x bf16 [N,Fin] -> out bf16 [N,Fout] (the projection + LayerNorm + activation alone)
  *   sldm_sage_layer_forward_bf16  x bf16 [N,Fin]; out bf16 [N,Fout]; agg bf16 [N,Fin]; xhat fp32, rstd fp32 (or NULL)
  *   sldm_sage_layer_backward_bf16 x, agg bf16; everything else as sldm_sage_layer_backward_stages (fp32)
  * Shapes: Fin in {64, 128}, Fout % 32 == 0, 32 <= Fout <= 128 (sldm_sage_bf16_supported); otherwise
@@ -207,6 +208,11 @@ int     sldm_sage_layer_backward_stages(const float* dout, const float* x, const
 int sldm_sage_bf16_supported(int32_t Fin, int32_t Fout);
 int sldm_segment_mean_bf16(const void* src, int64_t N, int32_t F, const int32_t* csr, int64_t E, void* out,
                            void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
+int sldm_sage_project_forward_bf16(const void* agg, const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                                   const float* W_l, const float* b_l, const float* W_r,
+                                   const float* ln_w, const float* ln_b, float eps, float slope,
+                                   void* out, float* xhat_out, float* rstd_out,
+                                   void* workspace, int64_t workspace_bytes, sldm_stream_t stream);
 int sldm_sage_layer_forward_bf16(const void* x, int64_t N, int32_t Fin, int32_t Fout,
                                  const int32_t* csr, int64_t E,
                                  const float* W_l, const float* b_l, const float* W_r,

@@ -55,6 +55,8 @@ _PROTOS = {
                                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i32]),
     "sldm_sage_bf16_supported": (C.c_int, [_i32, _i32]),
     "sldm_segment_mean_bf16": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p]),
+    "sldm_sage_project_forward_bf16": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _f, _f,
+                                                 _p, _p, _p, _p, _i64, _p]),
     "sldm_sage_layer_forward_bf16": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _p, _f, _f,
                                                _p, _p, _p, _p, _p, _i64, _p]),
     "sldm_sage_layer_backward_bf16": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, _f,

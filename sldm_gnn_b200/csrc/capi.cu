@@ -189,6 +189,20 @@ extern "C" int sldm_sage_layer_forward_bf16(const void* x, int64_t N, int32_t Fi
                                      static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int sldm_sage_project_forward_bf16(const void* agg, const void* x, int64_t N, int32_t Fin, int32_t Fout,
+                                              const float* W_l, const float* b_l, const float* W_r,
+                                              const float* ln_w, const float* ln_b, float eps, float slope,
+                                              void* out, float* xhat_out, float* rstd_out,
+                                              void* workspace, int64_t workspace_bytes, sldm_stream_t stream) {
+  SLDM_REQUIRE(sldm_sage_bf16_supported(Fin, Fout), SLDM_EUNSUPPORTED, "sldm_sage_project_forward_bf16: Fin=%d Fout=%d", Fin, Fout);
+  if (N == 0) return SLDM_OK;
+  SLDM_REQUIRE(agg && x && W_l && b_l && W_r && ln_w && ln_b && out, SLDM_EINVAL, "sldm_sage_project_forward_bf16: NULL pointer");
+  SLDM_REQUIRE(project_forward_bf16_eligible(N, Fin, Fout, agg, x, out, xhat_out), SLDM_EUNSUPPORTED,
+               "sldm_sage_project_forward_bf16: buffers must be 16-byte aligned (and SLDM_DISABLE_TC unset)");
+  return project_forward_bf16_launch(agg, x, N, Fin, Fout, W_l, b_l, W_r, ln_w, ln_b, eps, slope, out, xhat_out, rstd_out,
+                                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int sldm_sage_layer_backward_bf16(const float* dout, const void* x, const void* agg,
                                              const float* xhat, const float* rstd,
                                              int64_t N, int32_t Fin, int32_t Fout,

@@ -118,12 +118,14 @@ constexpr int kTraceIts = 96, kTraceEv = 32;
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
-// Hand-off tile in shared memory: row r (0..127) has 8*NT 16-byte chunks; chunk j sits at position j ^ (r & 7) of its
-// row (XOR on the low three bits).  Drain writes (8 lanes of a quarter warp = 8 consecutive rows, same j) and finisher
-// reads (the lanes of a row = consecutive j) both touch every bank group exactly once per phase.
+// Hand-off tile in shared memory, laid out so that the TMA engine can store it as it lies: NT column slabs of
+// [128 rows][128 bytes] (32 fp32 columns each), 128-byte swizzle -- 16-byte chunk c of row r sits at position
+// c ^ (r & 7) of its 128-byte row.  j = 16-byte chunk index inside the full row (0 .. 8*NT-1).  Drain writes (8 lanes
+// of a quarter warp = 8 consecutive rows, same j) and finisher reads (the lanes of a row = consecutive j) both touch
+// every bank group exactly once per phase.
 template <int NT>
 __device__ __forceinline__ uint32_t z_chunk_addr(uint32_t zbase, int r, int j) {
-  return zbase + (uint32_t)r * (128u * NT) + ((uint32_t)(j ^ (r & 7)) << 4);
+  return zbase + (uint32_t)(j >> 3) * (kTcBM * 128u) + (uint32_t)r * 128u + ((uint32_t)((j & 7) ^ (r & 7)) << 4);
 }
 
 struct DrainArgs {
@@ -251,6 +253,7 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
 #pragma unroll
       for (int c = 0; c < 2 * NT; ++c)
         sts128(z_chunk_addr<NT>(a.zbase, rloc, cq * 2 * NT + c), make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
+      fence_proxy_async_smem();                           // the tile is also read by the TMA engine (bulk stores)
       __syncwarp();
       if (lane == 0) mbar_arrive(&a.bar_z_full[q]);       // release: the finisher's wait acquires these writes
       if (tid == 256) TC_TRACE(13, it - 1);
@@ -262,6 +265,7 @@ struct FinArgs {
   int64_t N; int Fout; int64_t ntiles; int ngroups; float slope;
   float* out; float* xhat; uint32_t zbase;
   const float* gamma; const float* beta;       // global pointers (FWD)
+  const CUtensorMap* tm_s0; const CUtensorMap* tm_s1;   // bulk-store maps, box [32 rows][32 fp32]: FWD xhat | DGRAD dagg, dxroot
   uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
 };
 
@@ -296,6 +300,32 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
       mbar_wait(&a.bar_z_full[q], hand & 1);
       if (tid == 768) TC_TRACE(17, hand);
       float* const o_main = (MODE == MODE_FWD) ? a.out : (grp == 0 ? a.out : a.xhat);   // DGRAD: dagg | dxroot
+      // Whatever leaves unchanged -- xhat in training, dagg / dxroot in DGRAD -- is stored by the TMA engine straight
+      // from the parked tile (one [32 rows x 128 B] box per column slab): a warp's own st.global stream gets one
+      // 512-byte store through every ~190 cycles, and 128 KB per tile through four warps was the slowest stage of
+      // the kernel (profiles/r02_ab_kernel_variants.jsonl, "nostore").  Only the activated output takes that path.
+      // (whole 32-column slabs only: Fout == 32*NT; other widths keep the st.global path.  Measured at the batch
+      // shape: DGRAD 0.360 -> 0.353 ms; for the forward's xhat it was neutral to slightly worse (0.349 -> 0.357 ms: the
+      // finisher then waits for the engine before handing the tile back), so the forward keeps st.global for both.)
+      const bool bulk = (Fout == 32 * NT) && (MODE == MODE_DGRAD);
+      if (bulk && lane == 0) {
+        const CUtensorMap* tm = (MODE == MODE_FWD) ? a.tm_s0 : (grp == 0 ? a.tm_s0 : a.tm_s1);
+        const int grow0 = (int)(tile * kTcBM) + q * 32;
+#pragma unroll
+        for (int sl = 0; sl < NT; ++sl)
+          if (sl * 32 < Fout)
+            tma_store_2d_u32(tm, a.zbase + (uint32_t)sl * (kTcBM * 128u) + (uint32_t)q * 4096u, sl * 32, grow0);
+        tma_store_commit();
+      }
+      if (MODE == MODE_DGRAD && bulk) {
+        if (lane == 0) {
+          tma_store_wait_read<0>();                     // the engine has read the tile: hand it back
+          mbar_arrive(&a.bar_z_empty[q]);
+        }
+        __syncwarp();
+        if (tid == 768) TC_TRACE(18, hand);
+        continue;
+      }
 #pragma unroll 1
       for (int i = 0; i < 32; i += U * RPI) {
         float4 v[U];
@@ -312,7 +342,10 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
           for (int u = 0; u < U; ++u) guard += v[u].x;
           asm volatile("" ::"f"(guard) : "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a.bar_z_empty[q]);
+          if (lane == 0) {
+            if (bulk) tma_store_wait_read<0>();          // ... and the engine has read it too
+            mbar_arrive(&a.bar_z_empty[q]);
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -323,7 +356,7 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
           if (row < a.N && cvalid) {
 #endif
             if constexpr (MODE == MODE_FWD) {
-              if (a.xhat != nullptr) *reinterpret_cast<float4*>(a.xhat + row * Fout + c0) = v[u];
+              if (!bulk && a.xhat != nullptr) *reinterpret_cast<float4*>(a.xhat + row * Fout + c0) = v[u];
               float4 y;
               y.x = fmaf(v[u].x, gam4.x, bet4.x); y.y = fmaf(v[u].y, gam4.y, bet4.y);
               y.z = fmaf(v[u].z, gam4.z, bet4.z); y.w = fmaf(v[u].w, gam4.w, bet4.w);
@@ -344,6 +377,7 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
       if (tid == 768) TC_TRACE(18, hand);
     }
   }
+  if (lane == 0) tma_store_wait_all<0>();   // all global writes of this warp's bulk stores are complete before the CTA exits
 }
 
 // ABF (forward only): the A sources (agg, x) are bf16 rows.  TMA moves them as 32-bit words (a raw chunk [128 x 32
@@ -353,7 +387,8 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
 template <int NT, int MODE, bool ABF>  // NT = ceil(Nout / 32) in 1..4
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CUtensorMap tm_x,
-          const __grid_constant__ CUtensorMap tm_w, const TcProblem pb,
+          const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_s0,
+          const __grid_constant__ CUtensorMap tm_s1, const TcProblem pb,
           const float* __restrict__ b_l, const float* __restrict__ gamma,
           const float* __restrict__ beta, float eps, float slope,
           float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
@@ -633,7 +668,8 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   } else {
     reg_dec<56>();
     // ---------------------------------------------------------------- finisher --
-    FinArgs fa{N, Fout, ntiles, ngroups, slope, out, xhat, smem_u32(smem_z), gamma, beta, bar_z_full, bar_z_empty, trace};
+    FinArgs fa{N, Fout, ntiles, ngroups, slope, out, xhat, smem_u32(smem_z), gamma, beta, &tm_s0, &tm_s1,
+               bar_z_full, bar_z_empty, trace};
     finisher_role<NT, MODE, ABF>(fa);
   }
   tc_fence_before();
@@ -892,7 +928,8 @@ k_split_weights_t(const float* __restrict__ W_l, const float* __restrict__ W_r, 
 }
 
 template <int NT, int MODE, bool ABF = false>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& ms0,
+                     const CUtensorMap& ms1, const TcProblem& pb,
                      const float* b_l, const float* g, const float* b, float eps, float slope,
                      float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   const size_t smem = (size_t)kTcStages * kTcBM * 128 + (size_t)kTcBStages * 2 * pb.Nout * 128 + kTcZBytes + 1024;
@@ -905,7 +942,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
     SLDM_CUDA(cudaMalloc(&trace, sizeof(long long) * kTraceIts * kTraceEv));
     SLDM_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * kTraceIts * kTraceEv, s));
   }
-  k_sage_tc<NT, MODE, ABF><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
+  k_sage_tc<NT, MODE, ABF><<<grid, kTcThreads, smem, s>>>(ma, mx, mw, ms0, ms1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, trace);
   SLDM_LAUNCH_CHECK("k_sage_tc");
   if (trace) {
     static long long h[kTraceIts * kTraceEv];
@@ -930,14 +967,15 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtenso
 }
 
 template <int MODE, bool ABF = false>
-static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const TcProblem& pb,
+static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& ms0,
+                       const CUtensorMap& ms1, const TcProblem& pb,
                        const float* b_l, const float* g, const float* b, float eps, float slope,
                        float* out, float* xhat, float* rstd, const int32_t* rowptr, cudaStream_t s) {
   switch (ceil_div(pb.Nout, 32)) {
-    case 1: return launch_tc<1, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 2: return launch_tc<2, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    case 3: return launch_tc<3, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
-    default: return launch_tc<4, MODE, ABF>(ma, mx, mw, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 1: return launch_tc<1, MODE, ABF>(ma, mx, mw, ms0, ms1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 2: return launch_tc<2, MODE, ABF>(ma, mx, mw, ms0, ms1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    case 3: return launch_tc<3, MODE, ABF>(ma, mx, mw, ms0, ms1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
+    default: return launch_tc<4, MODE, ABF>(ma, mx, mw, ms0, ms1, pb, b_l, g, b, eps, slope, out, xhat, rstd, rowptr, s);
   }
 }
 
@@ -956,8 +994,10 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&ma, agg, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mx, x, (uint64_t)N, Fin, Fin, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
+  CUtensorMap ms = ma;   // bulk-store map of xhat (training, whole 32-column slabs): [32 rows][32 fp32] boxes out of the parked tile
+  if (xhat != nullptr && Fout % 32 == 0 && (rc = make_tmap_2d_f32(&ms, xhat, (uint64_t)N, Fout, Fout, 32, 32))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
-  return dispatch_tc<MODE_FWD>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
+  return dispatch_tc<MODE_FWD>(ma, mx, mw, ms, ms, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
 }
 
 // bf16 feature storage: agg, x and out are bf16 rows ([N,Fin] / [N,Fout] uint16), weights / LayerNorm / xhat / rstd fp32
@@ -982,8 +1022,10 @@ int project_forward_bf16_launch(const void* agg, const void* x, int64_t N, int32
   if ((rc = make_tmap_2d_f32(&ma, static_cast<const float*>(agg), (uint64_t)N, Fin / 2, Fin / 2, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mx, static_cast<const float*>(x), (uint64_t)N, Fin / 2, Fin / 2, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fout, Fin, Fin, Fout, 32))) return rc;
+  CUtensorMap ms = ma;
+  if (xhat != nullptr && Fout % 32 == 0 && (rc = make_tmap_2d_f32(&ms, xhat, (uint64_t)N, Fout, Fout, 32, 32))) return rc;
   TcProblem pb{N, Fin / 64, 2, 1, Fout};
-  return dispatch_tc<MODE_FWD, true>(ma, mx, mw, pb, b_l, ln_w, ln_b, eps, slope, static_cast<float*>(out), xhat, rstd,
+  return dispatch_tc<MODE_FWD, true>(ma, mx, mw, ms, ms, pb, b_l, ln_w, ln_b, eps, slope, static_cast<float*>(out), xhat, rstd,
                                      nullptr, s);
 }
 
@@ -1000,8 +1042,13 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
   int rc;
   if ((rc = make_tmap_2d_f32(&mz, dz, (uint64_t)N, Fout, Fout, kTcBM, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&mw, wsplit, (uint64_t)4 * Fin, Fout, Fout, Fin, 32))) return rc;
+  CUtensorMap ms0 = mz, ms1 = mz;   // bulk-store maps of dagg / dxroot (whole 32-column slabs)
+  if (Fin % 32 == 0) {
+    if ((rc = make_tmap_2d_f32(&ms0, dagg, (uint64_t)N, Fin, Fin, 32, 32))) return rc;
+    if ((rc = make_tmap_2d_f32(&ms1, dxroot, (uint64_t)N, Fin, Fin, 32, 32))) return rc;
+  }
   TcProblem pb{N, Fout / 32, 1, 2, Fin};
-  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
+  return dispatch_tc<MODE_DGRAD>(mz, mz, mw, ms0, ms1, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
 }
 
 bool wgrad_tc_eligible(int64_t N, int32_t Fin, int32_t Fout, const float* dz, const float* agg, const float* x) {

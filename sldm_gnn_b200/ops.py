@@ -179,11 +179,38 @@ def segment_reduce(src: torch.Tensor, csr: Csr, *, transpose: bool = False, mean
     return out
 
 
+def segment_mean_bf16(src: torch.Tensor, csr: Csr) -> torch.Tensor:
+    """Forward segment mean over bfloat16 rows (fp32 accumulation, one rounding): the aggregation of the bf16 feature mode."""
+    _require_cuda(src, "src")
+    src = src.contiguous()
+    N, F = src.shape
+    dev = src.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(src)
+        wsb = int(lib.sldm_segment_workspace_bytes(N, csr.E, F))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        check(lib.sldm_segment_mean_bf16(src.data_ptr(), N, F, csr.buf.data_ptr(), csr.E, out.data_ptr(), ws.data_ptr(),
+                                         wsb, _stream(dev)))
+    return out
+
+
 def project_forward(agg, x, W_l, b_l, W_r, ln_w, ln_b, eps, slope, save: bool):
     N, Fin = x.shape
     Fout = W_l.shape[0]
     dev = x.device
+    bf16 = x.dtype == torch.bfloat16
     with torch.cuda.device(dev):
+        if bf16:
+            out = torch.empty((N, Fout), dtype=torch.bfloat16, device=dev)
+            xhat = torch.empty((N, Fout), dtype=torch.float32, device=dev) if save else None
+            rstd = torch.empty((N,), dtype=torch.float32, device=dev) if save else None
+            wsb = int(lib.sldm_sage_project_workspace_bytes(N, Fin, Fout))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            check(lib.sldm_sage_project_forward_bf16(agg.data_ptr(), x.data_ptr(), N, Fin, Fout, W_l.data_ptr(),
+                                                     b_l.data_ptr(), W_r.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                                     float(eps), float(slope), out.data_ptr(), _ptr(xhat), _ptr(rstd),
+                                                     ws.data_ptr(), wsb, _stream(dev)))
+            return out, xhat, rstd
         out = torch.empty((N, Fout), dtype=torch.float32, device=dev)
         xhat = torch.empty((N, Fout), dtype=torch.float32, device=dev) if save else None
         rstd = torch.empty((N,), dtype=torch.float32, device=dev) if save else None
