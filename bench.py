@@ -463,6 +463,38 @@ def c4_record(dev, peak_gbs, steps=10):
             "note": "true random gather (no L2 absorption): SURVEY 8d's byte model is honest here"}
 
 
+def time_graphed(blk, batches, hdims, dev, fwd_only, steps=200):
+    """ms per step of the small workload through GraphedSageBlock (one bucket sized for the batch): inference = copy-in
+    + one graph launch + copy-out; training = forward graph + backward graph behind autograd.  Inputs alternate."""
+    Nmax = max(b["N"] for b in batches) + 1
+    Emax = max(b["E"] for b in batches)
+    res = {"bucket": {"max_nodes": Nmax, "max_edges": Emax}}
+    for mode in (("inference",) if fwd_only else ("inference", "training")):
+        g = blk.graphed(Nmax, Emax, training=(mode == "training"))
+
+        def step(b):
+            if mode == "inference":
+                return g(b["x"].detach(), b["ei"])
+            blk.zero_grad(set_to_none=True)
+            x = b["x"].detach().requires_grad_(True)
+            g(x, b["ei"]).backward(b["w"])
+            return x.grad
+
+        for i in range(10):
+            step(batches[i % 2])
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
+        t0.record()
+        for i in range(steps):
+            step(batches[i % 2])
+        t1.record()
+        host_ms = (time.perf_counter() - h0) * 1e3 / steps
+        t1.synchronize()
+        res[mode] = {"ms_per_step": t0.elapsed_time(t1) / steps, "host_enqueue_ms_per_step": round(host_ms, 4), "steps": steps}
+    return res
+
+
 def main_ours(args, wl):
     rank, local_rank, world = env_rank()
     assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU fallback)"
@@ -597,6 +629,21 @@ def main_ours(args, wl):
     e2e_ms_total = e0.elapsed_time(e1)
     assert loss_host == loss_host
 
+    # ---- the same step through captured CUDA graphs (GraphedSageBlock): what the launch-bound small workloads gain ----
+    graphed = None
+    if args.workload == "c1" and world == 1:
+        try:
+            graphed = time_graphed(blk, batches, hdims, dev, fwd_only)
+        except Exception as exc:                  # must never take the headline line down
+            graphed = {"error": repr(exc)[:300]}
+    grad_sync = None
+    if world > 1 and not fwd_only:               # after the exchange every rank must hold the SAME gradients, bit for bit
+        chk = ddp.flat_grad.double().sum().view(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        grad_sync = "ok" if all(torch.equal(allc[0], c) for c in allc) and bool(torch.isfinite(chk).all()) else "MISMATCH"
+        assert grad_sync == "ok", "gradient exchange left the ranks with different gradients"
+
     t = torch.tensor([ms_total, e2e_ms_total, float(E), float(graphs)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -664,6 +711,10 @@ def main_ours(args, wl):
                                         "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)")},
             "kernels": kern,
         }
+        if graphed is not None:
+            line["cuda_graph"] = graphed
+        if grad_sync is not None:
+            line["grad_sync_check"] = grad_sync
         if world == 1 and args.workload == "batch" and not args.no_c4 and not bf16:
             for b in batches:                      # release the batch workload's device buffers first
                 b.pop("x", None); b.pop("ei", None); b.pop("w", None)

@@ -216,23 +216,27 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
         // tile t are never overwritten (by tile t+2) before everybody has read them
         float* const sS = a.s_sum + (hand & 1) * 512;
         float* const sV = a.s_var + (hand & 1) * 512;
-        sS[cq * 128 + rloc] = sq;
+        sS[cq * 128 + rloc] = mq;                           // the quarter's MEAN (the merge needs means, not sums)
         sV[cq * 128 + rloc] = (pv[0] + pv[1]) + (pv[2] + pv[3]);
         named_bar_sync(2 + q, 128);
-        float s4[4], m2 = 0.f;
+        float m4[4], msum = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s4[k] = sS[k * 128 + rloc];
-        const float mean = __fdiv_rn((s4[0] + s4[1]) + (s4[2] + s4[3]), fF);
+        for (int k = 0; k < 4; ++k) {
+          m4[k] = sS[k * 128 + rloc];
+          const int nk_i = FULL ? HC : max(0, min(HC, Fout - k * HC));
+          msum = fmaf((float)nk_i, m4[k], msum);            // sum_q n_q m_q
+        }
+        const float mean = __fdiv_rn(msum, fF);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int nk_i = FULL ? HC : max(0, min(HC, Fout - k * HC));
-          const float nk = (float)nk_i;
-          const float dm = (nk_i > 0 ? __fdiv_rn(s4[k], nk) : mean) - mean;
-          m2 += sV[k * 128 + rloc] + nk * dm * dm;
+          const float dm = (nk_i > 0 ? m4[k] : mean) - mean;
+          m2 += sV[k * 128 + rloc] + (float)nk_i * dm * dm;
         }
         const float rs = __fdiv_rn(1.f, __fsqrt_rn(__fdiv_rn(m2, fF) + a.eps));
+        const float nmr = -mean * rs;
 #pragma unroll
-        for (int j = 0; j < HC; ++j) z[j] = (z[j] - mean) * rs;      // z now holds xhat
+        for (int j = 0; j < HC; ++j) z[j] = fmaf(z[j], rs, nmr);     // z now holds xhat = (z - mean) * rstd
         if (row < a.N && a.rstd != nullptr && cq == 0) a.rstd[row] = rs;
         if (tid == 256) TC_TRACE(14, it - 1);
       } else {
@@ -243,8 +247,15 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
             deg = deg < 1 ? 1 : (deg > 16777216 ? 16777216 : deg);
             cnt = (float)deg;
           }
+          // z / cnt as a reciprocal multiply with one FMA correction step: q = z*r, q += (z - q*cnt)*r.  Correctly
+          // rounded in all but rare double-rounding cases (and exact for cnt = 2^k) at 3 instructions per element
+          // instead of the ~10 of an IEEE division -- 32 divisions per thread were most of this tail.
+          const float rc = __fdiv_rn(1.f, cnt);
 #pragma unroll
-          for (int j = 0; j < HC; ++j) z[j] = __fdiv_rn(z[j], cnt);
+          for (int j = 0; j < HC; ++j) {
+            const float qv = z[j] * rc;
+            z[j] = fmaf(fmaf(-qv, cnt, z[j]), rc, qv);
+          }
         }
       }
       // ---- park the finished row for the finisher warp of this quadrant and move on

@@ -18,6 +18,10 @@
 // Measured (B200, batch workload F=128, profiles/r01b_*): generic kernel 0.38 ms (issue-bound, 362 warp instr/row),
 // lean kernel 0.27 ms; config-4 graph 1.20 -> 0.91 ms (6.2 TB/s algorithmic).
 // Bound: HBM.  Algorithmic bytes per call = E*(F*4 + 4) + 4(N+1) + N*F*4 (+N*F*4 addend).
+// Round 2 (ncu, profiles/r02_ncu_full_summary.txt): the lean kernel is issue bound on the batch workload (issue active
+// 77 %, 194 warp instructions per row, DRAM 54 %).  Tried and lost: 8 floats per lane with 256-bit loads (a 512-byte
+// row on 16 lanes, two rows per warp at a time: half the instructions per row) -- bit-identical, but 0.267 vs 0.198 ms
+// on the batch workload and 1.35 vs 0.90 ms on config 4 (44 registers, fewer resident warps, 32-byte lanes).
 #include "common.cuh"
 #include <algorithm>
 #include <type_traits>

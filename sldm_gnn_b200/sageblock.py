@@ -118,7 +118,8 @@ class _SageBlockFn(torch.autograd.Function):
             need_dx = l > 0 or ctx.needs_input_grad[0]
             dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
                 g, h, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slopes[l], need_dx,
-                record_event=ddp and l == 0)    # layer 0: the exchange of its gradients overlaps its own dx gather
+                record_event=ddp and l == 0 and not torch.cuda.is_current_stream_capturing())
+            # (layer 0: the exchange of its gradients overlaps its own dx gather)
             grads[5 * l:5 * l + 5] = [dW_l, db_l, dW_r, dln_w, dln_b]
             g = dx
         return (g, None, None, None, None, *grads)
@@ -157,9 +158,10 @@ class SageBlock(nn.Module):
     def clear_cache(self) -> None:
         self._csr_key = self._csr = None
 
-    def graphed(self, max_nodes: int, max_edges: int) -> "GraphedSageBlock":
-        """Inference through one captured CUDA graph for inputs of up to max_nodes - 1 nodes / max_edges edges."""
-        return GraphedSageBlock(self, max_nodes, max_edges)
+    def graphed(self, max_nodes: int, max_edges: int, training: bool = False) -> "GraphedSageBlock":
+        """The block through captured CUDA graphs for inputs of up to max_nodes - 1 nodes / max_edges edges
+        (inference: one graph; training=True: a forward and a backward graph behind autograd)."""
+        return GraphedSageBlock(self, max_nodes, max_edges, training=training)
 
     def forward(self, x, edge_index, batch=None):
         if len(self.convs) == 0:
@@ -202,23 +204,41 @@ class SageBlock(nn.Module):
         return _SageBlockFn.apply(x, csr, eps, slopes, drops, *params)
 
 
+class _UncachedBlock(nn.Module):
+    """The block with its CSR cache switched off: inside a CUDA graph the CSR build must be part of every replay."""
+
+    def __init__(self, block: "SageBlock"):
+        super().__init__()
+        self.block = block
+
+    def forward(self, x, edge_index):
+        self.block.clear_cache()
+        y = self.block(x, edge_index)
+        self.block.clear_cache()
+        return y
+
+
 class GraphedSageBlock:
-    """Inference through ONE captured CUDA graph per size bucket -- the reference's real operating point is
-    launch-bound: eval batches of 64 graphs (test.py:58) and, online, one un-batched graph of tens to ~300 vehicles
-    per call from a worker thread (rcv.py:77-84, :107), where ~20 kernel launches and their Python glue cost more
-    than the kernels.
+    """The block through captured CUDA graphs, one per size bucket -- the reference's real operating point is
+    launch-bound: training batches of 32 graphs (main.py:24), eval batches of 64 (test.py:58) and, online, one
+    un-batched graph of tens to ~300 vehicles per call from a worker thread (rcv.py:77-84, :107), where the ~20
+    (forward) / ~43 (forward + backward) kernel launches and their Python glue cost several times the kernels.
 
-        g = blk.graphed(max_nodes=512, max_edges=4096)     # captures CSR build + all layers once
-        y = g(x, edge_index)                               # copy-in, one graph launch, copy-out
+        g = blk.graphed(max_nodes=512, max_edges=4096)                 # inference: CSR build + all layers, one graph
+        y = g(x, edge_index)                                           # copy-in, one graph launch, copy-out
+        g = blk.graphed(max_nodes=8192, max_edges=40960, training=True)
+        loss(g(x, edge_index)).backward()                              # forward graph + backward graph, autograd-aware
 
-    The captured step works on static buffers of the bucket's size: x is copied into the first N rows (the rest stay
-    zero), edge_index into the first E columns, the remaining columns point at the last padding node (p, p) -- edges
-    among padding rows never touch a real node, and every kernel is row-wise independent, so rows [0, N) of the
-    result are bit-identical to the un-captured module's.  Requires N < max_nodes (one padding node) and
-    E <= max_edges; inference only (no autograd), eval-mode dropout.  Thread-safe: calls serialise on a lock.
+    The captured step works on static buffers of the bucket's size: x is copied into the first N rows, edge_index into
+    the first E columns, the remaining columns point at the last padding node (p, p) -- edges among padding rows never
+    touch a real node, and every kernel is row-wise independent, so rows [0, N) of the result (and of dx) are
+    bit-identical to the un-captured module's; the parameter gradients see only zero upstream gradient from the
+    padding rows.  Requires N < max_nodes (one padding node) and E <= max_edges.  Inference: eval-mode dropout, the
+    result is a copy.  Training (torch.cuda.make_graphed_callables): the result is a view of the graph's static
+    output, valid until the next call.  Thread-safe: calls serialise on a lock.
     """
 
-    def __init__(self, block: "SageBlock", max_nodes: int, max_edges: int, device=None):
+    def __init__(self, block: "SageBlock", max_nodes: int, max_edges: int, training: bool = False, device=None):
         import threading
         if len(block.convs) == 0:
             raise ValueError("GraphedSageBlock: the block has no layers")
@@ -226,30 +246,46 @@ class GraphedSageBlock:
         dev = torch.device(device) if device is not None else p0.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedSageBlock: CUDA only")
-        self.block, self.dev = block, dev
+        self.block, self.dev, self.training = block, dev, bool(training)
         self.max_nodes, self.max_edges = int(max_nodes), int(max_edges)
         self.fin, self.fout = block.convs[0].in_channels, block.convs[-1].out_channels
         self._lock = threading.Lock()
-        with torch.cuda.device(dev), torch.inference_mode():
+        with torch.cuda.device(dev):
             self._x = torch.zeros((self.max_nodes, self.fin), dtype=torch.float32, device=dev)
             self._ei = torch.full((2, self.max_edges), self.max_nodes - 1, dtype=torch.long, device=dev)
-            was_training = block.training
-            block.eval()
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):                  # warm-up outside the capture: opt-in attributes, tensor maps
-                for _ in range(2):
-                    block.clear_cache()
-                    block(self._x, self._ei)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            ops.index_checks.poll(block=True)              # nothing may be pending when the capture starts
-            self._graph = torch.cuda.CUDAGraph()
-            block.clear_cache()
-            with torch.cuda.graph(self._graph):
-                self._y = block(self._x, self._ei)
-            block.clear_cache()
-            block.train(was_training)
+            ops.index_checks.poll(block=True)                  # nothing may be pending when a capture starts
+            if self.training:
+                self._x.requires_grad_(True)
+                self._call = torch.cuda.make_graphed_callables(_UncachedBlock(block), (self._x, self._ei))
+                return
+            with torch.inference_mode():
+                was_training = block.training
+                block.eval()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):                  # warm-up outside the capture: opt-in attributes, tensor maps
+                    for _ in range(2):
+                        block.clear_cache()
+                        block(self._x, self._ei)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                ops.index_checks.poll(block=True)
+                self._graph = torch.cuda.CUDAGraph()
+                block.clear_cache()
+                with torch.cuda.graph(self._graph):
+                    self._y = block(self._x, self._ei)
+                block.clear_cache()
+                block.train(was_training)
+
+    def _fill(self, x, edge_index, N, E):
+        with torch.no_grad():
+            if x is not None:
+                self._x[:N].copy_(x, non_blocking=True)
+            self._ei[:, :E].copy_(edge_index, non_blocking=True)
+            if E < self.max_edges:
+                self._ei[:, E:].fill_(self.max_nodes - 1)
+        # rows beyond N keep whatever an earlier, larger call left there: they are padding rows (no edge from a real
+        # node reaches them), so their values never matter
 
     def __call__(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         ops.check_edge_index(edge_index)
@@ -259,12 +295,14 @@ class GraphedSageBlock:
         if N >= self.max_nodes or E > self.max_edges:
             raise RuntimeError(f"GraphedSageBlock: N = {N}, E = {E} exceed the bucket ({self.max_nodes - 1} nodes, "
                                f"{self.max_edges} edges)")
-        with self._lock, torch.cuda.device(self.dev), torch.inference_mode():
-            self._x[:N].copy_(x, non_blocking=True)
-            self._ei[:, :E].copy_(edge_index, non_blocking=True)
-            if E < self.max_edges:
-                self._ei[:, E:].fill_(self.max_nodes - 1)
-            # rows beyond N keep whatever an earlier, larger call left there: they are padding rows (no edge from a
-            # real node reaches them), so their values never matter
-            self._graph.replay()
-            return self._y[:N].clone()
+        with self._lock, torch.cuda.device(self.dev):
+            if self.training:
+                self._fill(None, edge_index, N, E)
+                # zero-padded copy of x through autograd (dx flows back to the caller's tensor); the graphed callable
+                # copies it into its static input and replays the forward graph, its backward replays the other one
+                xs = torch.nn.functional.pad(x, (0, 0, 0, self.max_nodes - N))
+                return self._call(xs, self._ei)[:N]
+            with torch.inference_mode():
+                self._fill(x, edge_index, N, E)
+                self._graph.replay()
+                return self._y[:N].clone()

@@ -62,6 +62,37 @@ def test_graphed_from_worker_threads(dev):
         assert torch.equal(a, b)
 
 
+def test_graphed_training_matches_eager(dev):
+    """Training through the forward / backward graph pair: output and dx equal the eager module's bit for bit (same
+    kernels on padded buffers, every kernel row-wise independent); the parameter gradients are split-K sums whose
+    slab boundaries depend on the (padded) row count, so they agree to fp32 rounding, not bit for bit."""
+    torch.manual_seed(3)
+    hdims = [64, 64, 64]
+    blk = sg.SageBlock(hdims, negative_slope=0.1).to(dev).train()
+    g = blk.graphed(max_nodes=1024, max_edges=5000, training=True)
+    for n_graphs, seed in ((2, 0), (4, 1), (1, 2)):
+        x, ei = _case(n_graphs, seed, hdims[0], dev)
+        w = torch.randn(x.size(0), hdims[-1], device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+        res = []
+        for fn in (blk, g):
+            blk.zero_grad(set_to_none=True)
+            xg = x.clone().requires_grad_(True)
+            y = fn(xg, ei)
+            (y * w).sum().backward()
+            res.append([y.detach().clone(), xg.grad.clone()] + [p.grad.clone() for p in blk.parameters()])
+        for a, b in zip(res[0][:2], res[1][:2]):
+            assert torch.equal(a, b), (n_graphs, seed)
+        for a, b in zip(res[0][2:], res[1][2:]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * max(1.0, float(a.abs().max()))), (n_graphs, seed)
+    opt = torch.optim.SGD(blk.parameters(), lr=0.1)         # parameters are updated in place: the graphs see the new values
+    x, ei = _case(2, 5, hdims[0], dev)
+    blk.zero_grad(set_to_none=True)
+    g(x, ei).square().mean().backward()
+    opt.step()
+    with torch.no_grad():
+        assert torch.equal(g(x, ei), blk(x, ei))
+
+
 def test_dropout_matches_torch_functional_dropout(dev):
     """The block's dropout is torch.native_dropout: the kernel nn.Dropout / F.dropout dispatch to on CUDA, so the global
     Philox stream is consumed exactly as by the reference's posts[i][2] (src/models/blocks/sageblock.py:13)."""
