@@ -101,6 +101,11 @@ int     sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
                        int32_t* csr, void* workspace, int64_t workspace_bytes,
                        sldm_stream_t stream);
 
+/* Deferred range report: copies meta[2] of a built CSR object into *status_host_pinned (page-locked host memory the
+ * caller preset to -1) behind the build on `stream`, without synchronising: 0 = all indices in range, 1 = some index
+ * was outside [0, N) (the reference stack raises IndexError / a device assert there; see sldm_gnn_b200/ops.py). */
+int     sldm_csr_status_async(const int32_t* csr, int32_t* status_host_pinned, sldm_stream_t stream);
+
 /* Same build from two separate int64 rows.  edge_src == NULL means source ids 0..E-1: the result is then a
  * membership list (row k of rowptr_dst / col_src = the positions e with edge_dst[e] == k, ascending), which is how
  * the graph readout below obtains the nodes of every graph from PyG's `batch` vector.  In that mode N only bounds

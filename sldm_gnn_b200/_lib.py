@@ -39,6 +39,7 @@ _PROTOS = {
     "sldm_csr_layout": (C.c_int, [_i64, _i64, C.POINTER(_i64)]),
     "sldm_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "sldm_csr_build": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p]),
+    "sldm_csr_status_async": (C.c_int, [_p, _p, _p]),
     "sldm_csr_build_pairs": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _p]),
     "sldm_segment_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "sldm_segment_reduce": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p]),

@@ -489,6 +489,15 @@ extern "C" int64_t sldm_csr_workspace_bytes(int64_t N, int64_t E) {
   return csr_ws_layout(N, E).total;
 }
 
+// meta[2] (1 if any index was outside [0, N)) -> *status_host_pinned, asynchronously behind the build on `stream`:
+// the host presets the word to -1 and reads 0 / 1 once the copy has landed -- no event, no synchronisation.
+extern "C" int sldm_csr_status_async(const int32_t* csr, int32_t* status_host_pinned, sldm_stream_t stream) {
+  SLDM_REQUIRE(csr != nullptr && status_host_pinned != nullptr, SLDM_EINVAL, "sldm_csr_status_async: NULL pointer");
+  SLDM_CUDA(cudaMemcpyAsync(status_host_pinned, csr + 2, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                            static_cast<cudaStream_t>(stream)));
+  return SLDM_OK;
+}
+
 extern "C" int sldm_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
                               int32_t* csr, void* workspace, int64_t workspace_bytes,
                               sldm_stream_t stream) {

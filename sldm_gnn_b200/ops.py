@@ -46,63 +46,67 @@ class _IndexChecks:
 
     The reference stack fails on them (CPU: IndexError from index_select / scatter_add_; CUDA: a device-side assert
     that surfaces at a later synchronisation).  The CSR build clamps such ids so that no kernel leaves its buffers and
-    raises meta[2]; here that flag is copied to pinned host memory behind the build (asynchronously) and looked at
-    when the copy has landed -- at the latest on the next call into this package -- where it raises IndexError, i.e.
-    the error is deferred like a CUDA device assert, never silent.  SLDM_CHECK_INDICES=1 checks synchronously at the
-    build (one host sync per new edge_index), =0 switches the check off.
+    raises meta[2]; sldm_csr_status_async copies that word into a slot of a page-locked ring behind the build (the
+    slot is preset to -1 on the host) and the slot is looked at once it has landed -- at the latest on the next call
+    into this package -- where it raises IndexError: the error is deferred like a CUDA device assert, never silent.
+    Cost on the hot path: one 4-byte cudaMemcpyAsync per new edge_index, no event, no synchronisation.
+    SLDM_CHECK_INDICES=1 checks synchronously at the build (one host sync per new edge_index), =0 switches it off.
     """
 
     SLOTS = 256
 
     def __init__(self):
         self.lock = threading.Lock()
-        self.pending = collections.deque()
-        self.ring = {}
+        self.pending = collections.deque()      # (slot index, description), oldest first
+        self.ring = None                        # pinned int32 tensor, its numpy view, its address
+        self.next = 0
 
     @staticmethod
     def mode() -> str:
         return os.environ.get("SLDM_CHECK_INDICES", "deferred")
 
-    def watch(self, meta: torch.Tensor, what: str) -> None:
+    def watch(self, csr_buf: torch.Tensor, what: str) -> None:
         mode = self.mode()
         if mode == "0":
             return
         if mode == "1":
-            if int(meta[2]) != 0:
+            if int(csr_buf[2]) != 0:
                 raise IndexError(f"{what}: index out of range")
             return
-        dev = meta.device
         if torch.cuda.is_current_stream_capturing():
             return
         with self.lock:
+            if self.ring is None:
+                t = torch.full((self.SLOTS,), -1, dtype=torch.int32).pin_memory()
+                self.ring = (t, t.numpy(), t.data_ptr())
             if len(self.pending) >= self.SLOTS - 1:
                 self._drain(block=True)
-            ring = self.ring.get(dev)
-            if ring is None:
-                ring = self.ring[dev] = [torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory(), 0]
-            slot = ring[0][ring[1] % self.SLOTS: ring[1] % self.SLOTS + 1]
-            ring[1] += 1
-            slot.copy_(meta[2:3], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            self.pending.append((ev, slot, what))
+            i = self.next % self.SLOTS
+            self.next += 1
+            self.ring[1][i] = -1
+            check(lib.sldm_csr_status_async(csr_buf.data_ptr(), self.ring[2] + 4 * i, _stream(csr_buf.device)))
+            self.pending.append((i, what))
 
     def _drain(self, block: bool) -> None:
         bad = None
+        arr = self.ring[1]
         while self.pending:
-            ev, slot, what = self.pending[0]
-            if not block and not ev.query():
-                break
-            ev.synchronize()
+            i, what = self.pending[0]
+            v = int(arr[i])
+            if v < 0:
+                if not block:
+                    break
+                torch.cuda.synchronize()
+                v = int(arr[i])
             self.pending.popleft()
-            if int(slot[0]) != 0 and bad is None:
+            if v > 0 and bad is None:
                 bad = what
         if bad is not None:
             raise IndexError(f"{bad}: index out of range (reported by an earlier device-side CSR build; "
                              "SLDM_CHECK_INDICES=1 raises at the call that passed it)")
 
     def poll(self, block: bool = False) -> None:
-        if not self.pending or torch.cuda.is_current_stream_capturing():   # (event queries are illegal during capture)
+        if not self.pending or torch.cuda.is_current_stream_capturing():   # (no host syncs during a capture)
             return
         with self.lock:
             self._drain(block)
@@ -158,7 +162,7 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int) -> Csr:
                                  _stream(dev)))
         csr = Csr(buf, N, E, layout)
         if E > 0:
-            index_checks.watch(csr.meta, f"edge_index (num_nodes = {N})")
+            index_checks.watch(buf, f"edge_index (num_nodes = {N})")
     return csr
 
 

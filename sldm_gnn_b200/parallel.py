@@ -98,7 +98,7 @@ class GraphDataParallel(nn.Module):
         self._comm = torch.cuda.Stream(device=dev) if self._overlap else None
         self._weight = None                      # set by expect_sync(): hooks may launch buckets during backward
         self._launched = set()
-        if self._overlap:
+        if self._overlap and self._ready():        # (single process: no exchange, no per-parameter Python hooks)
             for p in self._params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
 

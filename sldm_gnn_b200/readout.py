@@ -36,7 +36,7 @@ def _membership_csr(batch: torch.Tensor, N: int, G: int) -> Csr:
                                        wsb if N > 0 else 0, _stream(dev)))
         csr = Csr(buf, nodes, N, layout)
         if N > 0:
-            index_checks.watch(csr.meta, f"batch vector (num_graphs = {G})")
+            index_checks.watch(buf, f"batch vector (num_graphs = {G})")
     return csr
 
 
