@@ -556,6 +556,28 @@ def main_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    overlap_check = None
+    if world > 1 and not fwd_only:
+        # The overlapped exchange (buckets written by the kernels and all-reduced from inside backward) must give the
+        # SAME bits as the plain one (autograd accumulation, everything exchanged after backward) on the same batch.
+        def grads_of(b, overlap):
+            ddp.zero_grad()
+            b["x"].grad = None
+            if overlap:
+                ddp.expect_sync(local_weight=b["graphs"])
+            blk.clear_cache()
+            ddp(b["x"], b["ei"]).backward(b["w"])
+            ddp.sync_gradients(local_weight=b["graphs"])
+            return ddp.flat_grad.clone()
+
+        for _ in range(3):
+            ga, gb = grads_of(batches[0], True), grads_of(batches[0], False)
+            same = torch.equal(ga, gb)
+            flag = torch.tensor([0 if same else 1], device=dev)
+            dist.all_reduce(flag)
+            overlap_check = "ok" if int(flag) == 0 else "MISMATCH"
+            assert overlap_check == "ok", "overlapped gradient exchange differs from the plain exchange"
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -715,6 +737,7 @@ def main_ours(args, wl):
             line["cuda_graph"] = graphed
         if grad_sync is not None:
             line["grad_sync_check"] = grad_sync
+            line["grad_overlap_check"] = overlap_check
         if world == 1 and args.workload == "batch" and not args.no_c4 and not bf16:
             for b in batches:                      # release the batch workload's device buffers first
                 b.pop("x", None); b.pop("ei", None); b.pop("w", None)

@@ -272,24 +272,17 @@ def layer_forward(x, csr: Csr, W_l, b_l, W_r, ln_w, ln_b, eps: float, slope: flo
     return x, out, agg, xhat, rstd
 
 
-# ---- "parameter gradients of the last layer_backward are complete" event (consumed by parallel.GraphDataParallel) ----
-_param_grad_events: dict = {}
-
-
-def take_param_grad_event(dev):
-    """The event layer_backward recorded after its weight-gradient reduction and BEFORE launching the dx gather, or
-    None.  One-shot: a data-parallel wrapper waits on it from its side stream so that the gradient exchange of the
-    layer overlaps the gather."""
-    return _param_grad_events.pop(torch.device(dev), None)
-
-
-def backward_buffers(N: int, Fin: int, Fout: int, E: int, dev, need_dx: bool) -> dict:
-    """Outputs, scratch and workspace of one layer_backward call."""
+def backward_buffers(N: int, Fin: int, Fout: int, E: int, dev, need_dx: bool, grad_out=None) -> dict:
+    """Outputs, scratch and workspace of one layer_backward call.  grad_out: five preallocated fp32 tensors
+    (dW_l, db_l, dW_r, dln_w, dln_b) the kernels write the parameter gradients into (a data-parallel bucket)."""
     with torch.cuda.device(dev):
         f32 = dict(dtype=torch.float32, device=dev)
-        b = dict(dW_l=torch.empty((Fout, Fin), **f32), dW_r=torch.empty((Fout, Fin), **f32),
-                 db_l=torch.empty((Fout,), **f32), dln_w=torch.empty((Fout,), **f32), dln_b=torch.empty((Fout,), **f32),
-                 dz=torch.empty((N, Fout), **f32), dx=None, dagg=None, dxroot=None)
+        if grad_out is not None:
+            b = dict(dW_l=grad_out[0], db_l=grad_out[1], dW_r=grad_out[2], dln_w=grad_out[3], dln_b=grad_out[4])
+        else:
+            b = dict(dW_l=torch.empty((Fout, Fin), **f32), dW_r=torch.empty((Fout, Fin), **f32),
+                     db_l=torch.empty((Fout,), **f32), dln_w=torch.empty((Fout,), **f32), dln_b=torch.empty((Fout,), **f32))
+        b.update(dz=torch.empty((N, Fout), **f32), dx=None, dagg=None, dxroot=None)
         if need_dx:
             b.update(dx=torch.empty((N, Fin), **f32), dagg=torch.empty((N, Fin), **f32),
                      dxroot=torch.empty((N, Fin), **f32))
@@ -300,16 +293,18 @@ def backward_buffers(N: int, Fin: int, Fout: int, E: int, dev, need_dx: bool) ->
 
 
 def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slope: float, need_dx: bool,
-                   stages: int = _lib.BWD_STAGE_ALL, bufs: dict | None = None, record_event: bool = False):
+                   stages: int = _lib.BWD_STAGE_ALL, bufs: dict | None = None, on_param_grads=None, grad_out=None):
     """Returns (dx | None, dW_l, db_l, dW_r, dln_w, dln_b).
 
     `stages` / `bufs` are for profiling (bench.py): launch only the masked kernels on the buffers of an earlier
-    full call (include/sldm_sage.h, SLDM_BWD_STAGE_*)."""
+    full call (include/sldm_sage.h, SLDM_BWD_STAGE_*).  grad_out: write the parameter gradients into these five
+    tensors; on_param_grads(event): called with an event recorded when the parameter gradients are final on the
+    stream, BEFORE the dx gather is launched (a data-parallel wrapper starts the layer's exchange there)."""
     N, Fin = x.shape
     Fout = W_l.shape[0]
     dev = x.device
     dout = dout.contiguous()
-    b = bufs if bufs is not None else backward_buffers(N, Fin, Fout, csr.E, dev, need_dx)
+    b = bufs if bufs is not None else backward_buffers(N, Fin, Fout, csr.E, dev, need_dx, grad_out)
 
     entry = lib.sldm_sage_layer_backward_bf16 if x.dtype == torch.bfloat16 else lib.sldm_sage_layer_backward_stages
     if x.dtype != agg.dtype or dout.dtype != torch.float32:
@@ -324,13 +319,14 @@ def layer_backward(dout, x, agg, xhat, rstd, csr: Csr, W_l, W_r, ln_w, ln_b, slo
             _stream(dev), int(mask)))
 
     with torch.cuda.device(dev):
-        if record_event and need_dx and stages == _lib.BWD_STAGE_ALL and N > 0:
+        if on_param_grads is not None and stages == _lib.BWD_STAGE_ALL:
             # the parameter gradients are final before the dx gather starts: mark that point on the stream
             launch(_lib.BWD_STAGE_ALL & ~_lib.BWD_STAGE_GATHER)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
-            _param_grad_events[torch.device(dev)] = ev
-            launch(_lib.BWD_STAGE_GATHER)
+            on_param_grads(ev)
+            if need_dx and N > 0:
+                launch(_lib.BWD_STAGE_GATHER)
         else:
             launch(stages)
     return b["dx"], b["dW_l"], b["db_l"], b["dW_r"], b["dln_w"], b["dln_b"]

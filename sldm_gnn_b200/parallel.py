@@ -9,12 +9,20 @@ sum of the parameter gradients (~130-175 KB for a SageBlock), latency bound by c
 All parameters of the wrapped module live in ONE flat fp32 buffer and so do their
 gradients.  The gradient buffer is cut into BUCKETS in the order the backward pass
 finishes them (the last SageBlock layer first); each bucket carries one extra slot for
-the loss weight.  A post-accumulate hook on every parameter counts a bucket down and,
-when its last gradient has landed, launches that bucket's all-reduce on a side stream:
-the exchange of layer l runs under the backward kernels of layer l-1, and the exchange
-of the first layer under its own transpose gather (ops.layer_backward records an event
-after the weight-gradient reduction, before the dx gather is launched).
-`sync_gradients()` only waits for what is still in flight.
+the loss weight.  Two ways a bucket gets on its way while backward is still running:
+  * SageBlock layers (the whole block is ONE autograd node, so the engine would only
+    hand over their gradients after the last layer's backward): the block's backward
+    asks the armed wrapper for the bucket views of a layer's five parameters
+    (`claim()`), lets the kernels write dW_l, db_l, dW_r, dgamma, dbeta STRAIGHT into
+    them, records an event after the weight-gradient reduction -- before the layer's dx
+    gather is launched -- and calls `bucket_ready()`: the all-reduce of layer l runs on a
+    side stream under the gather of layer l and the backward kernels of layer l-1.
+    Autograd sees `None` for those parameters (their .grad IS the bucket view).
+  * every other parameter: a post-accumulate hook counts its bucket down and launches the
+    all-reduce behind an event recorded when the last accumulation has been enqueued.
+`sync_gradients()` only waits for what is still in flight.  The direct-write path needs
+gradients that were zeroed since the last backward (`zero_grad()` arms it, `expect_sync()`
+confirms it); otherwise everything falls back to autograd accumulation + hooks.
 
 LayerNorm is per node, so there are no cross-rank statistics.  A loss that is a mean
 over the local graphs needs the per-rank gradient weighted by the local graph count to
@@ -28,6 +36,13 @@ import re
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+
+
+_ACTIVE = None      # the wrapper armed by expect_sync() (one per process: one rank, one model replica)
+
+
+def active_wrapper():
+    return _ACTIVE
 
 
 def shard_graphs(num_graphs: int, rank: int, world_size: int) -> range:
@@ -84,6 +99,7 @@ class GraphDataParallel(nn.Module):
                 b["hi"] = goff
                 goff += 1                                                # the bucket's weight slot
                 self._buckets.append(b)
+        self._whole_bucket = {frozenset(id(p) for p in b["params"]): bi for bi, b in enumerate(self._buckets)}
         # zero_grad() is ONE copy of this template: zeros, and 1.0 in every bucket's weight slot (scaled with the bucket)
         self._template = torch.zeros_like(self._flat_grad)
         for b in self._buckets:
@@ -96,8 +112,9 @@ class GraphDataParallel(nn.Module):
         # ---- overlap machinery (CUDA only): hooks + one side stream
         self._overlap = bool(overlap and self._flat.is_cuda)
         self._comm = torch.cuda.Stream(device=dev) if self._overlap else None
-        self._weight = None                      # set by expect_sync(): hooks may launch buckets during backward
+        self._weight = None                      # set by expect_sync(): buckets may leave during backward
         self._launched = set()
+        self._zeroed = True                      # gradients are zero (fresh, or zero_grad() since the last backward)
         if self._overlap and self._ready():        # (single process: no exchange, no per-parameter Python hooks)
             for p in self._params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
@@ -119,6 +136,7 @@ class GraphDataParallel(nn.Module):
         for b in self._buckets:
             b["pending"] = len(b["params"])
         self._launched.clear()
+        self._zeroed = True
 
     @property
     def flat_grad(self) -> torch.Tensor:
@@ -133,9 +151,34 @@ class GraphDataParallel(nn.Module):
 
     # ------------------------------------------------------------------ exchange --
     def expect_sync(self, local_weight: float | None = None) -> None:
-        """Call before backward() to let the hooks start each bucket's all-reduce as soon as it is complete
-        (needs the weight up front).  Without it sync_gradients() launches everything itself."""
+        """Call after zero_grad() and before backward() to let every bucket's all-reduce start as soon as backward
+        has produced it (needs the weight up front).  Without it sync_gradients() launches everything itself."""
         self._weight = 1.0 if local_weight is None else float(local_weight)
+        global _ACTIVE
+        _ACTIVE = self if (self._overlap and self._ready() and self._zeroed) else None
+
+    # -- direct-write path, called from SageBlock's backward (sageblock._SageBlockFn) ------------------------------
+    def claim(self, params):
+        """The bucket views of `params` (in that order) if they are exactly one whole bucket of this armed wrapper
+        whose gradients are still zero and un-exchanged -- the kernels may then write into them directly -- else None."""
+        if _ACTIVE is not self or self._weight is None or not self._zeroed:
+            return None
+        bi = self._whole_bucket.get(frozenset(id(p) for p in params))
+        if bi is None or bi in self._launched:
+            return None
+        views = []
+        for p in params:
+            b, v = self._bucket_of[id(p)]
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                return None
+            views.append(v)
+        return bi, views
+
+    def bucket_ready(self, bi: int, event) -> None:
+        """The gradients of bucket `bi` are final on the current stream at `event`: exchange it on the side stream."""
+        self._comm.wait_event(event)
+        with torch.cuda.stream(self._comm):
+            self._reduce_bucket(bi, self._weight)
 
     def _reduce_bucket(self, bi: int, w: float) -> None:
         """sum_r w_r g_r / sum_r w_r for one bucket: the weight slot holds 1.0 (zero_grad's template), so scaling the
@@ -169,11 +212,9 @@ class GraphDataParallel(nn.Module):
         b["pending"] -= 1
         if b["pending"] != 0 or bi in self._launched:
             return
-        from . import ops                          # late: parallel.py is also used with CPU modules (gloo tests)
         main = torch.cuda.current_stream(self._flat.device)
-        ev = ops.take_param_grad_event(self._flat.device)      # recorded before the dx gather of this layer, if any
-        if ev is None:
-            ev = torch.cuda.Event(); ev.record(main)
+        ev = torch.cuda.Event()
+        ev.record(main)                            # every accumulation of this bucket has been enqueued before this point
         self._comm.wait_event(ev)
         with torch.cuda.stream(self._comm):
             self._reduce_bucket(bi, self._weight)
@@ -208,5 +249,9 @@ class GraphDataParallel(nn.Module):
                         self._reduce_bucket(bi, w)
         self._weight = None
         self._launched.clear()
+        self._zeroed = False
+        global _ACTIVE
+        if _ACTIVE is self:
+            _ACTIVE = None
         for b in self._buckets:
             b["pending"] = len(b["params"])

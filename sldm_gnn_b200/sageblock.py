@@ -106,7 +106,12 @@ class _SageBlockFn(torch.autograd.Function):
         params = saved[len(saved) - 5 * L:]
         it = iter(saved[:len(saved) - 5 * L])
         keep = [next(it) if present else None for present in ctx.layout]
-        ddp = torch.distributed.is_available() and torch.distributed.is_initialized()
+        # a data-parallel wrapper armed by expect_sync() hands out its bucket views: the kernels write the parameter
+        # gradients straight into them and the layer's exchange starts before its dx gather (parallel.py)
+        sink = None
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and not torch.cuda.is_current_stream_capturing():
+            from .parallel import active_wrapper
+            sink = active_wrapper()
         grads = [None] * (5 * L)
         g = dout if dout.dtype == torch.float32 else dout.float()    # bf16 features: the gradient path stays fp32
         for l in range(L - 1, -1, -1):
@@ -116,11 +121,16 @@ class _SageBlockFn(torch.autograd.Function):
                 g = torch.ops.aten.native_dropout_backward(g, mask, 1.0 / (1.0 - ctx.drops[l]))
             g = g.contiguous()
             need_dx = l > 0 or ctx.needs_input_grad[0]
-            dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
-                g, h, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slopes[l], need_dx,
-                record_event=ddp and l == 0 and not torch.cuda.is_current_stream_capturing())
-            # (layer 0: the exchange of its gradients overlaps its own dx gather)
-            grads[5 * l:5 * l + 5] = [dW_l, db_l, dW_r, dln_w, dln_b]
+            claim = sink.claim(params[5 * l:5 * l + 5]) if sink is not None else None
+            if claim is not None:
+                bi, views = claim
+                dx = ops.layer_backward(g, h, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slopes[l], need_dx,
+                                        grad_out=views, on_param_grads=lambda ev, bi=bi: sink.bucket_ready(bi, ev))[0]
+                # grads stay None: the parameters' .grad ARE the bucket views the kernels just wrote
+            else:
+                dx, dW_l, db_l, dW_r, dln_w, dln_b = ops.layer_backward(
+                    g, h, agg, xhat, rstd, ctx.csr, W_l, W_r, ln_w, ln_b, ctx.slopes[l], need_dx)
+                grads[5 * l:5 * l + 5] = [dW_l, db_l, dW_r, dln_w, dln_b]
             g = dx
         return (g, None, None, None, None, *grads)
 
