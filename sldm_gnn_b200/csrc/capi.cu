@@ -4,6 +4,7 @@
 #include <string.h>
 #include <vector>
 #include <atomic>
+#include <mutex>
 
 namespace sldm {
 
@@ -223,15 +224,63 @@ extern "C" int sldm_sage_layer_backward_bf16(const float* dout, const void* x, c
 
 // -------------------------------------------------- host buffers in and out --
 namespace {
+// Device memory of the host-buffer entry points comes from a small caching pool (per process, all devices): a block is
+// handed back on destruction and reused by the next call of at least that size on the same device, so a caller that
+// loops over sldm_sage_block_*_host pays cudaMalloc / cudaFree once, not ~25 times per call.  Blocks are only reused
+// after the call that owned them has synchronised its stream.  SLDM_HOST_POOL_MB caps what is kept (default 4096).
+struct DevPool {
+  struct Block { void* p; size_t bytes; int dev; };
+  std::mutex mu;
+  std::vector<Block> free_blocks;
+  size_t kept = 0;
+  static size_t cap() {
+    static size_t c = [] { const char* e = getenv("SLDM_HOST_POOL_MB"); return (size_t)(e ? atoll(e) : 4096) << 20; }();
+    return c;
+  }
+  void* take(size_t bytes, int dev, size_t* real) {
+    std::lock_guard<std::mutex> g(mu);
+    int best = -1;
+    for (int i = 0; i < (int)free_blocks.size(); ++i)
+      if (free_blocks[i].dev == dev && free_blocks[i].bytes >= bytes && free_blocks[i].bytes <= 2 * bytes + (1 << 20) &&
+          (best < 0 || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
+    if (best < 0) return nullptr;
+    void* p = free_blocks[best].p;
+    *real = free_blocks[best].bytes;
+    kept -= free_blocks[best].bytes;
+    free_blocks.erase(free_blocks.begin() + best);
+    return p;
+  }
+  void give(void* p, size_t bytes, int dev) {
+    std::lock_guard<std::mutex> g(mu);
+    if (kept + bytes > cap()) { cudaFree(p); return; }
+    free_blocks.push_back({p, bytes, dev});
+    kept += bytes;
+  }
+};
+DevPool& pool() { static DevPool* p = new DevPool; return *p; }   // leaked on purpose: no CUDA calls at exit
+
+thread_local cudaStream_t g_host_call_stream = nullptr;   // stream of the _host call running on this thread
+
 struct DevBuf {
   void* p = nullptr;
-  int alloc(int64_t bytes) {
-    if (bytes <= 0) bytes = 256;
-    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  size_t bytes = 0;
+  int dev = 0;
+  cudaStream_t s = nullptr;
+  int alloc(int64_t n) {
+    if (n <= 0) n = 256;
+    bytes = (size_t)((n + 255) / 256 * 256);
+    s = g_host_call_stream;
+    cudaGetDevice(&dev);
+    size_t real = 0;
+    p = pool().take(bytes, dev, &real);
+    if (p) { bytes = real; return SLDM_OK; }
+    cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
     return SLDM_OK;
   }
-  ~DevBuf() { if (p) cudaFree(p); }
+  // (a block goes back only when nothing on the call's stream can still touch it: a no-op after the final sync of a
+  //  successful call, a real wait on the error paths that return early)
+  ~DevBuf() { if (p) { if (s) cudaStreamSynchronize(s); pool().give(p, bytes, dev); } }
   template <typename T> T* as() { return static_cast<T*>(p); }
 };
 }  // namespace
@@ -264,7 +313,8 @@ static int block_host_impl(const float* x_h, const int64_t* ei_h, int64_t N, int
   }
   cudaStream_t s = nullptr;
   SLDM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{s};
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { g_host_call_stream = nullptr; cudaStreamDestroy(s); } } guard{s};
+  g_host_call_stream = s;
 
   int Fmax = 0;
   for (int l = 0; l <= L; ++l) Fmax = hdims[l] > Fmax ? hdims[l] : Fmax;

@@ -47,11 +47,13 @@
 // partial-line writes, 0.507 ms); LayerNorm in a lane-per-column finisher (2.9k cycles per 4 rows of shuffles and
 // divisions: 0.587 ms) and in a thread-per-row finisher over the parked tile (0.470 ms: four warps cannot absorb it);
 // deeper rings (A 3..8, B 2..3: no change).  Timing-only experiments (wrong results, -DSLDM_TC_NOSTORE / weights loaded
-// once): without the 128 KB of stores per tile 0.300 ms (the finisher's 64 STG.128 per warp and tile take ~11k cycles:
-// a warp gets one 512-byte store through every ~190 cycles), without the weight re-streaming 0.339 ms, without both
-// 0.278 ms (then the drain tail -- statistics 2.6k + park 0.8k during which the MMA stream runs out of accumulators --
-// sets the pace).  Three limits sit within 10 % of each other; the next step is a CTA pair sharing the weight stages
-// (cluster multicast) and TMA bulk stores from the parked tile.
+// once): without the 128 KB of stores per tile 0.300 ms (the finisher's 64 STG.128 per warp and tile take ~11k cycles
+// here, with or without TMA bulk stores; a stand-alone probe of the same pattern, tools/store_probe.cu, writes 6.2 TB/s
+// from two warps per SM and 2.5 + 2.5 TB/s next to an equal load stream -- so it is this kernel's own operand traffic
+// that slows them: 2.4 TB/s of HBM reads + 4.6 TB/s of weight re-reads from L2 + 2.2 TB/s of stores = 9.2 TB/s through
+// the L2 <-> SM fabric), without the weight re-streaming 0.339 ms, without both 0.278 ms (then the drain tail --
+// statistics 2.6k + park 0.8k during which the MMA stream runs out of accumulators -- sets the pace).  Three limits sit
+// within 10 % of each other; the next step is a CTA pair sharing the weight stages (cluster multicast).
 #include "common.cuh"
 #include "tc_common.cuh"
 

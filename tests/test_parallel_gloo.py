@@ -118,3 +118,35 @@ def test_single_process_wrapper_is_transparent():
     assert float(w.flat_grad.abs().sum()) > 0
     w.zero_grad()
     assert float(w.flat_grad.abs().sum()) == 0
+
+
+def test_direct_write_claims_only_whole_zeroed_buckets(monkeypatch):
+    """Host logic of the direct-write path (parallel.GraphDataParallel.claim): the block's backward may write a
+    layer's gradients straight into the bucket views only while the wrapper is armed (zero_grad -> expect_sync), for
+    exactly one whole bucket, once; everything else falls back to autograd accumulation."""
+    import sldm_gnn_b200.parallel as par
+    from oracle.sage_oracle import SageBlockOracle
+    torch.manual_seed(0)
+    m = SageBlockOracle([4, 6, 3])
+    w = par.GraphDataParallel(m)
+    w._overlap = True                                   # pretend CUDA + a process group (claim() itself launches nothing)
+    monkeypatch.setattr(w, "_ready", lambda: True)
+    layer = lambda l: [m.convs[l].lin_l.weight, m.convs[l].lin_l.bias, m.convs[l].lin_r.weight, m.posts[l][0].weight, m.posts[l][0].bias]
+    assert w.claim(layer(1)) is None                    # not armed
+    w.zero_grad(); w.expect_sync(local_weight=3.0)
+    assert par.active_wrapper() is w
+    bi, views = w.claim(layer(1))
+    assert bi == 0 and all(v.data_ptr() == p.grad.data_ptr() for v, p in zip(views, layer(1)))   # last layer = first bucket
+    assert w.claim(layer(0))[0] == 1
+    assert w.claim(layer(1)[:4]) is None                # not a whole bucket
+    assert w.claim(layer(0)[:3] + layer(1)[3:]) is None # parameters of two buckets
+    w._launched.add(0)
+    assert w.claim(layer(1)) is None                    # already exchanged
+    m.convs[0].lin_l.weight.grad = torch.zeros_like(m.convs[0].lin_l.weight)
+    assert w.claim(layer(0)) is None                    # someone replaced .grad: not the bucket view any more
+    monkeypatch.setattr(w, "_ready", lambda: False)
+    w.sync_gradients(local_weight=3.0)                  # disarms
+    assert par.active_wrapper() is None and w.claim(layer(1)) is None
+    monkeypatch.setattr(w, "_ready", lambda: True)
+    w.expect_sync(local_weight=3.0)                     # gradients were not zeroed since the last backward: stays off
+    assert par.active_wrapper() is None and w.claim(layer(1)) is None
