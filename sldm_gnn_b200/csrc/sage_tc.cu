@@ -46,7 +46,9 @@
 // What was tried and lost: 256-bit st.global straight from the accumulator registers (lane = row, 32 B per lane:
 // partial-line writes, 0.507 ms); LayerNorm in a lane-per-column finisher (2.9k cycles per 4 rows of shuffles and
 // divisions: 0.587 ms) and in a thread-per-row finisher over the parked tile (0.470 ms: four warps cannot absorb it);
-// deeper rings (A 3..8, B 2..3: no change).  Timing-only experiments (wrong results, -DSLDM_TC_NOSTORE / weights loaded
+// deeper rings (A 3..8, B 2..3: no change); per-quarter statistics in the drain + merge and normalisation in the finisher
+// (the drain's tail drops to 0.5k cycles but the finisher, whose stores already take ~11k per tile, becomes the pace
+// maker: 0.400 ms); an L2 prefetch of the next tile's rows (0.370 ms); mbarrier suspend-time hints (no change).  Timing-only experiments (wrong results, -DSLDM_TC_NOSTORE / weights loaded
 // once): without the 128 KB of stores per tile 0.300 ms (the finisher's 64 STG.128 per warp and tile take ~11k cycles
 // here, with or without TMA bulk stores; a stand-alone probe of the same pattern, tools/store_probe.cu, writes 6.2 TB/s
 // from two warps per SM and 2.5 + 2.5 TB/s next to an equal load stream -- so it is this kernel's own operand traffic
