@@ -15,9 +15,9 @@
 //
 // Pipeline (one persistent CTA per SM, 896 threads = 7 warpgroups, 128 rows x Fout per tile; setmaxnreg 56 / 72 / 80 / 56
 // of the 72 x 896 register pool):
-//   warp 0        TMA producer A: raw activation chunks [128 x 32] (agg, then x) into a 5-deep ring -- the HBM stream;
+//   warp 0        TMA producer A: raw activation chunks [128 x 32] (agg, then x) into a 3-deep ring -- the HBM stream;
 //                                a stage is handed back by the CONVERTER as soon as the tile is in registers
-//   warp 2        TMA producer B: pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk into a 2-deep ring (L2 hits)
+//   warp 2        TMA producer B: pre-split weight tiles B_hi, B_lo [Fout x 32] of the chunk into a 3-deep ring (L2 hits)
 //   warps 4-7     converter    : reads its row of the raw tile and parks a (the tensor core truncates it to tf32 = a_hi
 //                                itself) and a_lo = rna_tf32(a - a_hi) in TENSOR MEMORY with tcgen05.st (lane = row,
 //                                column = k; two 64-column slots with their own free barriers) -- the MMAs take A from
@@ -64,11 +64,16 @@ using namespace tc;
 
 constexpr int kTcThreads = 896;   // 7 warpgroups: {TMA, MMA, alloc+TMA B, MMA} {converter x4} {drain x4} x 4 {finisher x4}
 constexpr int kWgThreads = 512;   // k_wgrad_tc: {TMA, MMA, alloc, idle} {converter x4} {epilogue x4} x 2
+// Ring depths.  Round 1 ran A 5 / B 2; once the MMA issue was fixed (round 2) the weight ring became the pace maker of
+// DGRAD: a stage is free only when the MMAs that read it have completed, the reload then takes ~2k cycles (L2 hit, but
+// queued behind the operand loads), so with two stages a chunk took (0.8k MMA + 2k reload) / 2.  A 3 / B 3 (the same
+// 209 KB): dgrad 0.329 -> 0.302 ms, forward 0.357 -> 0.351 ms at the batch shape.  (A 4 / B 3 does not fit next to the
+// 64 KB hand-off tile.)
 #ifndef SLDM_TC_STAGES
-#define SLDM_TC_STAGES 5
+#define SLDM_TC_STAGES 3
 #endif
 #ifndef SLDM_TC_BSTAGES
-#define SLDM_TC_BSTAGES 2
+#define SLDM_TC_BSTAGES 3
 #endif
 constexpr int kTcStages = SLDM_TC_STAGES;     // A ring: raw activation chunks [128 x 32] (16 KB each) -- the HBM operand, prefetched deep
 constexpr int kTcBStages = SLDM_TC_BSTAGES;   // B ring: weight chunks B_hi | B_lo (32 KB each at Fout = 128; L2 resident)
@@ -430,6 +435,11 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
   constexpr int ACC_COLS = 32 * NT;
   constexpr uint32_t TMEM_COLS = 512;                   // accumulators [0, 384) + A slots [384, 512)
   static_assert(kTcAcc * 128 <= kTcACol0 && kTcACol0 + 64 * kTcASlots <= 512, "TMEM budget");
+  // Two MMA issuers alternate chunks; an mbarrier parity wait is only safe when the waiter cannot be two phases ahead.
+  // B = 2: a warp always meets the same stage (chunk parity == stage).  B == kTcAcc: before a warp waits for stage
+  // it % B it has waited for the accumulator of chunk it - kTcAcc to be drained, i.e. for the previous use of that very
+  // stage to be complete.  Other depths would need per-warp stage tracking.
+  static_assert(kTcBStages == 2 || kTcBStages == kTcAcc, "weight ring depth vs. the two-issuer parity waits");
 
   const int half = pb.Kc;
   const int nchunks = pb.nsrc * pb.Kc;
