@@ -8,17 +8,18 @@
 // segment in edge order, which is the summation order of the reference's CPU
 // scatter_add_.
 //
-// Kernels per build: k_convert (int64 -> int32, range / sortedness flags), then per
-// key array k_digit_hist (all digits in one read), k_digit_offsets, one
-// k_onesweep_pass per 8-bit digit, k_rowptr_from_sorted; k_plan_hubs for the split
-// rows.  A key array that is already non-decreasing (edge_index[0] as the
-// reference's builders emit it, src/gbuilder.py:88-112) skips its sort on the device.
+// Kernels per build (7 launches + 2 memsets; round 1: 17 + 2): k_convert_hist (int64 -> int32, range / sortedness
+// flags, digit histograms of the destination keys in the same read), k_digit_hist (source keys; exits at once when
+// they are ordered), one k_onesweep_pass per 8-bit digit serving BOTH sorts (blockIdx.y), k_rowptr_from_sorted and
+// k_plan_hubs (both arrays each).  A key array that is already non-decreasing (edge_index[0] as the reference's
+// builders emit it, src/gbuilder.py:88-112) skips its sort on the device.
 //
-// All of this is HBM-bound int32 work: 16E bytes read (int64 pairs), 8E written
-// per sorted column array, 8(N+1) for the row pointers.  Measured on B200
-// (profiles/r01g_csr_launches.txt): 4.1 M edges 0.29 ms, 10 M unsorted edges 0.81 ms; the
-// passes are bound by the stable ranking (warp votes on the ADU pipe, or shared-memory
-// atomics emulating match.any), not by HBM.
+// All of this is HBM-bound int32 work by its bytes -- 16E read (int64 pairs), 8E written per sorted column array,
+// 8(N+1) for the row pointers -- but not by its time.  Measured on B200 (profiles/r02j_csr_launches.txt): 4.1 M edges
+// 0.193 ms (round 1: 0.27), 10 M unsorted edges 0.60 ms (0.78), 32 k edges 0.054 ms (0.077).  A pass runs at
+// ~115 G keys/s: it is instruction-bound (ncu: issue slots 62 % busy, 209 warp instructions per 32 keys -- stable
+// ranking, regrouping through shared memory, look-back), the convert kernel is bound by its shared-memory atomics
+// (~64 LSU cycles per warp instruction: 1.4 per 32 keys = 40 us of the 41).
 #include "common.cuh"
 #include <algorithm>
 
@@ -74,58 +75,122 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total, int* smem
   return prefix;
 }
 
-// ---------------------------------------------------------------- convert --
-// int64 [2,E] -> two int32 arrays; range check (reported through meta, indices clamped) and the two
-// "already non-decreasing" flags.  Pure streaming: 16E bytes read, 8E written.
-__global__ void __launch_bounds__(256)
-k_convert(const int64_t* __restrict__ ei_src, const int64_t* __restrict__ ei_dst, int64_t E, int32_t N,
-          int32_t* __restrict__ src32, int32_t* __restrict__ dst32, int32_t* __restrict__ meta) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  bool bad = false, us = false, ud = false;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
-    int64_t s = ei_src ? ei_src[e] : e, d = ei_dst[e];   // ei_src == NULL: source ids are 0..E-1 (membership lists)
-    if (e > 0) {
-      us |= ei_src != nullptr && ei_src[e - 1] > s;
-      ud |= ei_dst[e - 1] > d;
-    }
-    if ((ei_src != nullptr && (s < 0 || s >= N)) || d < 0 || d >= N) {
-      bad = true;  // reported through meta; clamped so nothing goes out of bounds
-      if (ei_src != nullptr) s = s < 0 ? 0 : (s >= N ? N - 1 : s);
-      d = d < 0 ? 0 : (d >= N ? N - 1 : d);
-    }
-    src32[e] = (int32_t)s;
-    dst32[e] = (int32_t)d;
-  }
-  if (bad) meta[2] = 1;
-  if (us) meta[3] = 1;
-  if (ud) meta[4] = 1;
-}
-
-// ----------------------------------------------------- stable LSD radix sort --
-// One kernel per 8-bit digit ("onesweep"): a CTA takes a tile of 4096 consecutive keys, ranks them stably by digit
-// (per-warp match_any ranking + prefix over warps), learns how many keys with the same digit precede its tile from
-// the tiles before it (decoupled look-back over per-tile state words) and writes the tile out grouped by digit
-// through shared memory, so consecutive threads write consecutive addresses.  The global start of every digit comes
-// from a histogram of all digits taken in ONE read of the keys before the first pass.  Pure integer work, no float:
-// the result is the unique stable sort, bit-exact against argsort(stable).
+// ------------------------------------------------------------------ plan --
+// Stable LSD radix sort of (key, value) pairs, keys < N, 8-bit digits.  A 10-bit variant of the same kernels exists
+// behind SLDM_CSR_DIGIT_BITS=10 (tests run both): it saves a whole pass for 17..20 key bits (0.8 M .. 1 M nodes) and
+// still LOSES -- measured on B200, 4.1 M / 10 M edges: 0.262 / 0.83 ms against 0.234 / 0.61 ms, a 1024-bin pass costs
+// almost twice a 256-bin one (four digits per thread in the prefix phase, 73 KB of shared memory per CTA).
 constexpr int kOsThreads = 256;
 constexpr int kOsWarps = kOsThreads / 32;
 constexpr int kOsKpt = 16;                       // keys per thread
 constexpr int kOsTile = kOsThreads * kOsKpt;     // 4096 keys per CTA
 constexpr int kMaxPass = 4;
+#ifndef SLDM_OS_MIN_CTAS
+#define SLDM_OS_MIN_CTAS 4
+#endif
+constexpr int kOsMinCtas = SLDM_OS_MIN_CTAS;      // resident CTAs per SM the pass kernel is compiled for (64 registers at 4)
+constexpr int kHistInts = 4096;                  // per sort: npass * bins <= max(4 * 256, 3 * 1024)
 #ifndef SLDM_RANK_ATOMIC_OR
 #define SLDM_RANK_ATOMIC_OR 1
 #endif
 constexpr bool kRankAtomicOr = SLDM_RANK_ATOMIC_OR != 0;   // stable ranking: shared-memory atomicOr peer masks (1) or warp ballots (0)
 
-// ghist[p][d] += #keys whose p-th digit is d, for all passes at once.  High digits of clustered keys are uniform
-// across a warp: one shared-memory atomic per warp instead of 32.
+struct SortPlan { int db, npass, key_bits; };
+static int key_bits(int64_t N) {
+  int bits = 1;
+  while (bits < 31 && ((int64_t)1 << bits) < N) ++bits;
+  return bits;
+}
+static SortPlan sort_plan(int64_t N) {
+  SortPlan P;
+  P.key_bits = key_bits(N);
+  P.db = 8;
+  if (const char* e = getenv("SLDM_CSR_DIGIT_BITS")) { const int v = atoi(e); if (v == 8 || v == 10) P.db = v; }
+  P.npass = (P.key_bits + P.db - 1) / P.db;
+  return P;
+}
+
+// ---------------------------------------------------------------- convert --
+// Digit histogram of one warp-round of keys into shared-memory counters h[pass][digit].  The cost is the number of
+// shared-memory atomic instructions (~50-64 cycles per warp instruction on the LSU pipe, same-address or not), so a
+// digit that is uniform across the warp -- the high digits of clustered keys -- is counted by one lane.  (Leader
+// rounds for the first two distinct values of a warp were tried and lost: 57 -> 68 us on the batch, 114 -> 192 us on
+// random keys.)
+template <int DB>
+__device__ __forceinline__ void hist_round(int* __restrict__ h, int k, bool valid, unsigned vm, int npass, int lane) {
+  constexpr int NB = 1 << DB;
+  const int first = __ffs(vm) - 1;
+  for (int p = 0; p < npass; ++p) {
+    const int dg = (k >> (DB * p)) & (NB - 1);
+    const int d0 = __shfl_sync(0xffffffffu, dg, first);
+    const bool uniform = __ballot_sync(0xffffffffu, !valid || dg == d0) == 0xffffffffu;
+    if (uniform) { if (lane == first) atomicAdd(&h[p * NB + d0], __popc(vm)); }
+    else if (valid) atomicAdd(&h[p * NB + dg], 1);
+  }
+}
+
+// int64 [2,E] -> two int32 arrays; range check (reported through meta, indices clamped), the two "already
+// non-decreasing" flags, and -- in the same read -- the digit histograms of every pass of the sort by DESTINATION
+// (ghist[pass][digit], shared-memory counters flushed once per CTA): the copy is HBM-bound, the counting LSU-bound, so
+// the two overlap.  The histogram of the source keys is k_digit_hist below: edge_index[0] is normally ordered already
+// (src/gbuilder.py:88-112) and that kernel then exits at once.  16E bytes read, 8E written.
+template <int DB>
+__global__ void __launch_bounds__(256)
+k_convert_hist(const int64_t* __restrict__ ei_src, const int64_t* __restrict__ ei_dst, int64_t E, int32_t N, int npass,
+               int32_t* __restrict__ src32, int32_t* __restrict__ dst32, int32_t* __restrict__ meta,
+               int32_t* __restrict__ ghist_dst) {
+  constexpr int NB = 1 << DB;
+  extern __shared__ int h[];                      // [npass][NB]
+  const int nh = npass * NB;
+  for (int i = threadIdx.x; i < nh; i += 256) h[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  const int64_t nround = ceil_div<int64_t>(E, stride);
+  bool bad = false, us = false, ud = false;
+  for (int64_t r = 0; r < nround; ++r) {
+    const int64_t e = r * stride + (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool valid = e < E;
+    int64_t s = 0, d = 0;
+    if (valid) {
+      s = ei_src ? ei_src[e] : e;   // ei_src == NULL: source ids are 0..E-1 (membership lists)
+      d = ei_dst[e];
+      if (e > 0) {
+        us |= ei_src != nullptr && ei_src[e - 1] > s;
+        ud |= ei_dst[e - 1] > d;
+      }
+      if ((ei_src != nullptr && (s < 0 || s >= N)) || d < 0 || d >= N) {
+        bad = true;  // reported through meta; clamped so nothing goes out of bounds
+        if (ei_src != nullptr) s = s < 0 ? 0 : (s >= N ? N - 1 : s);
+        d = d < 0 ? 0 : (d >= N ? N - 1 : d);
+      }
+      src32[e] = (int32_t)s;
+      dst32[e] = (int32_t)d;
+    }
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    if (vm == 0) continue;
+    hist_round<DB>(h, (int)d, valid, vm, npass, lane);
+  }
+  if (bad) meta[2] = 1;
+  if (us) meta[3] = 1;
+  if (ud) meta[4] = 1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nh; i += 256) {
+    const int c = h[i];
+    if (c) atomicAdd(ghist_dst + i, c);
+  }
+}
+
+// ghist[p][d] += #keys whose p-th digit is d, for all passes at once (the sort by source; skipped when ordered)
+template <int DB>
 __global__ void __launch_bounds__(256)
 k_digit_hist(const int32_t* __restrict__ keys, int64_t n, int npass, int32_t* __restrict__ ghist,
              const int32_t* __restrict__ unsorted_flag) {
-  if (unsorted_flag && *unsorted_flag == 0) return;  // input already ordered: the sort is skipped
-  __shared__ int h[kMaxPass][256];
-  for (int i = threadIdx.x; i < kMaxPass * 256; i += 256) (&h[0][0])[i] = 0;
+  if (*unsorted_flag == 0) return;  // input already ordered: the sort is skipped
+  constexpr int NB = 1 << DB;
+  extern __shared__ int h[];
+  const int nh = npass * NB;
+  for (int i = threadIdx.x; i < nh; i += 256) h[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * 256;
@@ -136,41 +201,37 @@ k_digit_hist(const int32_t* __restrict__ keys, int64_t n, int npass, int32_t* __
     const int k = valid ? keys[idx] : 0;
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (vm == 0) continue;
-    const int first = __ffs(vm) - 1;
-    for (int p = 0; p < npass; ++p) {
-      const int d = (k >> (8 * p)) & 255;
-      const int d0 = __shfl_sync(0xffffffffu, d, first);
-      const bool uniform = __ballot_sync(0xffffffffu, !valid || d == d0) == 0xffffffffu;
-      if (uniform) { if (lane == first) atomicAdd(&h[p][d0], __popc(vm)); }
-      else if (valid) atomicAdd(&h[p][d], 1);
-    }
+    hist_round<DB>(h, k, valid, vm, npass, lane);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npass * 256; i += 256) {
-    const int c = (&h[0][0])[i];
+  for (int i = threadIdx.x; i < nh; i += 256) {
+    const int c = h[i];
     if (c) atomicAdd(ghist + i, c);
   }
 }
 
-// gbase[p][d] = exclusive prefix of ghist[p][*]; one CTA of 256 threads per key array, all passes
-__global__ void __launch_bounds__(256)
-k_digit_offsets(const int32_t* __restrict__ ghist, int32_t* __restrict__ gbase, int npass) {
-  __shared__ int sm[256 / 32 + 1];
-  for (int p = 0; p < npass; ++p) {
-    int total;
-    const int v = ghist[p * 256 + threadIdx.x];
-    gbase[p * 256 + threadIdx.x] = block_exclusive_scan<256>(v, total, sm);
-  }
-}
+// ----------------------------------------------------- stable LSD radix sort --
+// One kernel per digit ("onesweep"), both sorts of a build in ONE launch (blockIdx.y; a sort whose keys were already
+// non-decreasing exits at once): a CTA takes a tile of 4096 consecutive keys, ranks them stably by digit (per-warp
+// ranking + prefix over warps), regroups the tile by digit in shared memory, learns how many keys with the same digit
+// precede its tile from the tiles before it (decoupled look-back over per-tile state words) and writes the tile out
+// so that consecutive threads write consecutive addresses.  The global start of every digit comes from the histogram
+// the convert kernel took: tile 0 scans it and folds it into the prefix it publishes.  Pure integer work, no float:
+// the result is the unique stable sort, bit-exact against argsort(stable).
+//
+// Look-back: the tile's keys are already parked in shared memory when it starts, so the registers are free for a WIDE
+// window -- 32 state words per thread and round trip.  In the first wave no tile is inclusive yet and the walk is the
+// critical path of the pass: ~T / (2 * window) L2 round trips for T resident tiles (window 8: ~28 round trips of the
+// 40 us pass at 444 resident tiles; window 32: 7).
 
-// lanes of `vm` whose 8-bit digit equals this lane's: eight ballots.  (__match_any_sync does the same in one
+// lanes of `vm` whose digit equals this lane's: one ballot per digit bit.  (__match_any_sync does the same in one
 // instruction, but MATCH.ANY occupies the ADU pipe for ~140 cycles on sm_100 -- ncu: sm__inst_executed_pipe_adu 76%,
 // 206 us per pass on 10 M keys -- so the ranking loop was the whole cost of the pass.)
 __device__ __forceinline__ unsigned peers_same_digit(unsigned vm, int d, int nbits) {
   unsigned m = vm;
 #pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    if (b >= nbits) break;                         // the top digit of the key range is narrower than 8 bits
+  for (int b = 0; b < 10; ++b) {
+    if (b >= nbits) break;                         // the top digit of the key range may be narrower
     const bool bit = (d >> b) & 1;
     const unsigned bal = __ballot_sync(vm, bit);
     m &= bit ? bal : ~bal;
@@ -178,39 +239,65 @@ __device__ __forceinline__ unsigned peers_same_digit(unsigned vm, int d, int nbi
   return m;
 }
 
-__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+// per-tile state word: {flag (2 bits) | count}; flag 1 = this tile's own count, 2 = inclusive prefix over tiles 0..t
+// (tile 0: plus the global start of the digit).  32-bit words while every count fits 30 bits, else 64-bit.
+template <typename ST> struct StateWord;
+template <> struct StateWord<unsigned> {
+  static constexpr int kShift = 30;
+  static __device__ __forceinline__ unsigned ld(const unsigned* p) {
+    unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+  }
+  static __device__ __forceinline__ void st(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  }
+};
+template <> struct StateWord<unsigned long long> {
+  static constexpr int kShift = 62;
+  static __device__ __forceinline__ unsigned long long ld(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+  }
+  static __device__ __forceinline__ void st(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  }
+};
 
-// tile_state: [ntiles][256] 64-bit words, {flag (2 bits) | count}; flag 1 = this tile's own count, 2 = inclusive
-// prefix over tiles 0..t.  ticket: tiles are handed out in launch order so every earlier tile is running or done.
-__global__ void __launch_bounds__(kOsThreads)
-k_onesweep_pass(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift, int nbits,
-                const int32_t* __restrict__ gbase, unsigned long long* __restrict__ tile_state,
-                int32_t* __restrict__ ticket, int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
-                const int32_t* __restrict__ unsorted_flag) {
-  if (unsorted_flag && *unsorted_flag == 0) return;
-  __shared__ int wh[kOsWarps][256];          // per-warp digit counts, then per-warp start offsets
-  __shared__ int s_lstart[256];              // start of digit d inside the digit-grouped tile
-  __shared__ int s_gdelta[256];              // global position of element i of the grouped tile = s_gdelta[d] + i
-  __shared__ int s_scan[kOsThreads / 32 + 1];
-  __shared__ int s_tile;
-  __shared__ int skeys[kOsTile];
-  __shared__ int svals[kOsTile];
-  constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagInc = 2ull << 62, kMask = (1ull << 62) - 1;
+struct PassArgs {                     // one sort's view of one pass
+  const int32_t* keys_in; const int32_t* vals_in;
+  int32_t* keys_out; int32_t* vals_out;
+  const int32_t* ghist;               // [NB] counts of this pass's digit over all keys
+  void* tile_state;                   // [ntiles][NB] state words of this pass
+  int32_t* ticket;                    // tiles are handed out in launch order so every earlier tile is running or done
+  const int32_t* unsorted_flag;
+};
+
+template <int DB>
+constexpr int onesweep_smem_bytes() { return (kOsWarps * (1 << DB) + 2 * kOsTile + 2 * (1 << DB) + 16) * 4; }
+
+template <int DB, typename ST>
+__global__ void __launch_bounds__(kOsThreads, DB == 10 ? 3 : kOsMinCtas)   // 10-bit digits: 73 KB of shared memory, three CTAs fit anyway
+k_onesweep_pass(PassArgs a0, PassArgs a1, int64_t n, int shift, int nbits) {
+  const PassArgs& A = blockIdx.y == 0 ? a0 : a1;
+  if (A.unsorted_flag && *A.unsorted_flag == 0) return;   // input already ordered: the sort is skipped
+  constexpr int NB = 1 << DB;
+  constexpr int DPT = NB / kOsThreads;               // digits per thread in the per-digit phase (consecutive digits)
+  constexpr int kLook = 32 / DPT;                    // look-back window per digit
+  using SW = StateWord<ST>;
+  constexpr ST kFlagAgg = (ST)1 << SW::kShift, kFlagInc = (ST)2 << SW::kShift, kMask = ((ST)1 << SW::kShift) - 1;
+  extern __shared__ int sm_os[];
+  int (*wh)[NB] = reinterpret_cast<int (*)[NB]>(sm_os);      // per-warp digit counts, then per-warp start offsets
+  int* const skeys = sm_os + kOsWarps * NB;                   // the tile grouped by digit (the ranking's peer masks before that)
+  int* const svals = skeys + kOsTile;
+  int* const s_lstart = svals + kOsTile;                      // start of digit d inside the grouped tile
+  int* const s_gdelta = s_lstart + NB;                        // global position of element i of the grouped tile = s_gdelta[d] + i
+  int* const s_scan = s_gdelta + NB;                          // [kOsWarps + 1] + the ticket
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1);
-#pragma unroll
-  for (int w = 0; w < kOsWarps; ++w) wh[w][tid] = 0;
+  if (tid == 0) s_scan[12] = atomicAdd(A.ticket, 1);
+  for (int i = tid; i < kOsWarps * NB; i += kOsThreads) { sm_os[i] = 0; skeys[i] = 0; }   // counts and peer masks
   __syncthreads();
-  const int tile = s_tile;
+  const int tile = s_scan[12];
   const int64_t tbase = (int64_t)tile * kOsTile;
   const int tile_n = (int)((n - tbase < kOsTile) ? (n - tbase) : kOsTile);
+  const int dmask = NB - 1;
 
   // ---- load + stable rank inside the warp's 512-key slice (slice order = key order) ----
   int k[kOsKpt], v[kOsKpt];
@@ -220,20 +307,19 @@ k_onesweep_pass(const int32_t* __restrict__ keys_in, const int32_t* __restrict__
   for (int r = 0; r < kOsKpt; ++r) {
     const int i = wbase + r * 32;
     const bool valid = i < tile_n;
-    k[r] = valid ? keys_in[tbase + i] : 0;
-    v[r] = valid ? vals_in[tbase + i] : 0;
+    k[r] = valid ? A.keys_in[tbase + i] : 0;
+    v[r] = valid ? A.vals_in[tbase + i] : 0;
   }
   if (kRankAtomicOr && nbits > 5) {   // narrow digits: a few ballots are cheaper
     // peer mask through shared memory: every lane ORs its bit into the word of its digit, then reads the word back
-    // (an emulated match.any on the LSU pipe instead of eight votes on the ADU pipe)
-    unsigned* mk = reinterpret_cast<unsigned*>(skeys) + warp * 256;   // skeys is not used before the regroup step
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mk[lane + 32 * j] = 0u;
-    __syncwarp();
+    // (an emulated match.any on the LSU pipe instead of one vote per digit bit on the ADU pipe).  Letting every 2nd /
+    // 3rd / 4th round take the hardware MATCH.ANY, to use both pipes side by side, changed nothing (0.193-0.199 ms per
+    // build against 0.193 without).
+    unsigned* mk = reinterpret_cast<unsigned*>(skeys) + warp * NB;
 #pragma unroll
     for (int r = 0; r < kOsKpt; ++r) {
       const bool valid = wbase + r * 32 < tile_n;
-      const int d = (k[r] >> shift) & 255;
+      const int d = (k[r] >> shift) & dmask;
       if (valid) atomicOr(&mk[d], 1u << lane);
       __syncwarp();
       unsigned m = 0u;
@@ -246,128 +332,199 @@ k_onesweep_pass(const int32_t* __restrict__ keys_in, const int32_t* __restrict__
     }
   } else {
 #pragma unroll
-  for (int r = 0; r < kOsKpt; ++r) {
-    const bool valid = wbase + r * 32 < tile_n;
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      const int d = (k[r] >> shift) & 255;
-      const unsigned m = peers_same_digit(vm, d, nbits);
-      const int leader = __ffs(m) - 1;
-      int old = 0;
-      if (lane == leader) { old = wh[warp][d]; wh[warp][d] = old + __popc(m); }
-      old = __shfl_sync(m, old, leader);
-      rl[r] = (unsigned short)(old + __popc(m & ((1u << lane) - 1u)));
-    }
-    __syncwarp();
-  }
-  }
-  __syncthreads();
-
-  // ---- per digit (thread = digit): offsets over warps, tile count, position among the tiles ----
-  {
-    const int d = tid;
-    int run = 0;
-#pragma unroll
-    for (int w = 0; w < kOsWarps; ++w) { const int c = wh[w][d]; wh[w][d] = run; run += c; }
-    const int cnt = run;
-    int total;
-    const int lstart = block_exclusive_scan<kOsThreads>(cnt, total, s_scan);
-    unsigned long long* mine = tile_state + (int64_t)tile * 256 + d;
-    long long excl = 0;
-    if (tile == 0) {
-      st_state(mine, kFlagInc | (unsigned long long)cnt);
-    } else {
-      st_state(mine, kFlagAgg | (unsigned long long)cnt);
-      // Walk back over the earlier tiles until one with an inclusive prefix is found.  kLook state words are fetched
-      // per step (independent loads), so the walk costs one L2 round trip per kLook tiles; in the first wave, where
-      // no tile is inclusive yet, that walk is the critical path of the pass.
-      constexpr int kLook = 8;
-      int t = tile - 1;
-      bool done = false;
-      while (!done) {
-        unsigned long long sv[kLook];
-#pragma unroll
-        for (int j = 0; j < kLook; ++j)
-          sv[j] = (t - j >= 0) ? ld_state(tile_state + (int64_t)(t - j) * 256 + d) : kFlagInc;
-#pragma unroll
-        for (int j = 0; j < kLook; ++j) {
-          if (done) break;
-          const unsigned long long fl = sv[j] >> 62;
-          if (fl == 0) break;                      // not published yet: poll again from this tile
-          excl += (long long)(sv[j] & kMask);
-          --t;
-          if (fl == 2) done = true;
-        }
+    for (int r = 0; r < kOsKpt; ++r) {
+      const bool valid = wbase + r * 32 < tile_n;
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const int d = (k[r] >> shift) & dmask;
+        const unsigned m = peers_same_digit(vm, d, nbits);
+        const int leader = __ffs(m) - 1;
+        int old = 0;
+        if (lane == leader) { old = wh[warp][d]; wh[warp][d] = old + __popc(m); }
+        old = __shfl_sync(m, old, leader);
+        rl[r] = (unsigned short)(old + __popc(m & ((1u << lane) - 1u)));
       }
-      st_state(mine, kFlagInc | (unsigned long long)(excl + cnt));
+      __syncwarp();
     }
-    s_lstart[d] = lstart;
-    s_gdelta[d] = gbase[d] + (int)excl - lstart;
   }
   __syncthreads();
 
-  // ---- group the tile by digit in shared memory, then write runs of equal digits with consecutive threads ----
+  // ---- per digit (thread = DPT consecutive digits): offsets over warps, tile counts, position inside the tile ----
+  const int d0 = tid * DPT;
+  int cnt[DPT];
+  {
+    int tsum = 0;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) cnt[j] = 0;
+#pragma unroll
+    for (int w = 0; w < kOsWarps; ++w) {
+      if constexpr (DPT == 4) {
+        int4 c = *reinterpret_cast<int4*>(&wh[w][d0]);
+        *reinterpret_cast<int4*>(&wh[w][d0]) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        cnt[0] += c.x; cnt[1] += c.y; cnt[2] += c.z; cnt[3] += c.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) { const int c = wh[w][d0 + j]; wh[w][d0 + j] = cnt[j]; cnt[j] += c; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) tsum += cnt[j];
+    int total;
+    int lstart = block_exclusive_scan<kOsThreads>(tsum, total, s_scan);
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) { s_lstart[d0 + j] = lstart; lstart += cnt[j]; }
+  }
+  ST* const state = static_cast<ST*>(A.tile_state);
+  ST* const mine = state + (int64_t)tile * NB + d0;
+  long long excl[DPT];
+  if (tile == 0) {
+    // global start of every digit = exclusive prefix of the histogram; folded into the inclusive prefix of tile 0
+    int g[DPT], gsum = 0, total;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) { g[j] = A.ghist[d0 + j]; gsum += g[j]; }
+    int gb = block_exclusive_scan<kOsThreads>(gsum, total, s_scan);
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) { excl[j] = gb; gb += g[j]; SW::st(mine + j, kFlagInc | (ST)(excl[j] + cnt[j])); }
+  } else {
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) SW::st(mine + j, kFlagAgg | (ST)cnt[j]);
+  }
+  __syncthreads();   // s_lstart, wh offsets
+
+  // ---- group the tile by digit in shared memory (the registers are free after this) ----
 #pragma unroll
   for (int r = 0; r < kOsKpt; ++r) {
     if (wbase + r * 32 < tile_n) {
-      const int d = (k[r] >> shift) & 255;
+      const int d = (k[r] >> shift) & dmask;
       const int pos = s_lstart[d] + wh[warp][d] + rl[r];
       skeys[pos] = k[r];
       svals[pos] = v[r];
     }
   }
+
+  // ---- look-back: how many keys with my digits do the tiles before mine hold? ----
+  if (tile != 0) {
+    // A digit this tile does not hold needs no position: its thread leaves the aggregate word (count 0) in place and
+    // later tiles simply walk past it.  (The top digit of a 20-bit key range has 13 live values of 256.)  Every 64th
+    // tile walks for all digits and publishes inclusive prefixes, which bounds the walk for a digit that is rare.
+    int t[DPT]; bool done[DPT]; bool all = true;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) { t[j] = tile - 1; done[j] = cnt[j] == 0 && (tile & 63) != 0; excl[j] = 0; all &= done[j]; }
+    bool skip[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) skip[j] = done[j];
+    bool blocked = false;
+    while (!all) {
+      if (blocked) __nanosleep(64);                  // a predecessor had not published: do not steal issue slots
+      blocked = false;
+      ST sv[DPT][kLook];
+#pragma unroll
+      for (int j = 0; j < DPT; ++j)
+#pragma unroll
+        for (int w = 0; w < kLook; ++w)
+          sv[j][w] = (!done[j] && t[j] - w >= 0) ? SW::ld(state + (int64_t)(t[j] - w) * NB + d0 + j) : kFlagInc;
+      all = true;
+#pragma unroll
+      for (int j = 0; j < DPT; ++j) {
+#pragma unroll
+        for (int w = 0; w < kLook; ++w) {
+          if (done[j]) break;
+          const ST fl = sv[j][w] >> SW::kShift;
+          if (fl == 0) { blocked = true; break; }  // not published yet: poll again from this tile
+          excl[j] += (long long)(sv[j][w] & kMask);
+          --t[j];
+          if (fl == 2) done[j] = true;
+        }
+        all &= done[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) if (!skip[j]) SW::st(mine + j, kFlagInc | (ST)(excl[j] + cnt[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < DPT; ++j) s_gdelta[d0 + j] = (int)excl[j] - s_lstart[d0 + j];
   __syncthreads();
+
+  // ---- write runs of equal digits with consecutive threads ----
 #pragma unroll
   for (int j = 0; j < kOsKpt; ++j) {
     const int i = j * kOsThreads + tid;
     if (i < tile_n) {
       const int key = skeys[i];
-      const int pos = s_gdelta[(key >> shift) & 255] + i;
-      keys_out[pos] = key;
-      vals_out[pos] = svals[i];
+      const int pos = s_gdelta[(key >> shift) & dmask] + i;
+      A.keys_out[pos] = key;
+      A.vals_out[pos] = svals[i];
     }
   }
 }
 
-// when the keys were already non-decreasing the stable sort is the identity
-__global__ void __launch_bounds__(256)
-k_copy_if_sorted(const int32_t* __restrict__ vals, int64_t n, int32_t* __restrict__ out,
-                 const int32_t* __restrict__ unsorted_flag) {
-  if (*unsorted_flag != 0) return;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = vals[i];
-}
-
 // rowptr[k] = first position whose key is >= k, from the sorted keys (the input itself when it was already ordered):
-// rowptr == cumsum(bincount(keys)) without a single atomic.  rowptr[N] = n.
+// rowptr == cumsum(bincount(keys)) without a single atomic.  rowptr[N] = n.  Both sorts in one launch (blockIdx.y);
+// when the keys were already non-decreasing the stable sort is the identity and the values are copied here.
+struct RowptrArgs {
+  const int32_t* keys_if_sorted; const int32_t* keys_after_sort; const int32_t* vals0;
+  int32_t* vals_out; int32_t* rowptr; const int32_t* unsorted_flag;
+};
 __global__ void __launch_bounds__(256)
-k_rowptr_from_sorted(const int32_t* __restrict__ keys_if_sorted, const int32_t* __restrict__ keys_after_sort,
-                     int64_t n, int32_t N, int32_t* __restrict__ rowptr, const int32_t* __restrict__ unsorted_flag) {
+k_rowptr_from_sorted(RowptrArgs a0, RowptrArgs a1, int64_t n, int32_t N) {
   // Position i writes rowptr[k] = i for every k in (keys[i-1], keys[i]].  Runs of absent keys are normally short; a long
   // one (trailing isolated nodes, membership lists whose keys only span the graphs) is parked in shared memory and
-  // filled by the whole CTA, so no single thread ever writes more than kInline entries in a row.
-  constexpr int kInline = 16, kMaxGaps = 64;
+  // filled by the whole CTA, so no single thread ever writes more than kInline entries in a row.  A thread owns kPer
+  // consecutive positions (two 128-bit loads; one position per thread and round was latency-bound: 17 us per array
+  // for 4.1 M keys).
+  constexpr int kInline = 16, kMaxGaps = 64, kPer = 8;
   __shared__ int g_lo[kMaxGaps], g_hi[kMaxGaps], g_val[kMaxGaps];
   __shared__ int g_n;
-  const int32_t* __restrict__ keys = (*unsorted_flag == 0) ? keys_if_sorted : keys_after_sort;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const RowptrArgs& A = blockIdx.y == 0 ? a0 : a1;
+  const bool was_sorted = *A.unsorted_flag == 0;
+  const int32_t* __restrict__ keys = was_sorted ? A.keys_if_sorted : A.keys_after_sort;
+  int32_t* __restrict__ rowptr = A.rowptr;
+  // sections of the workspace / CSR object are 256-byte aligned whenever the caller's buffers are 16-byte aligned
+  const bool vec = ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(A.vals0) |
+                     reinterpret_cast<uintptr_t>(A.vals_out)) & 15) == 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * kPer;
   const int64_t rounds = ceil_div<int64_t>(n + 1, stride);
   for (int64_t r = 0; r < rounds; ++r) {
-    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int lo = 0, hi = 0;
-    if (i <= n) {
-      lo = (i == 0) ? -1 : keys[i - 1];
-      hi = (i == n) ? N : keys[i];
+    const int64_t i0 = r * stride + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPer;
+    int kv[kPer + 1];                               // kv[j] = keys[i0 + j - 1], with keys[-1] = -1 and keys[n] = N
+    kv[0] = (i0 == 0) ? -1 : (i0 - 1 < n ? keys[i0 - 1] : N);
+    if (i0 + kPer <= n && vec) {                    // whole strip inside the array
+      const int4 q0 = *reinterpret_cast<const int4*>(keys + i0), q1 = *reinterpret_cast<const int4*>(keys + i0 + 4);
+      kv[1] = q0.x; kv[2] = q0.y; kv[3] = q0.z; kv[4] = q0.w; kv[5] = q1.x; kv[6] = q1.y; kv[7] = q1.z; kv[8] = q1.w;
+      if (was_sorted) {
+        const int4 v0 = *reinterpret_cast<const int4*>(A.vals0 + i0), v1 = *reinterpret_cast<const int4*>(A.vals0 + i0 + 4);
+        *reinterpret_cast<int4*>(A.vals_out + i0) = v0;
+        *reinterpret_cast<int4*>(A.vals_out + i0 + 4) = v1;
+      }
+    } else {
+#pragma unroll
+      for (int j = 1; j <= kPer; ++j) kv[j] = (i0 + j - 1 < n) ? keys[i0 + j - 1] : N;
+      if (was_sorted) {
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) if (i0 + j < n) A.vals_out[i0 + j] = A.vals0[i0 + j];
+      }
     }
-    const bool big = hi - lo > kInline;
-    if (!big) for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;
+    bool big = false;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (i0 + j > n) break;
+      const int lo = kv[j], hi = kv[j + 1];
+      if (hi - lo > kInline) big = true;
+      else for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)(i0 + j);
+    }
     if (!__syncthreads_or(big)) continue;          // the common case: no long run in this CTA's slice
     if (threadIdx.x == 0) g_n = 0;
     __syncthreads();
     if (big) {
-      const int slot = atomicAdd(&g_n, 1);
-      if (slot < kMaxGaps) { g_lo[slot] = lo; g_hi[slot] = hi; g_val[slot] = (int32_t)i; }
-      else for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)i;   // list full: fall back to the serial fill
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        if (i0 + j > n) break;
+        const int lo = kv[j], hi = kv[j + 1];
+        if (hi - lo <= kInline) continue;
+        const int slot = atomicAdd(&g_n, 1);
+        if (slot < kMaxGaps) { g_lo[slot] = lo; g_hi[slot] = hi; g_val[slot] = (int32_t)(i0 + j); }
+        else for (int kk = lo + 1; kk <= hi; ++kk) rowptr[kk] = (int32_t)(i0 + j);   // list full: serial fill
+      }
     }
     __syncthreads();
     const int ng = min(g_n, kMaxGaps);
@@ -377,60 +534,75 @@ k_rowptr_from_sorted(const int32_t* __restrict__ keys_if_sorted, const int32_t* 
   }
 }
 
-struct SortWs {            // per key array
-  int32_t* ghist;          // [kMaxPass][256]
-  int32_t* gbase;          // [kMaxPass][256]
+struct SortWs {            // per sort
+  int32_t* ghist;          // [npass][bins] (kHistInts)
   int32_t* tickets;        // [kMaxPass]
-  unsigned long long* tile_state;   // [npass][ntiles][256]
+  char* tile_state;        // [npass][ntiles][bins] state words
+  int32_t *kA, *vA, *kB, *vB;
 };
 
-// keys0/vals0 -> final_vals (stable by key); the sorted keys end in *sorted_keys_out (kA or kB)
-static int radix_sort_pairs(const int32_t* keys0, const int32_t* vals0, int64_t n, int npass, int key_bits,
-                            int32_t* kA, int32_t* vA, int32_t* kB, int32_t* vB,
-                            int32_t* final_vals, const SortWs& W, const int32_t** sorted_keys_out,
-                            const int32_t* unsorted_flag, cudaStream_t s) {
+template <int DB, typename ST>
+static int launch_pass(const PassArgs& a0, const PassArgs& a1, int64_t n, int nsort, int shift, int nbits, cudaStream_t s) {
+  constexpr int smem = onesweep_smem_bytes<DB>();
+  SLDM_OPT_IN_SMEM((k_onesweep_pass<DB, ST>), smem);
+  const dim3 grid((unsigned)ceil_div<int64_t>(n, kOsTile), (unsigned)nsort);
+  k_onesweep_pass<DB, ST><<<grid, kOsThreads, smem, s>>>(a0, a1, n, shift, nbits);
+  SLDM_LAUNCH_CHECK("k_onesweep_pass");
+  return SLDM_OK;
+}
+
+// both sorts pass by pass: sort i takes (keys0[i], vals0[i]) -> final_vals[i] (stable by key); the sorted keys end in
+// sorted_keys_out[i] (its kA or kB)
+static int radix_sort_pairs2(int nsort, const int32_t* const keys0[2], const int32_t* const vals0[2], int64_t n,
+                             const SortPlan& P, const SortWs W[2], int32_t* const final_vals[2],
+                             const int32_t* sorted_keys_out[2], const int32_t* const unsorted_flag[2], cudaStream_t s) {
   const int64_t ntiles = ceil_div<int64_t>(n, kOsTile);
-  {
-    int grid = (int)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 4), (int64_t)num_sms() * 8);
-    k_copy_if_sorted<<<grid, 256, 0, s>>>(vals0, n, final_vals, unsorted_flag);
-    SLDM_LAUNCH_CHECK("k_copy_if_sorted");
-    grid = (int)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 8), (int64_t)num_sms() * 8);
-    k_digit_hist<<<grid, 256, 0, s>>>(keys0, n, npass, W.ghist, unsorted_flag);
-    SLDM_LAUNCH_CHECK("k_digit_hist");
-    k_digit_offsets<<<1, 256, 0, s>>>(W.ghist, W.gbase, npass);
-    SLDM_LAUNCH_CHECK("k_digit_offsets");
+  const int NB = 1 << P.db;
+  const bool wide = n >= ((int64_t)1 << 30);
+  const int64_t word = wide ? 8 : 4;
+  const int32_t* in_k[2] = {keys0[0], keys0[1]};
+  const int32_t* in_v[2] = {vals0[0], vals0[1]};
+  for (int p = 0; p < P.npass; ++p) {
+    const bool last = (p == P.npass - 1);
+    PassArgs a[2];
+    for (int i = 0; i < 2; ++i) {
+      const int j = i < nsort ? i : 0;
+      a[i].keys_in = in_k[j]; a[i].vals_in = in_v[j];
+      a[i].keys_out = (p & 1) ? W[j].kB : W[j].kA;
+      a[i].vals_out = last ? final_vals[j] : ((p & 1) ? W[j].vB : W[j].vA);
+      a[i].ghist = W[j].ghist + p * NB;
+      a[i].tile_state = W[j].tile_state + (int64_t)p * ntiles * NB * word;
+      a[i].ticket = W[j].tickets + p;
+      a[i].unsorted_flag = unsorted_flag[j];
+    }
+    const int nbits = std::min(P.db, P.key_bits - P.db * p);
+    int rc;
+    if (P.db == 10) rc = wide ? launch_pass<10, unsigned long long>(a[0], a[1], n, nsort, P.db * p, nbits, s)
+                              : launch_pass<10, unsigned>(a[0], a[1], n, nsort, P.db * p, nbits, s);
+    else            rc = wide ? launch_pass<8, unsigned long long>(a[0], a[1], n, nsort, P.db * p, nbits, s)
+                              : launch_pass<8, unsigned>(a[0], a[1], n, nsort, P.db * p, nbits, s);
+    if (rc) return rc;
+    for (int i = 0; i < nsort; ++i) { in_k[i] = a[i].keys_out; in_v[i] = a[i].vals_out; }
   }
-  const int32_t* in_k = keys0;
-  const int32_t* in_v = vals0;
-  for (int p = 0; p < npass; ++p) {
-    const bool last = (p == npass - 1);
-    int32_t* out_k = (p & 1) ? kB : kA;
-    int32_t* out_v = last ? final_vals : ((p & 1) ? vB : vA);
-    const int nbits = std::min(8, key_bits - 8 * p);
-    k_onesweep_pass<<<(unsigned)ntiles, kOsThreads, 0, s>>>(in_k, in_v, n, 8 * p, nbits, W.gbase + p * 256,
-                                                           W.tile_state + (int64_t)p * ntiles * 256, W.tickets + p,
-                                                           out_k, out_v, unsorted_flag);
-    SLDM_LAUNCH_CHECK("k_onesweep_pass");
-    in_k = out_k; in_v = out_v;
-  }
-  *sorted_keys_out = in_k;
+  for (int i = 0; i < nsort; ++i) sorted_keys_out[i] = in_k[i];
   return SLDM_OK;
 }
 
 // ----------------------------------------------------------- hub work list --
+struct HubArgs { const int32_t* rowptr; int32_t* hub_list; int32_t* counter; };
 __global__ void __launch_bounds__(256)
-k_plan_hubs(const int32_t* __restrict__ rowptr, int32_t N, int32_t* __restrict__ hub_list,
-            int32_t* __restrict__ counter, int32_t cap) {
+k_plan_hubs(HubArgs a0, HubArgs a1, int32_t N, int32_t cap) {
+  const HubArgs& A = blockIdx.y == 0 ? a0 : a1;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  int deg = rowptr[i + 1] - rowptr[i];
+  int deg = A.rowptr[i + 1] - A.rowptr[i];
   if (deg <= SLDM_HUB_DEGREE) return;
   int nch = (deg + SLDM_HUB_CHUNK - 1) / SLDM_HUB_CHUNK;
-  int k = atomicAdd(counter, nch);
+  int k = atomicAdd(A.counter, nch);
   if (k + nch > cap) return;  // cannot happen: cap >= E/CHUNK + E/HUB_DEGREE
   for (int c = 0; c < nch; ++c) {
     int4 ent = make_int4((int)i, c, nch, k);
-    reinterpret_cast<int4*>(hub_list)[k + c] = ent;
+    reinterpret_cast<int4*>(A.hub_list)[k + c] = ent;
   }
 }
 
@@ -439,41 +611,36 @@ k_plan_hubs(const int32_t* __restrict__ rowptr, int32_t N, int32_t* __restrict__
 // ================================================================== C ABI ==
 using namespace sldm;
 
-static int key_bits(int64_t N) {
-  int bits = 1;
-  while (bits < 31 && ((int64_t)1 << bits) < N) ++bits;
-  return bits;
-}
-static int radix_passes(int64_t N) { return (key_bits(N) + 7) / 8; }
-
-// workspace: int32 copies of the two index rows, two ping-pong (key, value) pairs, and the sort state.  The sort
-// state (histograms, tickets, per-tile look-back words for every pass of both sorts) is one contiguous region that a
-// single memset clears.
-struct CsrWs { int64_t src32, dst32, kA, vA, kB, vB, state, state_bytes, total; int64_t ntiles; int npass; };
-static int64_t sort_state_bytes(int64_t ntiles, int npass) {
-  return align_bytes(2 * kMaxPass * 256 * 4) + align_bytes(kMaxPass * 4) + align_bytes((int64_t)npass * ntiles * 256 * 8);
+// workspace: int32 copies of the two index rows, per sort two ping-pong (key, value) pairs, and the sort state.  The
+// sort state (histograms, tickets, per-tile look-back words for every pass of both sorts) is one contiguous region
+// that a single memset clears.
+struct CsrWs { int64_t src32, dst32, pp[2][4], state, state_bytes, total; int64_t ntiles; SortPlan plan; int64_t word; };
+static int64_t sort_state_bytes(int64_t ntiles, const SortPlan& P, int64_t word) {
+  return align_bytes(kHistInts * 4) + align_bytes(kMaxPass * 4) + align_bytes((int64_t)P.npass * ntiles * (1 << P.db) * word);
 }
 static CsrWs csr_ws_layout(int64_t N, int64_t E) {
   CsrWs w; int64_t o = 0;
   int64_t e = align_bytes((E > 0 ? E : 1) * 4);
   w.ntiles = ceil_div<int64_t>(E > 0 ? E : 1, kOsTile);
-  w.npass = radix_passes(N);
+  w.plan = sort_plan(N);
+  w.word = E >= ((int64_t)1 << 30) ? 8 : 4;
   w.src32 = o; o += e;  w.dst32 = o; o += e;
-  w.kA = o; o += e;  w.vA = o; o += e;  w.kB = o; o += e;  w.vB = o; o += e;
-  w.state = o; w.state_bytes = 2 * sort_state_bytes(w.ntiles, w.npass); o += w.state_bytes;
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 4; ++j) { w.pp[i][j] = o; o += e; }
+  w.state = o; w.state_bytes = 2 * sort_state_bytes(w.ntiles, w.plan, w.word); o += w.state_bytes;
   w.total = o;
   return w;
 }
-static SortWs sort_ws_at(char* base, int64_t ntiles, int npass) {
-  SortWs W;
-  W.ghist = reinterpret_cast<int32_t*>(base);
-  W.gbase = W.ghist + kMaxPass * 256;
-  char* p = base + align_bytes(2 * kMaxPass * 256 * 4);
-  W.tickets = reinterpret_cast<int32_t*>(p);
+static SortWs sort_ws_at(char* wb, const CsrWs& W, int i) {
+  SortWs S;
+  char* base = wb + W.state + i * (W.state_bytes / 2);
+  S.ghist = reinterpret_cast<int32_t*>(base);
+  char* p = base + align_bytes(kHistInts * 4);
+  S.tickets = reinterpret_cast<int32_t*>(p);
   p += align_bytes(kMaxPass * 4);
-  W.tile_state = reinterpret_cast<unsigned long long*>(p);
-  (void)ntiles; (void)npass;
-  return W;
+  S.tile_state = p;
+  S.kA = reinterpret_cast<int32_t*>(wb + W.pp[i][0]);  S.vA = reinterpret_cast<int32_t*>(wb + W.pp[i][1]);
+  S.kB = reinterpret_cast<int32_t*>(wb + W.pp[i][2]);  S.vB = reinterpret_cast<int32_t*>(wb + W.pp[i][3]);
+  return S;
 }
 
 extern "C" int sldm_csr_layout(int64_t N, int64_t E, int64_t* out8) {
@@ -538,47 +705,47 @@ extern "C" int sldm_csr_build_pairs(const int64_t* edge_src, const int64_t* edge
   char* wb = static_cast<char*>(workspace);
   int32_t* src32 = reinterpret_cast<int32_t*>(wb + W.src32);
   int32_t* dst32 = reinterpret_cast<int32_t*>(wb + W.dst32);
-  int32_t* kA = reinterpret_cast<int32_t*>(wb + W.kA);
-  int32_t* vA = reinterpret_cast<int32_t*>(wb + W.vA);
-  int32_t* kB = reinterpret_cast<int32_t*>(wb + W.kB);
-  int32_t* vB = reinterpret_cast<int32_t*>(wb + W.vB);
   SLDM_CUDA(cudaMemsetAsync(wb + W.state, 0, (size_t)W.state_bytes, s));
-  const SortWs Wd = sort_ws_at(wb + W.state, W.ntiles, W.npass);
-  const SortWs Ws = sort_ws_at(wb + W.state + W.state_bytes / 2, W.ntiles, W.npass);
-
-  {
-    int grid = (int)std::min<int64_t>(ceil_div<int64_t>(E, 256 * 4), (int64_t)num_sms() * 8);
-    k_convert<<<grid, 256, 0, s>>>(edge_src, edge_dst, E, (int32_t)N, src32, dst32, meta);
-    SLDM_LAUNCH_CHECK("k_convert");
-  }
-  int rc;
-  const int npass = W.npass;
-  const int32_t* sorted_d = nullptr;
-  const int32_t* sorted_s = nullptr;
-  // by destination: keys = dst, payload = src  -> col_src   (skipped on the device when dst is already ordered)
-  if ((rc = radix_sort_pairs(dst32, src32, E, npass, key_bits(N), kA, vA, kB, vB, col_s, Wd, &sorted_d, meta + 4, s))) return rc;
-  {
-    int grid = (int)std::min<int64_t>(ceil_div<int64_t>(E + 1, 256), (int64_t)num_sms() * 16);
-    k_rowptr_from_sorted<<<grid, 256, 0, s>>>(dst32, sorted_d, E, (int32_t)N, rp_d, meta + 4);
-    SLDM_LAUNCH_CHECK("k_rowptr_from_sorted(dst)");
-  }
+  const SortWs Wsort[2] = {sort_ws_at(wb, W, 0), sort_ws_at(wb, W, 1)};
+  const SortPlan& P = W.plan;
   const bool membership = (edge_src == nullptr);   // only (rowptr_dst, col_src) are produced; source ids may exceed N
-  if (!membership) {
-    // by source (transpose): keys = src, payload = dst -> col_dst.  The ping-pong buffers are reused: stream order
-    // guarantees the row pointers above were derived before they are overwritten.
-    if ((rc = radix_sort_pairs(src32, dst32, E, npass, key_bits(N), kA, vA, kB, vB, col_d, Ws, &sorted_s, meta + 3, s))) return rc;
-    int grid = (int)std::min<int64_t>(ceil_div<int64_t>(E + 1, 256), (int64_t)num_sms() * 16);
-    k_rowptr_from_sorted<<<grid, 256, 0, s>>>(src32, sorted_s, E, (int32_t)N, rp_s, meta + 3);
-    SLDM_LAUNCH_CHECK("k_rowptr_from_sorted(src)");
-  }
+  const int nsort = membership ? 1 : 2;
 
-  int cap = (int)hub_capacity(E);
-  int grid = (int)ceil_div<int64_t>(N, 256);
-  k_plan_hubs<<<grid, 256, 0, s>>>(rp_d, (int32_t)N, hub_d, meta + 0, cap);
-  SLDM_LAUNCH_CHECK("k_plan_hubs(dst)");
-  if (!membership) {
-    k_plan_hubs<<<grid, 256, 0, s>>>(rp_s, (int32_t)N, hub_s, meta + 1, cap);
-    SLDM_LAUNCH_CHECK("k_plan_hubs(src)");
+  {
+    const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(E, 256 * 4), (int64_t)num_sms() * 8);
+    const size_t smem = (size_t)P.npass * (1 << P.db) * 4;
+    if (P.db == 10) k_convert_hist<10><<<grid, 256, smem, s>>>(edge_src, edge_dst, E, (int32_t)N, P.npass, src32, dst32, meta, Wsort[0].ghist);
+    else            k_convert_hist<8><<<grid, 256, smem, s>>>(edge_src, edge_dst, E, (int32_t)N, P.npass, src32, dst32, meta, Wsort[0].ghist);
+    SLDM_LAUNCH_CHECK("k_convert_hist");
+    if (!membership) {
+      const int hgrid = (int)std::min<int64_t>(ceil_div<int64_t>(E, 256 * 8), (int64_t)num_sms() * 8);
+      if (P.db == 10) k_digit_hist<10><<<hgrid, 256, smem, s>>>(src32, E, P.npass, Wsort[1].ghist, meta + 3);
+      else            k_digit_hist<8><<<hgrid, 256, smem, s>>>(src32, E, P.npass, Wsort[1].ghist, meta + 3);
+      SLDM_LAUNCH_CHECK("k_digit_hist");
+    }
+  }
+  // sort 0, by destination: keys = dst, payload = src -> col_src; sort 1, by source (transpose): keys = src,
+  // payload = dst -> col_dst.  Each is skipped on the device when its keys are already ordered.
+  const int32_t* const keys0[2] = {dst32, src32};
+  const int32_t* const vals0[2] = {src32, dst32};
+  int32_t* const final_vals[2] = {col_s, col_d};
+  const int32_t* const flags[2] = {meta + 4, meta + 3};
+  const int32_t* sorted[2] = {nullptr, nullptr};
+  int rc;
+  if ((rc = radix_sort_pairs2(nsort, keys0, vals0, E, P, Wsort, final_vals, sorted, flags, s))) return rc;
+  {
+    const RowptrArgs r0{dst32, sorted[0], src32, col_s, rp_d, meta + 4};
+    const RowptrArgs r1{src32, sorted[1], dst32, col_d, rp_s, meta + 3};
+    const dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(E + 1, 256 * 8), (int64_t)num_sms() * 8), (unsigned)nsort);
+    k_rowptr_from_sorted<<<grid, 256, 0, s>>>(r0, membership ? r0 : r1, E, (int32_t)N);
+    SLDM_LAUNCH_CHECK("k_rowptr_from_sorted");
+  }
+  {
+    const int cap = (int)hub_capacity(E);
+    const HubArgs h0{rp_d, hub_d, meta + 0}, h1{rp_s, hub_s, meta + 1};
+    const dim3 grid((unsigned)ceil_div<int64_t>(N, 256), (unsigned)nsort);
+    k_plan_hubs<<<grid, 256, 0, s>>>(h0, membership ? h0 : h1, (int32_t)N, cap);
+    SLDM_LAUNCH_CHECK("k_plan_hubs");
   }
   return SLDM_OK;
 }

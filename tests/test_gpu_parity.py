@@ -98,6 +98,25 @@ def test_csr_bit_exact(dev, kind, N, E):
     assert st["hub_chunks_dst"] == int(((hubs + _lib.HUB_CHUNK - 1) // _lib.HUB_CHUNK).sum())
 
 
+@pytest.mark.parametrize("kind,N,E", [
+    ("random", 7, 3), ("random", 257, 4097), ("sorted_src", 6400, 32000), ("hub", 66000, 50000), ("random", 1025, 20000),
+    ("random", (1 << 20) + 1, 300000), ("random", (1 << 24) + 5, 60000), ("sorted_both", 5000, 70000), ("low_ids", 500000, 3000),
+    # look-back: > 64 tiles (a checkpoint tile walks for all digits), few live digits per tile (skipped walks)
+    ("one_dst", 1000, 300000), ("low_ids", 70000, 600000),
+])
+@pytest.mark.parametrize("bits", ["8", "10"])
+def test_csr_bit_exact_digit_widths(dev, monkeypatch, kind, N, E, bits):
+    """The 10-bit-digit variant of the sort kernels (SLDM_CSR_DIGIT_BITS=10; 8 is the default) and the look-back's
+    skip / checkpoint rules give the same unique stable sort."""
+    monkeypatch.setenv("SLDM_CSR_DIGIT_BITS", bits)
+    ei = edge_cases(kind, N, E, seed=N + E + 1)
+    csr = sg.build_csr(ei.to(dev), N)
+    want = csr_oracle(ei, N)
+    for name, g, w in zip(("rowptr_dst", "col_src", "rowptr_src", "col_dst"),
+                          (csr.rowptr_dst, csr.col_src, csr.rowptr_src, csr.col_dst), want):
+        assert torch.equal(g.cpu(), w), f"{name} differs ({kind}, N={N}, E={E}, {bits}-bit digits)"
+
+
 def test_csr_full_size_properties(dev):
     """C4 shape (1M nodes, 10M skewed edges): checksum-of-checksums + sortedness instead of an oracle sort."""
     N, E = 1_000_000, 10_000_000
