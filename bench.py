@@ -463,6 +463,49 @@ def c4_record(dev, peak_gbs, steps=10):
             "note": "true random gather (no L2 absorption): SURVEY 8d's byte model is honest here"}
 
 
+def cabi_host_record(blk, b, hdims, slope, N, E, fwd_only, calls=3):
+    """The same step through the C-ABI entry points that take HOST buffers (include/sldm_sage.h:
+    sldm_sage_block_forward_host / _train_host -- the call a host without torch would bind):
+    every call copies x and edge_index (and the upstream gradient) to the device, builds the CSR, runs the layers and
+    copies the output (and dx and every parameter gradient) back, synchronously.  Pinned host buffers; wall clock
+    around the blocking call.  It moves 2-4x the bytes of the module-level e2e (whose loss stays a 4-byte read)."""
+    import ctypes as C
+    from sldm_gnn_b200 import _lib
+    L = len(hdims) - 1
+    pin = lambda t: t.detach().to("cpu", torch.float32).contiguous().pin_memory()
+    pbufs = []
+    for l in range(L):
+        pbufs += [pin(blk.convs[l].lin_l.weight), pin(blk.convs[l].lin_l.bias), pin(blk.convs[l].lin_r.weight),
+                  pin(blk.posts[l][0].weight), pin(blk.posts[l][0].bias)]
+    params = (C.c_void_p * len(pbufs))(*[t.data_ptr() for t in pbufs])
+    hd = (C.c_int32 * (L + 1))(*hdims)
+    x_h, ei_h = b["x_h"], b["ei_h"]
+    out_h = torch.empty((N, hdims[-1]), dtype=torch.float32).pin_memory()
+    h2d = x_h.numel() * 4 + ei_h.numel() * 8
+    d2h = out_h.numel() * 4
+    if fwd_only:
+        call = lambda: _lib.check(_lib.lib.sldm_sage_block_forward_host(
+            x_h.data_ptr(), ei_h.data_ptr(), N, E, hd, L, params, 1e-5, slope, out_h.data_ptr()))
+    else:
+        w_h = b["w"].detach().to("cpu", torch.float32).contiguous().pin_memory()
+        dx_h = torch.empty_like(x_h).pin_memory()
+        gbufs = [torch.empty_like(t).pin_memory() for t in pbufs]
+        grads = (C.c_void_p * len(gbufs))(*[t.data_ptr() for t in gbufs])
+        h2d += w_h.numel() * 4
+        d2h += dx_h.numel() * 4 + sum(t.numel() * 4 for t in gbufs)
+        call = lambda: _lib.check(_lib.lib.sldm_sage_block_train_host(
+            x_h.data_ptr(), ei_h.data_ptr(), N, E, hd, L, params, 1e-5, slope, w_h.data_ptr(), out_h.data_ptr(),
+            dx_h.data_ptr(), grads))
+    call()                                          # warm-up: fills the library's device pool
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        call()
+    ms = (time.perf_counter() - t0) * 1e3 / calls
+    return {"entry": "sldm_sage_block_forward_host" if fwd_only else "sldm_sage_block_train_host", "ms_per_call": round(ms, 3),
+            "value": E * L / (ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_call": int(h2d), "d2h_bytes_per_call": int(d2h),
+            "calls": calls, "note": "blocking C call, pinned host buffers in and out, no overlap between copies and kernels"}
+
+
 def time_graphed(blk, batches, hdims, dev, fwd_only, steps=200):
     """ms per step of the small workload through GraphedSageBlock (one bucket sized for the batch): inference = copy-in
     + one graph launch + copy-out; training = forward graph + backward graph behind autograd.  Inputs alternate."""
@@ -658,6 +701,12 @@ def main_ours(args, wl):
             graphed = time_graphed(blk, batches, hdims, dev, fwd_only)
         except Exception as exc:                  # must never take the headline line down
             graphed = {"error": repr(exc)[:300]}
+    cabi = None
+    if world == 1 and not bf16 and args.workload in ("batch", "infer", "c1"):
+        try:
+            cabi = cabi_host_record(blk, batches[0], hdims, SLOPE, N, E, fwd_only)
+        except Exception as exc:                  # must never take the headline line down
+            cabi = {"error": repr(exc)[:300]}
     grad_sync = None
     if world > 1 and not fwd_only:               # after the exchange every rank must hold the SAME gradients, bit for bit
         chk = ddp.flat_grad.double().sum().view(1)
@@ -733,6 +782,8 @@ def main_ours(args, wl):
                                         "SURVEY 8d: sum_l [2E(Fin*4+4) + 4N(6Fin+5Fout) + 28N] + 24E + 8(N+1) (CSR rebuilt every step)")},
             "kernels": kern,
         }
+        if cabi is not None:
+            line["e2e_cabi_host"] = cabi
         if graphed is not None:
             line["cuda_graph"] = graphed
         if grad_sync is not None:

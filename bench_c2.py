@@ -230,6 +230,67 @@ def main_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- the same training step with forward and backward as captured CUDA graphs (GraphedGruSage): what the
+    #      reference's real batch sizes (32 / 64 graphs) gain once the ~200 launches of a step are two graph launches ----
+    # (captured before the component timings below: torch.cuda.make_graphed_callables must not find a live autograd
+    #  graph of an earlier eager step -- its AccumulateGrad nodes belong to the default stream and a backward capture
+    #  that has to synchronise with them is invalidated)
+    graphed = None
+    if world == 1 and G <= 256:
+        try:
+            import gc
+            from sldm_gnn_b200.grusage import GraphedGruSage
+            del cur, nxt
+            gc.collect()
+            gm = GraphedGruSage(model, max_nodes=max(b["N"] for b in batches) + 1, max_edges=max(b["E"] for b in batches),
+                                max_graphs=G + 1, training=True)
+
+            def gstep(data):
+                opt.zero_grad()
+                loss = crit(gm(data), data.y)
+                loss.backward()
+                opt.step()
+                return loss.item()
+
+            for i in range(5):
+                gstep(batches[i % 2]["dev"])
+            torch.cuda.synchronize()
+            gsteps = max(args.steps, 50)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(gsteps):
+                gstep(batches[i % 2]["dev"])
+            b.record(); torch.cuda.synchronize()
+            gms = a.elapsed_time(b) / gsteps
+            graphed = {"ms_per_step": round(gms, 4), "graphs_per_sec": G / (gms * 1e-3), "steps": gsteps,
+                       "what": "GraphedGruSage: padded static buffers, forward graph + backward graph behind autograd; loss, "
+                               "Adam and loss.item() stay eager"}
+            # ... and the whole step as ONE graph (GraphedTrainStep: zero_grad + forward + loss + backward + Adam)
+            import torch.nn.functional as Fn
+            from sldm_gnn_b200.grusage import GraphedTrainStep
+            del gm
+            gc.collect()
+            pw = torch.tensor(POS_WEIGHT, device=dev)
+            opt2 = torch.optim.Adam(params, lr=LR, weight_decay=WD, capturable=True, fused=True)
+            ts = GraphedTrainStep(model, opt2, lambda lg, y, w: Fn.binary_cross_entropy_with_logits(lg, y, weight=w, pos_weight=pw, reduction="sum"),
+                                  max_nodes=max(b["N"] for b in batches) + 1, max_edges=max(b["E"] for b in batches), max_graphs=G + 1)
+            for i in range(5):
+                ts(batches[i % 2]["dev"], batches[i % 2]["dev"].y).item()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = time.perf_counter()
+            a.record()
+            for i in range(gsteps):
+                lossv = ts(batches[i % 2]["dev"], batches[i % 2]["dev"].y).item()
+            b.record(); torch.cuda.synchronize()
+            tms = a.elapsed_time(b) / gsteps
+            graphed["one_graph_step"] = {"ms_per_step": round(tms, 4), "graphs_per_sec": G / (tms * 1e-3), "steps": gsteps, "last_loss": lossv,
+                                         "what": "GraphedTrainStep: zero_grad + forward + BCE + backward + fused Adam in ONE graph; "
+                                                 "per step: copy-in of the batch, one graph launch, loss.item()"}
+        except Exception as exc:                   # must never take the headline line down
+            import traceback
+            graphed = {"error": repr(exc)[:300], "where": [l.strip() for l in traceback.format_exc().splitlines() if l.strip().startswith("File")][-8:]}
+
     # ---- where the time goes: forward stages with CUDA events (untimed for the headline), backward and optimizer as wholes ----
     comp = {}
     if rank == 0:
@@ -273,6 +334,8 @@ def main_ours(args):
                         "ms_per_step": ms2, "steps": e2e_steps},
                 "gpu_launches": int(launches), "components_ms": comp,
                 "roofline": gru_roofline(N, comp.get("gru_last_hidden_fwd_training"), clocks)}
+        if graphed is not None:
+            line["cuda_graph"] = graphed
         if not args.no_cpu:
             r = run_cpu(G, min(G, 32), 1, 1, 10.0)
             line["cpu_baseline"] = {"value": r["graphs_per_s"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",

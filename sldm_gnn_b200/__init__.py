@@ -15,8 +15,8 @@ from .readout import global_mean_pool, global_max_pool, global_mean_max_pool
 from .collate import GraphData, GraphBatch, collate
 from .map_attention import MapSpatialAttention
 from .edges import build_proximity_edges
-from .grusage import GruSage, MapEncoder, MapZscoreNorm
+from .grusage import GruSage, MapEncoder, MapZscoreNorm, GraphedGruSage, GraphedTrainStep
 
 __all__ = ["SageBlock", "SageConvParams", "GraphedSageBlock", "Csr", "build_csr", "segment_reduce", "ops", "install_reference_shim",
            "global_mean_pool", "global_max_pool", "global_mean_max_pool", "GraphData", "GraphBatch", "collate",
-           "MapSpatialAttention", "build_proximity_edges", "GruSage", "MapEncoder", "MapZscoreNorm"]
+           "MapSpatialAttention", "build_proximity_edges", "GruSage", "MapEncoder", "MapZscoreNorm", "GraphedGruSage", "GraphedTrainStep"]

@@ -648,7 +648,12 @@ k_map_attention_demb(const float* __restrict__ dctx, int D, const float* __restr
       if (cnt == 32) {
         float r[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = on ? __ldg(dctx + __shfl_sync(0xffffffffu, rowoff, j) + c) : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          // the shuffle is executed by ALL lanes, also those beyond column D (it sat inside the `on ?` branch once:
+          // with D < 32 and a segment of >= 32 members the source lanes 16.. were not in the shuffle -> wild offsets)
+          const unsigned ro = __shfl_sync(0xffffffffu, rowoff, j);
+          r[j] = on ? __ldg(dctx + ro + c) : 0.f;
+        }
         if (inext < end) w_n = __ldg(wgt + p_n);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc = fmaf(__shfl_sync(0xffffffffu, wp, j), r[j], acc);

@@ -24,6 +24,7 @@ import torch.nn as nn
 
 from .gru import fused_gru_eligible, gru_last_hidden
 from .map_attention import MapSpatialAttention
+from .ops import index_checks
 from .readout import global_max_pool, global_mean_max_pool, global_mean_pool
 from .sageblock import SageBlock
 
@@ -200,3 +201,219 @@ class GruSage(nn.Module):
         present = [g for g in flat.values() if g is not None]
         total = torch.cat(present).norm().item() if present else None
         return total, {name: (g.norm().item() if g is not None else None) for name, g in flat.items()}
+
+
+class _TensorArgs(nn.Module):
+    """GruSage.forward over plain tensors (torch.cuda.make_graphed_callables wants tensor arguments)."""
+
+    def __init__(self, model: "GruSage", num_graphs: int):
+        super().__init__()
+        self.model, self.num_graphs = model, int(num_graphs)
+
+    def forward(self, x, xdims, xsttype, pos_raw, edge_index, batch):
+        from types import SimpleNamespace
+        self.model.sage.clear_cache()      # inside a CUDA graph the CSR build of the batch must be part of every replay
+        out = self.model(SimpleNamespace(x=x, xdims=xdims, xsttype=xsttype, pos_raw=pos_raw, edge_index=edge_index,
+                                         batch=batch, num_graphs=self.num_graphs))
+        self.model.sage.clear_cache()
+        return out
+
+
+class GraphedGruSage:
+    """GruSage.forward (+ its backward) through captured CUDA graphs for batches of up to max_nodes - 1 vehicles,
+    max_edges edges and max_graphs - 1 graphs -- the reference trains on batches of 32 graphs (main.py:24) and tests on
+    64 (test.py:58), where the ~200 kernel launches of a step and their Python glue cost several times the kernels.
+
+        g = GraphedGruSage(model, max_nodes=8192, max_edges=40960, max_graphs=33)
+        loss = crit(g(data), data.y); loss.backward(); opt.step()      # forward graph + backward graph, autograd-aware
+
+    The captured step works on static buffers of the bucket's size.  Rows [0, N) hold the batch; the padding vehicles
+    [N, max_nodes) belong to one extra padding graph (id max_graphs - 1), the padding edges are self loops of the last
+    padding vehicle.  Every stage is row-wise independent (GRU, fc stacks, map attention, SageBlock) or graph-wise
+    independent (readout), so the logits of the real graphs see the same inputs as in the un-captured model; the
+    padding graph's logit is sliced off, its upstream gradient is exactly zero and the parameter gradients therefore
+    equal the un-captured ones up to the association of their fp32 sums.  training=True uses
+    torch.cuda.make_graphed_callables (dropout draws from the graph-safe generator state); training=False captures one
+    inference graph (eval mode).  The returned logits are a view of the graph's static output, valid until the next
+    call.  Thread-safe: calls serialise on a lock.  Like any use of make_graphed_callables, construct it while no
+    autograd graph of an earlier eager step of the same model is alive (a kept `loss` is enough): the backward capture
+    would have to synchronise with the default stream and is invalidated.
+    """
+
+    _FIELDS = ("x", "xdims", "xsttype", "pos_raw", "edge_index", "batch")
+
+    def __init__(self, model: "GruSage", max_nodes: int, max_edges: int, max_graphs: int, training: bool = True):
+        import threading
+        p0 = next(model.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError("GraphedGruSage: CUDA only")
+        self.model, self.dev, self.training = model, p0.device, bool(training)
+        self.max_nodes, self.max_edges, self.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
+        cfg = model.config_dict
+        T, F = int(cfg["frames_num"]), int(cfg["dynamic_features_num"])
+        dev, Nm, Em = self.dev, self.max_nodes, self.max_edges
+        self._lock = threading.Lock()
+        with torch.cuda.device(dev):
+            self._static = dict(
+                x=torch.zeros((Nm, T, F), device=dev), xdims=torch.zeros((Nm, 2), device=dev),
+                xsttype=torch.zeros((Nm,), dtype=torch.long, device=dev), pos_raw=torch.zeros((Nm, T, 2), device=dev),
+                edge_index=torch.full((2, Em), Nm - 1, dtype=torch.long, device=dev),
+                batch=torch.full((Nm,), self.max_graphs - 1, dtype=torch.long, device=dev))
+            args = tuple(self._static[k] for k in self._FIELDS)
+            wrapped = _TensorArgs(model, self.max_graphs)
+            index_checks.poll(block=True)                      # nothing may be pending when a capture starts
+            if self.training:
+                model.train()
+                self._call = torch.cuda.make_graphed_callables(wrapped, args, allow_unused_input=True)
+            else:
+                was_training = model.training
+                model.eval()
+                with torch.inference_mode():
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):              # warm-up outside the capture: opt-in attributes, caches
+                        for _ in range(2):
+                            wrapped(*args)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    torch.cuda.synchronize(dev)
+                    index_checks.poll(block=True)
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        self._y = wrapped(*args)
+                model.train(was_training)
+            # objects the captured kernels read but the graph does not own: the static map graph's CSR and the
+            # centroid grid of the attention stay alive as long as this object does
+            self._keep = []
+            if getattr(model, "map_tensors", False):
+                self._keep.append(model.map_encoder.sage._csr)
+            if getattr(model, "map_provided", False):
+                self._keep.append((model.map_attention._grid, getattr(model.map_attention, "_grid_cent", None)))
+
+    def _fill(self, data, N, E):
+        s = self._static
+        with torch.no_grad():
+            s["x"][:N].copy_(data.x, non_blocking=True)
+            s["xdims"][:N].copy_(data.xdims, non_blocking=True)
+            s["xsttype"][:N].copy_(data.xsttype, non_blocking=True)
+            s["pos_raw"][:N].copy_(data.pos_raw, non_blocking=True)
+            s["batch"][:N].copy_(data.batch, non_blocking=True)
+            s["batch"][N:].fill_(self.max_graphs - 1)
+            s["edge_index"][:, :E].copy_(data.edge_index, non_blocking=True)
+            if E < self.max_edges:
+                s["edge_index"][:, E:].fill_(self.max_nodes - 1)
+        # feature rows beyond N keep what an earlier, larger batch left there: they are padding vehicles now (no edge
+        # from a real vehicle reaches them, they pool into the padding graph), so their values never matter
+
+    def __call__(self, data) -> torch.Tensor:
+        N, E = int(data.x.size(0)), int(data.edge_index.size(1))
+        G = getattr(data, "num_graphs", None)
+        if G is None:
+            raise RuntimeError("GraphedGruSage: data.num_graphs is required (reading it off `batch` would synchronise)")
+        if N >= self.max_nodes or E > self.max_edges or G >= self.max_graphs:
+            raise RuntimeError(f"GraphedGruSage: N = {N}, E = {E}, graphs = {G} exceed the bucket ({self.max_nodes - 1} vehicles, "
+                               f"{self.max_edges} edges, {self.max_graphs - 1} graphs)")
+        with self._lock, torch.cuda.device(self.dev):
+            self._fill(data, N, E)
+            if self.training:
+                return self._call(*(self._static[k] for k in self._FIELDS))[:G]
+            self._graph.replay()
+            return self._y[:G].clone()
+
+
+class GraphedTrainStep:
+    """One whole training step of a GruSage -- zero_grad, forward, loss, backward, optimizer step (the body of the
+    reference's loop, src/utils.py:218-236) -- as ONE captured CUDA graph over the padded static buffers of
+    GraphedGruSage: per step the host copies the batch in, launches one graph and reads the loss.
+
+        opt  = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-5, capturable=True)   # fused=True works too
+        step = GraphedTrainStep(model, opt, loss_fn, max_nodes=8192, max_edges=40960, max_graphs=33)
+        loss = step(data, data.y)            # 0-dim device tensor (static: valid until the next call); .item() to read it
+
+    loss_fn(logits [max_graphs, out], y [max_graphs, out], weight [max_graphs, 1]) -> scalar must be a weighted SUM:
+    `weight` is 1 / num_graphs on the rows of real graphs and 0 on the padding rows, so that e.g.
+    F.binary_cross_entropy_with_logits(logits, y, weight=weight, pos_weight=pw, reduction="sum") is the reference's
+    BCEWithLogitsLoss(pos_weight) mean over the real graphs.  The optimizer must be capturable (its step counter lives
+    on the device).  Warm-up and capture run the step on all-padding inputs; parameters and optimizer state are put back
+    in place afterwards (state tensors the optimizer created during warm-up are zeroed: Adam / AdamW / SGD momentum).
+    After a call every parameter's .grad holds this step's gradient (the reference logs gradient norms from it).
+    """
+
+    def __init__(self, model: "GruSage", optimizer, loss_fn, max_nodes: int, max_edges: int, max_graphs: int):
+        import threading
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise ValueError("GraphedTrainStep: the optimizer must be constructed with capturable=True")
+        base = GraphedGruSage.__new__(GraphedGruSage)          # static buffers and padding rules are GraphedGruSage's
+        p0 = next(model.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError("GraphedTrainStep: CUDA only")
+        base.model, base.dev, base.training = model, p0.device, True
+        base.max_nodes, base.max_edges, base.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
+        cfg = model.config_dict
+        T, F, out_dim = int(cfg["frames_num"]), int(cfg["dynamic_features_num"]), int(cfg["out_dim"])
+        dev, Nm, Em, Gm = base.dev, base.max_nodes, base.max_edges, base.max_graphs
+        self._base, self.model, self.dev, self._lock = base, model, dev, threading.Lock()
+        with torch.cuda.device(dev):
+            base._static = dict(
+                x=torch.zeros((Nm, T, F), device=dev), xdims=torch.zeros((Nm, 2), device=dev),
+                xsttype=torch.zeros((Nm,), dtype=torch.long, device=dev), pos_raw=torch.zeros((Nm, T, 2), device=dev),
+                edge_index=torch.full((2, Em), Nm - 1, dtype=torch.long, device=dev),
+                batch=torch.full((Nm,), Gm - 1, dtype=torch.long, device=dev))
+            self._y = torch.zeros((Gm, out_dim), device=dev)
+            self._w = torch.zeros((Gm, 1), device=dev)
+            args = tuple(base._static[k] for k in GraphedGruSage._FIELDS)
+            wrapped = _TensorArgs(model, Gm)
+            params = [p for g in optimizer.param_groups for p in g["params"]]
+            saved_p = [p.detach().clone() for p in params]
+            had_state = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in optimizer.state.get(p, {}).items()}
+                         for p in params}
+            model.train()
+
+            def one_step():
+                optimizer.zero_grad(set_to_none=True)
+                loss = loss_fn(wrapped(*args), self._y, self._w)
+                loss.backward()
+                optimizer.step()
+                return loss
+
+            index_checks.poll(block=True)                      # nothing may be pending when a capture starts
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            index_checks.poll(block=True)
+            optimizer.zero_grad(set_to_none=True)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._loss = one_step()
+            torch.cuda.synchronize(dev)
+            with torch.no_grad():                              # undo the warm-up steps, in place (the graph holds the pointers)
+                for p, s in zip(params, saved_p):
+                    p.copy_(s)
+                    before = had_state[id(p)]
+                    for k, v in optimizer.state.get(p, {}).items():
+                        if torch.is_tensor(v):
+                            v.copy_(before[k]) if k in before else v.zero_()
+            base._keep = []
+            if getattr(model, "map_tensors", False):
+                base._keep.append(model.map_encoder.sage._csr)
+            if getattr(model, "map_provided", False):
+                base._keep.append((model.map_attention._grid, getattr(model.map_attention, "_grid_cent", None)))
+
+    def __call__(self, data, y: torch.Tensor) -> torch.Tensor:
+        b = self._base
+        N, E = int(data.x.size(0)), int(data.edge_index.size(1))
+        G = int(y.size(0))
+        if N >= b.max_nodes or E > b.max_edges or G >= b.max_graphs:
+            raise RuntimeError(f"GraphedTrainStep: N = {N}, E = {E}, graphs = {G} exceed the bucket ({b.max_nodes - 1} vehicles, "
+                               f"{b.max_edges} edges, {b.max_graphs - 1} graphs)")
+        with self._lock, torch.cuda.device(self.dev):
+            b._fill(data, N, E)
+            with torch.no_grad():
+                self._y[:G].copy_(y, non_blocking=True)
+                self._w[:G].fill_(1.0 / max(G, 1))
+                self._w[G:].zero_()
+            self._graph.replay()
+            return self._loss

@@ -141,3 +141,135 @@ def test_cuda_model_without_map_and_through_collate():
     assert torch.allclose(out_g.cpu(), out_o, rtol=1e-4, atol=1e-5), float((out_g.cpu() - out_o).abs().max())
     with torch.inference_mode():
         assert torch.equal(ours(batch), out_g)
+
+
+def _c2_like(dev, dropout=None, seed=0):
+    """A small full model (map encoder + attention + GRU head) and two batches of different size."""
+    import sldm_gnn_b200 as sg
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(100 + seed)
+    S = 48
+    mt = dict(float_features=torch.randn(S, 6, generator=g), bool_features=torch.rand(S, 3, generator=g) > 0.5,
+              lane_type_cats=torch.randint(0, 4, (S,), generator=g),
+              mgraph_edge_indexes=torch.stack([torch.randint(0, S, (4 * S,), generator=g), torch.randint(0, S, (4 * S,), generator=g)]),
+              mseg_centroids=torch.rand(S, 2, generator=g) * 100.0)
+    kw = dict(dynamic_features_num=6, frames_num=8, gru_hidden_size=32, gru_num_layers=1, fc1dims=[24], sage_hidden_dims=[32, 32],
+              fc2dims=[16], out_dim=1, num_st_types=9, emb_dim=4, dropout=dropout, negative_slope=0.1, global_pooling="double",
+              mapenc_lane_embdim=4, mapenc_sage_hdims=[16, 16], map_attention_topk=3)
+    torch.manual_seed(seed)
+    model = sg.GruSage(**kw, map_tensors=mt).to(dev)
+
+    def batch(graphs, s):
+        gg = torch.Generator().manual_seed(s)
+        ns = [int(torch.randint(4, 11, (1,), generator=gg)) for _ in range(graphs)]
+        off, eis, bv = 0, [], []
+        for i, n in enumerate(ns):
+            src = torch.randint(0, n, (3 * n,), generator=gg)
+            eis.append(torch.stack([src, (src + 1 + torch.randint(0, n - 1, (3 * n,), generator=gg)) % n]) + off)
+            bv += [i] * n
+            off += n
+        N = off
+        d = dict(x=torch.randn(N, 8, 6, generator=gg), xdims=torch.randn(N, 2, generator=gg),
+                 xsttype=torch.randint(0, 9, (N,), generator=gg), pos_raw=torch.rand(N, 8, 2, generator=gg) * 100.0,
+                 edge_index=torch.cat(eis, 1), batch=torch.tensor(bv), y=(torch.rand(graphs, 1, generator=gg) > 0.5).float())
+        return SimpleNamespace(**{k: v.to(dev) for k, v in d.items()}, num_graphs=graphs)
+
+    return model, batch
+
+
+@pytest.mark.gpu
+def test_graphed_grusage_training_matches_the_uncaptured_model():
+    """GraphedGruSage (forward + backward CUDA graphs over padded static buffers) against the same model called
+    directly: logits of the real graphs and every parameter gradient, on two batches of different size through one
+    bucket, the larger one first (stale rows beyond N must not matter)."""
+    from sldm_gnn_b200.grusage import GraphedGruSage
+    dev = torch.device("cuda:0")
+    model, batch = _c2_like(dev, dropout=None)
+    crit = torch.nn.BCEWithLogitsLoss()
+    g = GraphedGruSage(model, max_nodes=128, max_edges=512, max_graphs=12, training=True)
+    for graphs, seed in ((11, 1), (5, 2), (8, 3)):
+        data = batch(graphs, seed)
+        model.zero_grad(set_to_none=True)
+        ref_logits = model(data)
+        crit(ref_logits, data.y).backward()
+        ref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        model.zero_grad(set_to_none=True)
+        out = g(data)
+        assert out.shape == ref_logits.shape
+        assert torch.allclose(out, ref_logits, rtol=1e-5, atol=1e-6), float((out - ref_logits).abs().max())
+        crit(out, data.y).backward()
+        got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert set(got) == set(ref)
+        for k in ref:
+            scale = max(1.0, float(ref[k].abs().max()))
+            assert torch.allclose(got[k], ref[k], rtol=1e-4, atol=2e-6 * scale), (k, float((got[k] - ref[k]).abs().max()))
+    with pytest.raises(RuntimeError, match="exceed the bucket"):
+        g(batch(12, 4))
+
+
+@pytest.mark.gpu
+def test_graphed_grusage_inference_and_dropout_training():
+    from sldm_gnn_b200.grusage import GraphedGruSage
+    dev = torch.device("cuda:0")
+    model, batch = _c2_like(dev, dropout=0.25, seed=1)
+    data = batch(6, 7)
+    model.eval()
+    with torch.inference_mode():
+        want = model(data)
+    gi = GraphedGruSage(model, max_nodes=96, max_edges=400, max_graphs=8, training=False)
+    got = gi(data)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), float((got - want).abs().max())
+    # training with dropout: finite, different draws on successive replays, a loss that an optimizer step lowers
+    gt = GraphedGruSage(model, max_nodes=96, max_edges=400, max_graphs=8, training=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    crit = torch.nn.BCEWithLogitsLoss()
+    a, b = gt(data).detach().clone(), gt(data).detach().clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b), "dropout must draw fresh masks on every replay"
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        loss = crit(gt(data), data.y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert sum(losses[-5:]) < sum(losses[:5]), (losses[:5], losses[-5:])
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_follows_the_eager_loop():
+    """GraphedTrainStep (zero_grad + forward + loss + backward + Adam as ONE CUDA graph) against the reference's loop
+    run eagerly on a copy of the model: same first-step gradients, the same loss curve over batches of changing size,
+    and construction leaves parameters and optimizer state untouched."""
+    import copy
+    import torch.nn.functional as Fn
+    from sldm_gnn_b200.grusage import GraphedTrainStep
+    dev = torch.device("cuda:0")
+    model, batch = _c2_like(dev, dropout=None, seed=2)
+    twin = copy.deepcopy(model)
+    pw = torch.tensor(1.5, device=dev)
+    crit = torch.nn.BCEWithLogitsLoss(pos_weight=pw)
+    loss_fn = lambda logits, y, w: Fn.binary_cross_entropy_with_logits(logits, y, weight=w, pos_weight=pw, reduction="sum")
+    opt_e = torch.optim.Adam(twin.parameters(), lr=1e-3, weight_decay=5e-5)
+    opt_g = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-5, capturable=True)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    step = GraphedTrainStep(model, opt_g, loss_fn, max_nodes=128, max_edges=512, max_graphs=12)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k]), f"construction changed {k}"
+    assert all(float(s["step"]) == 0 and not bool(s["exp_avg"].any()) for s in opt_g.state.values())
+    losses_e, losses_g = [], []
+    for i, (graphs, seed) in enumerate(((11, 1), (5, 2), (8, 3), (11, 4), (3, 5), (9, 6))):
+        data = batch(graphs, seed)
+        opt_e.zero_grad()
+        le = crit(twin(data), data.y)
+        le.backward()
+        lg = step(data, data.y)
+        if i == 0:
+            ge = dict(twin.named_parameters())
+            for k, p in model.named_parameters():
+                scale = max(1.0, float(ge[k].grad.abs().max()))
+                assert torch.allclose(p.grad, ge[k].grad, rtol=1e-4, atol=2e-6 * scale), (k, float((p.grad - ge[k].grad).abs().max()))
+        opt_e.step()
+        losses_e.append(float(le)); losses_g.append(float(lg))
+    assert all(abs(a - b) <= 2e-3 * max(1.0, abs(a)) for a, b in zip(losses_e, losses_g)), (losses_e, losses_g)
+    with pytest.raises(ValueError, match="capturable"):
+        GraphedTrainStep(model, torch.optim.Adam(model.parameters()), loss_fn, 128, 512, 12)

@@ -111,7 +111,10 @@ def test_cuda_matches_reference_golden(path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,S,D,K", [(1, 5, 4, 5), (257, 33, 32, 5), (1000, 3000, 32, 5), (64, 2049, 128, 8), (9, 40, 7, 2),
-                                     (300, 5000, 16, 5), (50, 9000, 32, 3)])   # more than 4096 segments: tiled scan
+                                     (300, 5000, 16, 5), (50, 9000, 32, 3),    # more than 4096 segments: tiled scan
+                                     # busy segments (>= 32 selecting positions each) with an embedding width that leaves
+                                     # lanes idle in k_map_attention_demb: D = 8 is the reference's default map width
+                                     (2000, 12, 16, 3), (3000, 7, 8, 5), (1500, 20, 40, 4)])
 def test_cuda_matches_oracle_random(B, S, D, K):
     import sldm_gnn_b200 as sg
     dev = torch.device("cuda:0")
