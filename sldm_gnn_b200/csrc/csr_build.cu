@@ -101,6 +101,12 @@ static int key_bits(int64_t N) {
   while (bits < 31 && ((int64_t)1 << bits) < N) ++bits;
   return bits;
 }
+// 64-bit look-back words are needed from 2^30 keys on; SLDM_CSR_WIDE_STATE=1 forces them for any size (tests: the
+// variant would otherwise only ever run on inputs of 17 GB and more)
+static bool wide_state(int64_t n) {
+  const char* e = getenv("SLDM_CSR_WIDE_STATE");
+  return n >= ((int64_t)1 << 30) || (e && e[0] == '1');
+}
 static SortPlan sort_plan(int64_t N) {
   SortPlan P;
   P.key_bits = key_bits(N);
@@ -558,7 +564,7 @@ static int radix_sort_pairs2(int nsort, const int32_t* const keys0[2], const int
                              const int32_t* sorted_keys_out[2], const int32_t* const unsorted_flag[2], cudaStream_t s) {
   const int64_t ntiles = ceil_div<int64_t>(n, kOsTile);
   const int NB = 1 << P.db;
-  const bool wide = n >= ((int64_t)1 << 30);
+  const bool wide = wide_state(n);
   const int64_t word = wide ? 8 : 4;
   const int32_t* in_k[2] = {keys0[0], keys0[1]};
   const int32_t* in_v[2] = {vals0[0], vals0[1]};
@@ -623,7 +629,7 @@ static CsrWs csr_ws_layout(int64_t N, int64_t E) {
   int64_t e = align_bytes((E > 0 ? E : 1) * 4);
   w.ntiles = ceil_div<int64_t>(E > 0 ? E : 1, kOsTile);
   w.plan = sort_plan(N);
-  w.word = E >= ((int64_t)1 << 30) ? 8 : 4;
+  w.word = wide_state(E) ? 8 : 4;
   w.src32 = o; o += e;  w.dst32 = o; o += e;
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 4; ++j) { w.pp[i][j] = o; o += e; }
   w.state = o; w.state_bytes = 2 * sort_state_bytes(w.ntiles, w.plan, w.word); o += w.state_bytes;

@@ -104,11 +104,13 @@ def test_csr_bit_exact(dev, kind, N, E):
     # look-back: > 64 tiles (a checkpoint tile walks for all digits), few live digits per tile (skipped walks)
     ("one_dst", 1000, 300000), ("low_ids", 70000, 600000),
 ])
-@pytest.mark.parametrize("bits", ["8", "10"])
-def test_csr_bit_exact_digit_widths(dev, monkeypatch, kind, N, E, bits):
-    """The 10-bit-digit variant of the sort kernels (SLDM_CSR_DIGIT_BITS=10; 8 is the default) and the look-back's
-    skip / checkpoint rules give the same unique stable sort."""
+@pytest.mark.parametrize("bits,wide", [("8", "0"), ("10", "0"), ("8", "1"), ("10", "1")])
+def test_csr_bit_exact_digit_widths(dev, monkeypatch, kind, N, E, bits, wide):
+    """The 10-bit-digit variant of the sort kernels (SLDM_CSR_DIGIT_BITS=10; 8 is the default), the 64-bit look-back
+    words that inputs of 2^30 edges and more use (forced here by SLDM_CSR_WIDE_STATE=1) and the look-back's skip /
+    checkpoint rules give the same unique stable sort."""
     monkeypatch.setenv("SLDM_CSR_DIGIT_BITS", bits)
+    monkeypatch.setenv("SLDM_CSR_WIDE_STATE", wide)
     ei = edge_cases(kind, N, E, seed=N + E + 1)
     csr = sg.build_csr(ei.to(dev), N)
     want = csr_oracle(ei, N)
