@@ -584,11 +584,13 @@ def main_ours(args, wl):
         if fwd_only:                           # inference (test.py:136): no autograd graph, nothing saved
             with torch.inference_mode():
                 return blk(x.detach(), ei)
-        ddp.zero_grad()
-        x.grad = None
         if world > 1:
+            ddp.zero_grad()
             ddp.expect_sync(local_weight=b["graphs"])   # buckets leave for the all-reduce as backward finishes them
-        y = ddp(x, ei)
+        else:
+            blk.zero_grad(set_to_none=True)             # one GPU: the reference's own loop (optimizer.zero_grad(), src/utils.py:219)
+        x.grad = None
+        y = (ddp if world > 1 else blk)(x, ei)
         y.backward(b["w"])
         if world > 1:
             ddp.sync_gradients(local_weight=b["graphs"])
