@@ -389,6 +389,7 @@ class GraphedTrainStep:
             with torch.cuda.graph(self._graph):
                 self._loss = one_step()
             torch.cuda.synchronize(dev)
+            self._params, self._grads = params, [p.grad for p in params]   # the graph's static gradient tensors
             with torch.no_grad():                              # undo the warm-up steps, in place (the graph holds the pointers)
                 for p, s in zip(params, saved_p):
                     p.copy_(s)
@@ -416,4 +417,6 @@ class GraphedTrainStep:
                 self._w[:G].fill_(1.0 / max(G, 1))
                 self._w[G:].zero_()
             self._graph.replay()
+            for p, g in zip(self._params, self._grads):        # a zero_grad(set_to_none=True) outside must not hide them
+                p.grad = g
             return self._loss

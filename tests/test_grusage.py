@@ -262,6 +262,7 @@ def test_graphed_train_step_follows_the_eager_loop():
         opt_e.zero_grad()
         le = crit(twin(data), data.y)
         le.backward()
+        opt_g.zero_grad(set_to_none=True)        # a caller's own zero_grad must not detach the graph's gradient tensors
         lg = step(data, data.y)
         if i == 0:
             ge = dict(twin.named_parameters())
