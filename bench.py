@@ -104,7 +104,7 @@ KERNEL_NAMES = {"segment_mean_fwd": "k_segment_rows_lean", "project_ln_act_fwd":
                 "dgrad": "k_split_weights_t + k_sage_tc<NT, MODE_DGRAD>", "wgrad": "k_wgrad_tc<NB> + k_reduce_parts x2",
                 "csr_build": "k_convert + k_digit_hist + k_onesweep_pass x3 + k_rowptr_from_sorted",
                 "layer_backward": "k_ln_bwd_rows + k_sage_tc<NT, MODE_DGRAD> + k_wgrad_tc + k_reduce_parts + k_segment_rows_lean",
-                "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_coef + k_readout_bwd",
+                "readout_mean_max_fwd": "membership CSR build + k_readout_fwd", "readout_bwd": "k_readout_bwd_graph",
                 "map_attention_fwd": "k_map_attention_fwd", "map_attention_bwd": "k_map_attention_bwd + membership CSR + k_map_attention_demb",
                 "collate_32_graphs": "k_concat_chunks x5 + k_collate_edge_index + k_batch_from_ptr (+ host table upload)"}
 # every group that is ONE dominant kernel (the candidates of `roofline`), launches per layer and step
@@ -331,7 +331,7 @@ def widened_groups(sg, x, out, batch_vec, num_graphs, N, s):
     ro = sg.global_mean_max_pool(xo, bv, G)
     dro = torch.randn_like(ro)
     groups["readout_mean_max_fwd"] = (lambda: sg.global_mean_max_pool(out, bv, G), N * Fo * s + G * 2 * Fo * s + 8 * N)
-    groups["readout_bwd"] = (lambda: torch.autograd.grad(ro, xo, dro, retain_graph=True), 2 * N * Fo * s + N * Fo * s + 8 * N)
+    groups["readout_bwd"] = (lambda: torch.autograd.grad(ro, xo, dro, retain_graph=True), N * Fo * s + N * Fo * s + 4 * N)   # x from HBM once (its second sweep hits L2), dx written
     # mini-batch assembly at the reference's DataLoader batch size: 32 device-resident unit graphs with the
     # fields of a pack (x [n,T,6], edge_index, xsttype, xdims, pos_raw, y); timed end to end (host tables + kernels)
     from workloads import unit_map_graphs

@@ -10,9 +10,11 @@
 // The reference path does a host sync (batch.max().item()) and four scatter passes; here the graph segments come
 // from the same device-side CSR machinery as the aggregation (members of graph g = one CSR row, in node order, so an
 // unsorted batch vector is handled too), one CTA per graph streams its rows once for both statistics, and the backward
-// is two streaming kernels (per-graph coefficients, then one pass over the nodes).  No atomics: every result is deterministic.
+// is one kernel, a CTA per graph: a sweep that counts the ties, then a sweep over the same rows (from L2) that writes
+// dx.  No atomics: every result is deterministic.
 //
-// Bound: HBM.  Algorithmic bytes: forward N*F*4 read + G*2F*4 written; backward 2*N*F*4 read + N*F*4 written.
+// Bound: HBM.  Algorithmic bytes: forward N*F*4 read + G*2F*4 written; backward N*F*4 read + N*F*4 written (x a second
+// time from L2).
 #include "common.cuh"
 #include <algorithm>
 #include <math.h>
@@ -202,6 +204,132 @@ k_readout_coef(const float* __restrict__ x, int32_t F, const int32_t* __restrict
   }
 }
 
+// The whole backward of one graph in one CTA: sweep 1 counts the ties per feature (k_readout_coef's walk) and leaves
+// the two coefficient rows in shared memory, sweep 2 walks the same rows again -- ~100 KB per graph, still in L2 --
+// and writes dx.  HBM traffic: x read once, dx written once (the two-kernel version read x twice: 76 + 182 us at the
+// bench shape).  Every node is a member of exactly one CSR row, so every dx row is written exactly once.
+template <bool VEC>
+__global__ void __launch_bounds__(kRoThreads)
+k_readout_bwd_graph(const float* __restrict__ x, int32_t F, const int32_t* __restrict__ ptr,
+                    const int32_t* __restrict__ members, const float* __restrict__ out_max, int64_t ld_max,
+                    const float* __restrict__ dmean, const float* __restrict__ dmax, int64_t ld_d,
+                    float* __restrict__ dx) {
+  extern __shared__ float sm[];                 // [kRoWarps][F] tie counts, then [3][F]: coefA | coefB | max
+  const int g = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int beg = __ldg(ptr + g), end = __ldg(ptr + g + 1);
+  if (end <= beg) return;
+  constexpr int W = VEC ? 4 : 1;
+  if (dmax != nullptr) {
+    for (int c = lane * W; c < F; c += 32 * W) {
+      float mx[4], n[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < W; ++e) mx[e] = __ldg(out_max + (int64_t)g * ld_max + c + e);
+      int i = beg + warp;
+      for (; i + 3 * kRoWarps < end; i += 4 * kRoWarps) {   // four independent rows in flight (counts: order-free)
+        const float* row[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) row[k] = x + (int64_t)__ldg(members + i + k * kRoWarps) * F + c;
+        if (VEC) {
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = ldg4(row[k]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            n[0] += v[k].x == mx[0] ? 1.f : 0.f; n[1] += v[k].y == mx[1] ? 1.f : 0.f;
+            n[2] += v[k].z == mx[2] ? 1.f : 0.f; n[3] += v[k].w == mx[3] ? 1.f : 0.f;
+          }
+        } else {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = __ldg(row[k]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) n[0] += v[k] == mx[0] ? 1.f : 0.f;
+        }
+      }
+      for (; i < end; i += kRoWarps) {
+        const float* row = x + (int64_t)__ldg(members + i) * F + c;
+        if (VEC) {
+          const float4 v = ldg4(row);
+          n[0] += v.x == mx[0] ? 1.f : 0.f; n[1] += v.y == mx[1] ? 1.f : 0.f;
+          n[2] += v.z == mx[2] ? 1.f : 0.f; n[3] += v.w == mx[3] ? 1.f : 0.f;
+        } else {
+          n[0] += __ldg(row) == mx[0] ? 1.f : 0.f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < W; ++e) sm[warp * F + c + e] = n[e];
+    }
+  }
+  __syncthreads();
+  const float fc = (float)(end - beg);
+  float ca[4], cb[4], cm[4];                     // F <= 1024 = 4 columns per thread
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = threadIdx.x + j * kRoThreads;
+    ca[j] = cb[j] = cm[j] = 0.f;
+    if (c < F) {
+      ca[j] = dmean ? __fdiv_rn(__ldg(dmean + (int64_t)g * ld_d + c), fc) : 0.f;
+      if (dmax != nullptr) {
+        float n = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRoWarps; ++w) n += sm[w * F + c];
+        cb[j] = n > 0.f ? __fdiv_rn(__ldg(dmax + (int64_t)g * ld_d + c), n) : 0.f;
+        cm[j] = __ldg(out_max + (int64_t)g * ld_max + c);
+      }
+    }
+  }
+  __syncthreads();                               // the tie counts have been read: reuse the buffer
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = threadIdx.x + j * kRoThreads;
+    if (c < F) { sm[c] = ca[j]; sm[F + c] = cb[j]; sm[2 * F + c] = cm[j]; }
+  }
+  __syncthreads();
+  const bool use_max = dmax != nullptr;
+  int i = beg + warp;
+  if (VEC && use_max) {                          // four rows in flight per warp, like sweep 1
+    for (; i + 3 * kRoWarps < end; i += 4 * kRoWarps) {
+      int64_t id[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) id[k] = __ldg(members + i + k * kRoWarps);
+      for (int c = lane * 4; c < F; c += 128) {
+        float4 xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv[k] = ldg4(x + id[k] * F + c);
+        const float4 a = *reinterpret_cast<const float4*>(sm + c), b = *reinterpret_cast<const float4*>(sm + F + c),
+                     mx = *reinterpret_cast<const float4*>(sm + 2 * F + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4 r = a;
+          r.x += xv[k].x == mx.x ? b.x : 0.f; r.y += xv[k].y == mx.y ? b.y : 0.f;
+          r.z += xv[k].z == mx.z ? b.z : 0.f; r.w += xv[k].w == mx.w ? b.w : 0.f;
+          st4(dx + id[k] * F + c, r);
+        }
+      }
+    }
+  }
+  for (; i < end; i += kRoWarps) {
+    const int64_t id = __ldg(members + i);
+    for (int c = lane * W; c < F; c += 32 * W) {
+      if (VEC) {
+        float4 r = *reinterpret_cast<const float4*>(sm + c);
+        if (use_max) {
+          const float4 xv = ldg4(x + id * F + c);
+          const float4 b = *reinterpret_cast<const float4*>(sm + F + c), mx = *reinterpret_cast<const float4*>(sm + 2 * F + c);
+          r.x += xv.x == mx.x ? b.x : 0.f; r.y += xv.y == mx.y ? b.y : 0.f;
+          r.z += xv.z == mx.z ? b.z : 0.f; r.w += xv.w == mx.w ? b.w : 0.f;
+        }
+        st4(dx + id * F + c, r);
+      } else {
+        float r = sm[c];
+        if (use_max && __ldg(x + id * F + c) == sm[2 * F + c]) r += sm[F + c];
+        dx[id * F + c] = r;
+      }
+    }
+  }
+}
+
 // dx[i,c] = coef[g,c] + (x[i,c] == max[g,c] ? coef[g,F+c] : 0);  one warp per node row, 128-bit accesses when aligned
 template <bool VEC>
 __global__ void __launch_bounds__(256)
@@ -299,6 +427,13 @@ extern "C" int sldm_readout_backward(const float* x, int64_t N, int32_t F, const
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool vec = (F % 4 == 0) && a16(x) && a16(dx) && a16(out_max) && (ld_max % 4 == 0);
   const size_t smem = (size_t)kRoWarps * F * sizeof(float);
+  static const bool fused = [] { const char* e = getenv("SLDM_READOUT_TWO_KERNELS"); return !(e && e[0] == '1'); }();
+  if (fused) {   // one CTA per graph does both sweeps (SLDM_READOUT_TWO_KERNELS=1: the coefficient kernel + the row-parallel kernel)
+    if (vec) k_readout_bwd_graph<true><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_max, ld_max, dmean, dmax, ld_d, dx);
+    else     k_readout_bwd_graph<false><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_max, ld_max, dmean, dmax, ld_d, dx);
+    SLDM_LAUNCH_CHECK("k_readout_bwd_graph");
+    return SLDM_OK;
+  }
   if (vec) k_readout_coef<true><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_max, ld_max, dmean, dmax, ld_d, coef);
   else     k_readout_coef<false><<<(unsigned)G, kRoThreads, smem, s>>>(x, F, ptr, members, out_max, ld_max, dmean, dmax, ld_d, coef);
   SLDM_LAUNCH_CHECK("k_readout_coef");
