@@ -88,7 +88,7 @@ constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
 //   FWD  : nsrc = 2 (agg, x), ngroups = 1, Nout = Fout, Kc = Fin/32
 //   DGRAD: nsrc = 1 (dz),     ngroups = 2 (W_l -> dagg, W_r -> dxroot), Nout = Fin, Kc = Fout/32
 // Weight tiles come from one packed array [4 * Nout][K]: block (2*(g*nsrc+src) + lo) holds the hi / lo part.
-struct TcProblem { int64_t N; int Kc, nsrc, ngroups, Nout; };
+struct TcProblem { int64_t N; int Kc, nsrc, ngroups, Nout; int rev = 0; };   // rev: tiles are walked from the last row block to the first
 
 __global__ void __launch_bounds__(256)
 k_split_weights(const float* __restrict__ W_l, const float* __restrict__ W_r, int count, float* __restrict__ out) {
@@ -141,6 +141,7 @@ struct DrainArgs {
   int64_t N; int Fout; int64_t ntiles; int nchunks; int ngroups; float eps; uint32_t tmem_base; uint32_t zbase;
   float* rstd; const int32_t* rowptr; const float* s_bias; float* s_sum; float* s_var;
   uint64_t* bar_acc_full; uint64_t* bar_acc_empty; uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
+  int64_t tbase; int tstep;      // row block of loop index t = tbase + tstep * t (walk direction)
 };
 
 // Drain role: 16 warps (512 threads).  Thread (quadrant q, lane, column quarter CQ) owns tile row q*32+lane and the
@@ -193,7 +194,7 @@ __device__ __forceinline__ void drain_role(const DrainArgs a) {
         }
       }
       if (tid == 256) TC_TRACE(11, it - 1);
-      const int64_t row = tile * kTcBM + rloc;
+      const int64_t row = (a.tbase + a.tstep * tile) * kTcBM + rloc;
       if constexpr (MODE == MODE_FWD) {
         // ---- bias + LayerNorm statistics; the four column quarters of a row live in warps 8+q, 12+q, 16+q, 20+q.
         //      Each quarter computes its own (sum, M2 about its own mean); ONE exchange through smem on a 128-thread
@@ -287,6 +288,7 @@ struct FinArgs {
   const float* gamma; const float* beta;       // global pointers (FWD)
   const CUtensorMap* tm_s0; const CUtensorMap* tm_s1;   // bulk-store maps, box [32 rows][32 fp32]: FWD xhat | DGRAD dagg, dxroot
   uint64_t* bar_z_full; uint64_t* bar_z_empty; long long* trace;
+  int64_t tbase; int tstep;
 };
 
 // Finisher role: 4 warps, warp q owns rows [32q, 32q+32) of the parked tile.  A row is spread over LPRW = 8*NT lanes
@@ -330,7 +332,7 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
       const bool bulk = (Fout == 32 * NT) && (MODE == MODE_DGRAD);
       if (bulk && lane == 0) {
         const CUtensorMap* tm = (MODE == MODE_FWD) ? a.tm_s0 : (grp == 0 ? a.tm_s0 : a.tm_s1);
-        const int grow0 = (int)(tile * kTcBM) + q * 32;
+        const int grow0 = (int)((a.tbase + a.tstep * tile) * kTcBM) + q * 32;
 #pragma unroll
         for (int sl = 0; sl < NT; ++sl)
           if (sl * 32 < Fout)
@@ -369,7 +371,7 @@ __device__ __forceinline__ void finisher_role(const FinArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int64_t row = tile * kTcBM + rl[u];
+          const int64_t row = (a.tbase + a.tstep * tile) * kTcBM + rl[u];
 #ifdef SLDM_TC_NOSTORE   /* timing experiment only (no results): the finisher issues no global stores */
           if (row < 0 && cvalid) {
 #else
@@ -487,7 +489,7 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
       const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row0 = (int)(tile * kTcBM);
+        const int row0 = (int)((pb.rev ? ntiles - 1 - tile : tile) * kTcBM);
         for (int g = 0; g < ngroups; ++g) {
           for (int c = 0; c < nchunks; ++c, ++it) {
             const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
@@ -688,13 +690,14 @@ k_sage_tc(const __grid_constant__ CUtensorMap tm_agg, const __grid_constant__ CU
     reg_inc<80>();
     // ------------------------------------------------------------------- drain --
     DrainArgs da{N, Fout, ntiles, nchunks, ngroups, eps, tmem_base, smem_u32(smem_z), rstd, rowptr, s_bias,
-                 &s_sum[0][0][0], &s_var[0][0][0], bar_acc_full, bar_acc_empty, bar_z_full, bar_z_empty, trace};
+                 &s_sum[0][0][0], &s_var[0][0][0], bar_acc_full, bar_acc_empty, bar_z_full, bar_z_empty, trace,
+                 pb.rev ? ntiles - 1 : 0, pb.rev ? -1 : 1};
     if (Fout == 32 * NT) drain_role<NT, true, MODE>(da); else drain_role<NT, false, MODE>(da);
   } else {
     reg_dec<56>();
     // ---------------------------------------------------------------- finisher --
     FinArgs fa{N, Fout, ntiles, ngroups, slope, out, xhat, smem_u32(smem_z), gamma, beta, &tm_s0, &tm_s1,
-               bar_z_full, bar_z_empty, trace};
+               bar_z_full, bar_z_empty, trace, pb.rev ? ntiles - 1 : 0, pb.rev ? -1 : 1};
     finisher_role<NT, MODE, ABF>(fa);
   }
   tc_fence_before();
@@ -952,6 +955,16 @@ k_split_weights_t(const float* __restrict__ W_l, const float* __restrict__ W_r, 
   }
 }
 
+// SLDM_TC_REVERSE: bit 0 = the forward projection, bit 1 = DGRAD walk their row blocks from the last to the first, so
+// that the rows the PREVIOUS kernel of the chain wrote last (the tail of agg / dz, still in the 126 MB L2) are read
+// first.  Measured on the batch step (three alternating runs each): forward reversed 3.518 vs 3.542 ms (inference
+// 1.283 vs 1.294), DGRAD reversed 3.574 (worse: k_ln_bwd_rows does not finish with the last rows), both 3.532.
+// Default: the forward only.
+static int tc_reverse_mask() {
+  static const int m = [] { const char* e = getenv("SLDM_TC_REVERSE"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
 template <int NT, int MODE, bool ABF = false>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& ms0,
                      const CUtensorMap& ms1, const TcProblem& pb,
@@ -1022,6 +1035,7 @@ int project_forward_tc_launch(const float* agg, const float* x, int64_t N, int32
   CUtensorMap ms = ma;   // bulk-store map of xhat (training, whole 32-column slabs): [32 rows][32 fp32] boxes out of the parked tile
   if (xhat != nullptr && Fout % 32 == 0 && (rc = make_tmap_2d_f32(&ms, xhat, (uint64_t)N, Fout, Fout, 32, 32))) return rc;
   TcProblem pb{N, Fin / 32, 2, 1, Fout};
+  pb.rev = tc_reverse_mask() & 1;
   return dispatch_tc<MODE_FWD>(ma, mx, mw, ms, ms, pb, b_l, ln_w, ln_b, eps, slope, out, xhat, rstd, nullptr, s);
 }
 
@@ -1073,6 +1087,7 @@ int dgrad_tc_launch(const float* dz, int64_t N, int32_t Fin, int32_t Fout, const
     if ((rc = make_tmap_2d_f32(&ms1, dxroot, (uint64_t)N, Fin, Fin, 32, 32))) return rc;
   }
   TcProblem pb{N, Fout / 32, 1, 2, Fin};
+  pb.rev = (tc_reverse_mask() >> 1) & 1;
   return dispatch_tc<MODE_DGRAD>(mz, mz, mw, ms0, ms1, pb, nullptr, nullptr, nullptr, 0.f, 0.f, dagg, dxroot, nullptr, rowptr_dst, s);
 }
 
